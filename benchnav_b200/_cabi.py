@@ -1,0 +1,111 @@
+"""ctypes binding of libbnvmppi.so -- the C ABI declared in ``include/bnv_mppi.h``.
+
+This is the stub a maintainer of the reference would add to call the engine from Python (see
+INTEGRATION.md).  Nothing here touches PyTorch: pointers are plain integers (``tensor.data_ptr()``)
+and the stream is a ``cudaStream_t`` integer.  Loading fails loudly if the library is missing --
+there is no CPU fallback.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+from typing import List
+
+from . import build as _build
+
+BNV_OK = 0
+BNV_FLAG_RECORD_STATES = 0x1
+ABI_VERSION = 1
+
+
+class BnvError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libbnvmppi error {code}: {msg}")
+        self.code = code
+
+
+class MppiCfg(C.Structure):
+    """Mirror of ``bnv_mppi_cfg`` (include/bnv_mppi.h)."""
+
+    _fields_ = [
+        ("num_samples", C.c_int32),
+        ("horizon", C.c_int32),
+        ("sigma", C.c_float * 2),
+        ("lambda_", C.c_float),
+        ("u_min", C.c_float * 2),
+        ("u_max", C.c_float * 2),
+        ("dt", C.c_float),
+        ("seed", C.c_uint64),
+        ("rank", C.c_int32),
+        ("world_size", C.c_int32),
+        ("device", C.c_int32),
+        ("flags", C.c_uint32),
+    ]
+
+
+_VP = C.c_void_p
+_SIGNATURES = {
+    "bnv_abi_version": (C.c_int, []),
+    "bnv_last_error": (C.c_char_p, []),
+    "bnv_mppi_create": (C.c_int, [C.POINTER(_VP), C.POINTER(MppiCfg)]),
+    "bnv_mppi_destroy": (None, [_VP]),
+    "bnv_mppi_set_problem": (C.c_int, [_VP, _VP, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float,
+                                       C.c_float, C.POINTER(C.c_float), C.c_float, _VP]),
+    "bnv_mppi_forward": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP]),
+    "bnv_mppi_forward_host": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP]),
+    "bnv_mppi_partial": (_VP, [_VP]),
+    "bnv_mppi_partial_len": (C.c_int32, [_VP]),
+    "bnv_mppi_finalize": (C.c_int, [_VP, _VP, _VP, _VP, _VP]),
+    "bnv_mppi_top_samples": (C.c_int, [_VP, C.c_int32, _VP, _VP, _VP]),
+    "bnv_mppi_weights": (_VP, [_VP]),
+    "bnv_mppi_costs": (_VP, [_VP]),
+    "bnv_mppi_states": (_VP, [_VP]),
+    "bnv_mppi_noise": (_VP, [_VP]),
+    "bnv_mppi_u_prev": (_VP, [_VP]),
+    "bnv_mppi_local_samples": (C.c_int32, [_VP]),
+    "bnv_mppi_sample_offset": (C.c_int32, [_VP]),
+    "bnv_mppi_reset": (C.c_int, [_VP, _VP]),
+    "bnv_mppi_launch_count": (C.c_uint64, [_VP]),
+    "bnv_mppi_kernel_timing": (C.c_int, [_VP, C.c_int32]),
+    "bnv_mppi_kernel_time": (C.c_int, [_VP, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+    "bnv_debug_sincos": (C.c_int, [_VP, _VP, _VP, C.c_int32, _VP]),
+}
+
+_lib = None
+
+
+def header_path() -> str:
+    return os.path.join(_build.INCLUDE, "bnv_mppi.h")
+
+
+def declared_symbols() -> List[str]:
+    """Every function name declared in include/bnv_mppi.h (used by the export test)."""
+    text = open(header_path()).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(bnv_[a-z0-9_]+)\s*\(", text)))
+
+
+def load() -> C.CDLL:
+    """Load (building first if stale and nvcc is available) and type the library."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.ensure_built()
+    if not os.path.exists(path):
+        raise ImportError(f"{path} is missing: build it with `python -m benchnav_b200.build` (needs nvcc)")
+    lib = C.CDLL(path)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.bnv_abi_version() != ABI_VERSION:
+        raise ImportError(f"ABI mismatch: library {lib.bnv_abi_version()} vs binding {ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def check(code: int) -> None:
+    if code != BNV_OK:
+        raise BnvError(code, load().bnv_last_error().decode("utf-8", "replace"))

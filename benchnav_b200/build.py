@@ -1,0 +1,79 @@
+"""In-tree build of libbnvmppi.so (the C-ABI CUDA library) for sm_100a with nvcc.
+
+The library has no PyTorch dependency: it is compiled straight from ``csrc/*.cu`` and loaded with
+ctypes (``_cabi.py``).  The built ``.so`` is git-ignored but travels to the GPU box with the repo
+snapshot.  ``python -m benchnav_b200.build`` rebuilds it; ``ensure_built()`` rebuilds only when a
+source is newer than the library.
+"""
+
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(PKG_DIR, "csrc")
+INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
+LIB_DIR = os.path.join(PKG_DIR, "lib")
+LIB_PATH = os.path.join(LIB_DIR, "libbnvmppi.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo",
+    "-Xcompiler", "-fPIC", "-shared",
+    "-cudart", "static",
+    "-Xptxas", "-v",
+]
+
+
+def _sources():
+    srcs = [os.path.join(CSRC, "bnv_mppi.cu")]
+    deps = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(INCLUDE, "bnv_mppi.h")]
+    return srcs, deps
+
+
+def nvcc_path() -> str:
+    exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(exe):
+        raise RuntimeError("nvcc not found: libbnvmppi.so cannot be built")
+    return exe
+
+
+def is_stale() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    _, deps = _sources()
+    lib_m = os.path.getmtime(LIB_PATH)
+    return any(os.path.getmtime(d) > lib_m for d in deps)
+
+
+def build_library(verbose: bool = False) -> str:
+    srcs, _ = _sources()
+    os.makedirs(LIB_DIR, exist_ok=True)
+    cmd = [nvcc_path(), *NVCC_FLAGS, "-I", INCLUDE, "-I", CSRC, "-o", LIB_PATH, *srcs]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+    log = proc.stdout + proc.stderr
+    with open(os.path.join(LIB_DIR, "build.log"), "w") as f:
+        f.write(" ".join(cmd) + "\n" + log)
+    if verbose:
+        print(log)
+    return LIB_PATH
+
+
+def ensure_built() -> str:
+    """Build if missing or stale and nvcc is present; otherwise return the existing library path."""
+    if is_stale():
+        try:
+            build_library()
+        except RuntimeError:
+            if not os.path.exists(LIB_PATH):
+                raise
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build_library(verbose="-v" in sys.argv))

@@ -1,0 +1,480 @@
+// libbnvmppi.so -- host side of the C ABI declared in include/bnv_mppi.h.
+// Owns the solver handle (device buffers, TMA descriptor, launch geometry) and launches the sm_100a
+// kernels of mppi_kernels.cuh.  No PyTorch types anywhere: callers pass raw device pointers and a stream.
+#include "../../include/bnv_mppi.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "mppi_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define BNV_CUDA(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t e__ = (expr);                                                                       \
+    if (e__ != cudaSuccess)                                                                         \
+      return fail(BNV_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+constexpr size_t kMaxDynSmem = 200 * 1024;   // leave headroom below the 227 KB per-CTA limit
+constexpr int kMaxPatchBytes = 64 * 1024;    // larger reach windows are looked up in the global map (L2)
+
+bool is_pow2_float(float v) {
+  int e;
+  return v > 0.0f && std::isfinite(v) && std::frexp(v, &e) == 0.5f;
+}
+
+}  // namespace
+
+struct bnv_mppi {
+  bnv_mppi_cfg cfg{};
+  int Kl = 0, k_offset = 0;
+  bool problem_set = false, have_weights = false;
+  uint64_t iteration = 0, launches = 0;
+  bnv::EngineParams P{};
+  // owned device buffers
+  float* tau = nullptr;
+  float* noise = nullptr;
+  float* rec = nullptr;
+  float* costs = nullptr;
+  float* weights = nullptr;
+  float* u_prev = nullptr;
+  float* part_ms = nullptr;
+  float* part_u = nullptr;
+  float* shard_partial = nullptr;
+  float* io_dev = nullptr;  // [3] state + [2T] u_out + [3(T+1)] opt states, staging for forward_host
+  unsigned int* ticket = nullptr;
+  int* top_idx = nullptr;
+  unsigned long long* top_pairs = nullptr;
+  size_t top_pairs_cap = 0, top_idx_cap = 0;
+  float* io_host = nullptr;  // pinned mirror of io_dev
+  int grid = 0;
+  size_t rollout_smem = 0, finalize_smem = 0;
+  // optional CUDA-event timing of the rollout kernel alone (bench.py's roofline)
+  bool timing = false;
+  std::vector<cudaEvent_t> ev;  // pairs: [2i] before, [2i+1] after the rollout kernel
+  size_t ev_used = 0;
+};
+
+namespace {
+
+void free_all(bnv_mppi* h) {
+  cudaFree(h->tau);
+  cudaFree(h->noise);
+  cudaFree(h->rec);
+  cudaFree(h->costs);
+  cudaFree(h->weights);
+  cudaFree(h->u_prev);
+  cudaFree(h->part_ms);
+  cudaFree(h->part_u);
+  cudaFree(h->shard_partial);
+  cudaFree(h->io_dev);
+  cudaFree(h->ticket);
+  cudaFree(h->top_idx);
+  cudaFree(h->top_pairs);
+  for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+  if (h->io_host) cudaFreeHost(h->io_host);
+}
+
+// Choose warps per CTA so that noise + recorded-state slabs fit shared memory; prefer 4 (one per SM sub-partition).
+int configure_launch(bnv_mppi* h) {
+  bnv::EngineParams& P = h->P;
+  for (int w = bnv::kMaxWarps; w >= 1; w >>= 1) {
+    bnv::RolloutSmem L = bnv::rollout_smem_layout(P.T, w, P.patch_w, P.patch_h, P.use_patch, P.record);
+    if (static_cast<size_t>(L.total) <= kMaxDynSmem) {
+      P.warps = w;
+      h->rollout_smem = L.total;
+      h->grid = (h->Kl + w * 32 - 1) / (w * 32);
+      return BNV_OK;
+    }
+  }
+  return fail(BNV_ERR_UNSUPPORTED, "horizon %d does not fit the rollout kernel's shared-memory staging", P.T);
+}
+
+}  // namespace
+
+extern "C" {
+
+int bnv_abi_version(void) { return BNV_ABI_VERSION; }
+const char* bnv_last_error(void) { return g_last_error.c_str(); }
+
+int bnv_mppi_create(bnv_mppi** out, const bnv_mppi_cfg* cfg) {
+  if (!out || !cfg) return fail(BNV_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (cfg->num_samples < 1 || cfg->horizon < 1) return fail(BNV_ERR_INVALID, "num_samples and horizon must be >= 1");
+  if (cfg->world_size < 1 || cfg->rank < 0 || cfg->rank >= cfg->world_size)
+    return fail(BNV_ERR_INVALID, "rank %d / world_size %d invalid", cfg->rank, cfg->world_size);
+  if (!(cfg->sigma[0] > 0.0f) || !(cfg->sigma[1] > 0.0f)) return fail(BNV_ERR_INVALID, "sigmas must be positive");
+  if (!(cfg->lambda_ > 0.0f)) return fail(BNV_ERR_INVALID, "lambda_ must be positive");
+  if (!(cfg->u_min[0] <= cfg->u_max[0]) || !(cfg->u_min[1] <= cfg->u_max[1]))
+    return fail(BNV_ERR_INVALID, "u_min must not exceed u_max");
+  if (!(cfg->dt > 0.0f)) return fail(BNV_ERR_INVALID, "dt must be positive");
+  if (cfg->num_samples < cfg->world_size) return fail(BNV_ERR_INVALID, "fewer samples than shards");
+  BNV_CUDA(cudaSetDevice(cfg->device));
+  int major = 0;
+  BNV_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, cfg->device));
+  if (major != 10) return fail(BNV_ERR_UNSUPPORTED, "device %d is sm_%dx; this library is built for sm_100a only", cfg->device, major);
+
+  bnv_mppi* h = new (std::nothrow) bnv_mppi();
+  if (!h) return fail(BNV_ERR_INVALID, "out of host memory");
+  h->cfg = *cfg;
+  const long long K = cfg->num_samples, W = cfg->world_size, r = cfg->rank;
+  h->k_offset = static_cast<int>(r * K / W);  // shard = global samples [r K / W, (r+1) K / W)
+  h->Kl = static_cast<int>((r + 1) * K / W) - h->k_offset;
+  const int T = cfg->horizon, Kl = h->Kl;
+  const bool record = (cfg->flags & BNV_FLAG_RECORD_STATES) != 0;
+  const size_t io_floats = 3 + 2 * static_cast<size_t>(T) + 3 * static_cast<size_t>(T + 1);
+  cudaError_t e = cudaSuccess;
+  auto alloc = [&](void** p, size_t bytes) {
+    if (e == cudaSuccess) e = cudaMalloc(p, bytes);
+  };
+  const int max_grid = (Kl + 31) / 32;
+  alloc(reinterpret_cast<void**>(&h->noise), sizeof(float) * Kl * T * 2);
+  if (record) alloc(reinterpret_cast<void**>(&h->rec), sizeof(float) * Kl * (T + 1) * 3);
+  alloc(reinterpret_cast<void**>(&h->costs), sizeof(float) * Kl);
+  alloc(reinterpret_cast<void**>(&h->weights), sizeof(float) * Kl);
+  alloc(reinterpret_cast<void**>(&h->u_prev), sizeof(float) * T * 2);
+  alloc(reinterpret_cast<void**>(&h->part_ms), sizeof(float) * max_grid * 2);
+  alloc(reinterpret_cast<void**>(&h->part_u), sizeof(float) * max_grid * 2 * T);
+  alloc(reinterpret_cast<void**>(&h->shard_partial), sizeof(float) * (2 + 2 * T));
+  alloc(reinterpret_cast<void**>(&h->io_dev), sizeof(float) * io_floats);
+  alloc(reinterpret_cast<void**>(&h->ticket), sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&h->io_host), sizeof(float) * io_floats);
+  if (e == cudaSuccess) e = cudaMemset(h->u_prev, 0, sizeof(float) * T * 2);  // mppi.py:116
+  if (e == cudaSuccess) e = cudaMemset(h->ticket, 0, sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMemset(h->weights, 0, sizeof(float) * Kl);    // mppi.py:126-128
+  if (e == cudaSuccess && record) e = cudaMemset(h->rec, 0, sizeof(float) * Kl * (T + 1) * 3);  // mppi.py:119-125
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    free_all(h);
+    delete h;
+    return fail(BNV_ERR_CUDA, "allocating solver buffers failed: %s", cudaGetErrorString(e));
+  }
+  bnv::EngineParams& P = h->P;
+  P.bounds = {cfg->u_min[0], cfg->u_min[1], cfg->u_max[0], cfg->u_max[1], cfg->dt};
+  P.lambda = cfg->lambda_;
+  P.icov0 = 1.0f / (cfg->sigma[0] * cfg->sigma[0]);  // inverse of diag(sigma^2), mppi.py:94-97
+  P.icov1 = 1.0f / (cfg->sigma[1] * cfg->sigma[1]);
+  P.Kl = Kl;
+  P.T = T;
+  P.world = cfg->world_size;
+  P.record = record ? 1 : 0;
+  P.noise = h->noise;
+  P.u_prev = h->u_prev;
+  P.rec = h->rec;
+  P.costs = h->costs;
+  P.weights = h->weights;
+  P.part_ms = h->part_ms;
+  P.part_u = h->part_u;
+  P.shard_partial = h->shard_partial;
+  P.ticket = h->ticket;
+  *out = h;
+  return BNV_OK;
+}
+
+void bnv_mppi_destroy(bnv_mppi* h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  cudaDeviceSynchronize();
+  free_all(h);
+  delete h;
+}
+
+int bnv_mppi_set_problem(bnv_mppi* h, const float* risk_dev, int32_t grid_size, int32_t pitch, float resolution,
+                         float x_min, float x_max, float y_min, float y_max, const float goal_xy[2],
+                         float stuck_threshold, void* stream) {
+  if (!h || !risk_dev || !goal_xy) return fail(BNV_ERR_INVALID, "null argument");
+  if (grid_size < 1 || pitch < grid_size) return fail(BNV_ERR_INVALID, "grid_size %d / pitch %d invalid", grid_size, pitch);
+  if (!(resolution > 0.0f)) return fail(BNV_ERR_INVALID, "resolution must be positive");
+  if (!(x_min < x_max) || !(y_min < y_max)) return fail(BNV_ERR_INVALID, "empty map limits");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  BNV_CUDA(cudaSetDevice(h->cfg.device));
+  bnv::EngineParams& P = h->P;
+  const int G = grid_size;
+  const int tpitch = (G + 3) & ~3;  // TMA needs a row stride that is a multiple of 16 bytes
+  if (!h->tau || P.G != G) {
+    if (h->tau) {
+      BNV_CUDA(cudaStreamSynchronize(s));
+      BNV_CUDA(cudaFree(h->tau));
+      h->tau = nullptr;
+    }
+    BNV_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->tau), sizeof(float) * static_cast<size_t>(G) * tpitch));
+  }
+  dim3 grid((tpitch + 127) / 128, G);
+  bnv::trav_map_kernel<<<grid, 128, 0, s>>>(risk_dev, pitch, h->tau, tpitch, G);
+  BNV_CUDA(cudaGetLastError());
+  h->launches++;
+
+  P.tau = h->tau;
+  P.G = G;
+  P.pitch = tpitch;
+  P.geom.x_min = x_min;
+  P.geom.y_min = y_min;
+  P.geom.x_max = x_max;
+  P.geom.y_max = y_max;
+  P.geom.res = resolution;
+  P.geom.inv_res = 1.0f / resolution;
+  P.geom.res_pow2 = is_pow2_float(resolution) ? 1 : 0;
+  P.goal_x = goal_xy[0];
+  P.goal_y = goal_xy[1];
+  P.thr = stuck_threshold;
+
+  // Reach bound: tau <= 1 and |v| <= vmax, so a rollout moves at most T * vmax * dt from the (clamped) start.
+  const float vmax = std::max(std::fabs(h->cfg.u_min[0]), std::fabs(h->cfg.u_max[0]));
+  const double reach_cells = static_cast<double>(P.T) * vmax * h->cfg.dt / resolution;
+  const long long rho = static_cast<long long>(std::floor(reach_cells)) + 2;
+  const long long side = 2 * rho + 1;
+  const long long pw = (side + 3) & ~3LL;
+  P.use_patch = (pw <= 256 && side <= 256 && pw * side * 4 <= kMaxPatchBytes) ? 1 : 0;
+  if (P.use_patch) {
+    P.rho = static_cast<int>(rho);
+    P.patch_w = static_cast<int>(pw);
+    P.patch_h = static_cast<int>(side);
+    EncodeTiledFn enc = get_encode_tiled();
+    if (!enc) return fail(BNV_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(G), static_cast<cuuint64_t>(G)};
+    cuuint64_t gstride[1] = {static_cast<cuuint64_t>(tpitch) * sizeof(float)};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(P.patch_w), static_cast<cuuint32_t>(P.patch_h)};
+    cuuint32_t estride[2] = {1, 1};
+    CUresult r = enc(&P.tau_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, h->tau, gdim, gstride, box, estride,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(BNV_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+  } else {
+    P.rho = 0;
+    P.patch_w = P.patch_h = 0;
+    std::memset(&P.tau_map, 0, sizeof(P.tau_map));
+  }
+  int rc = configure_launch(h);
+  if (rc != BNV_OK) return rc;
+  h->finalize_smem = 128 + (P.use_patch ? ((P.patch_w * P.patch_h + 31) / 32) * 32 * 4 : 0) + 2 * P.T * 4 + 16;
+  BNV_CUDA(cudaFuncSetAttribute(bnv::rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(h->rollout_smem)));
+  BNV_CUDA(cudaFuncSetAttribute(bnv::finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(h->finalize_smem)));
+  h->problem_set = true;
+  return BNV_OK;
+}
+
+static int launch_forward(bnv_mppi* h, const float* state_dev, const float* noise_dev, float* u_out_dev,
+                          float* opt_states_dev, cudaStream_t s) {
+  bnv::EngineParams P = h->P;
+  const int T = P.T;
+  if (!noise_dev) {
+    const long long work = static_cast<long long>(h->Kl) * ((T + 1) / 2);
+    const int blocks = static_cast<int>((work + 255) / 256);
+    bnv::noise_kernel<<<blocks, 256, 0, s>>>(h->noise, h->Kl, T, h->k_offset, static_cast<uint32_t>(h->cfg.seed),
+                                             static_cast<uint32_t>(h->cfg.seed >> 32),
+                                             static_cast<uint32_t>(h->iteration),
+                                             static_cast<uint32_t>(h->iteration >> 32), h->cfg.sigma[0],
+                                             h->cfg.sigma[1]);
+    BNV_CUDA(cudaGetLastError());
+    h->launches++;
+    P.noise = h->noise;
+  } else {
+    P.noise = noise_dev;
+  }
+  P.noise_bulk_ok = (reinterpret_cast<uintptr_t>(P.noise) & 15u) == 0 ? 1 : 0;
+  P.rec_bulk_ok = (reinterpret_cast<uintptr_t>(P.rec) & 15u) == 0 ? 1 : 0;
+  P.state = state_dev;
+  h->P.state = state_dev;  // finalize (world_size > 1) re-reads the state of the iteration in flight
+  P.u_out = u_out_dev;
+  P.opt_rec = opt_states_dev;
+  const bool timed = h->timing && h->ev_used + 2 <= h->ev.size();
+  if (timed) BNV_CUDA(cudaEventRecord(h->ev[h->ev_used], s));
+  bnv::rollout_kernel<<<h->grid, P.warps * 32, h->rollout_smem, s>>>(P);
+  BNV_CUDA(cudaGetLastError());
+  if (timed) {
+    BNV_CUDA(cudaEventRecord(h->ev[h->ev_used + 1], s));
+    h->ev_used += 2;
+  }
+  h->launches++;
+  h->iteration++;
+  h->have_weights = (P.world == 1);
+  return BNV_OK;
+}
+
+int bnv_mppi_forward(bnv_mppi* h, const float* state_dev, const float* noise_dev, float* u_out_dev,
+                     float* opt_states_dev, void* stream) {
+  if (!h || !state_dev) return fail(BNV_ERR_INVALID, "null argument");
+  if (!h->problem_set) return fail(BNV_ERR_STATE, "bnv_mppi_set_problem must be called before forward");
+  if (h->cfg.world_size == 1 && (!u_out_dev || !opt_states_dev)) return fail(BNV_ERR_INVALID, "null output buffer");
+  BNV_CUDA(cudaSetDevice(h->cfg.device));
+  return launch_forward(h, state_dev, noise_dev, u_out_dev, opt_states_dev, static_cast<cudaStream_t>(stream));
+}
+
+int bnv_mppi_forward_host(bnv_mppi* h, const float state_host[3], const float* noise_dev, float* u_out_host,
+                          float* opt_states_host, void* stream) {
+  if (!h || !state_host || !u_out_host || !opt_states_host) return fail(BNV_ERR_INVALID, "null argument");
+  if (!h->problem_set) return fail(BNV_ERR_STATE, "bnv_mppi_set_problem must be called before forward");
+  if (h->cfg.world_size != 1) return fail(BNV_ERR_INVALID, "forward_host needs world_size == 1");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  BNV_CUDA(cudaSetDevice(h->cfg.device));
+  const int T = h->P.T;
+  const size_t n_out = 2 * static_cast<size_t>(T) + 3 * static_cast<size_t>(T + 1);
+  std::memcpy(h->io_host, state_host, 3 * sizeof(float));
+  BNV_CUDA(cudaMemcpyAsync(h->io_dev, h->io_host, 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+  int rc = launch_forward(h, h->io_dev, noise_dev, h->io_dev + 3, h->io_dev + 3 + 2 * T, s);
+  if (rc != BNV_OK) return rc;
+  BNV_CUDA(cudaMemcpyAsync(h->io_host + 3, h->io_dev + 3, n_out * sizeof(float), cudaMemcpyDeviceToHost, s));
+  BNV_CUDA(cudaStreamSynchronize(s));
+  std::memcpy(u_out_host, h->io_host + 3, 2 * static_cast<size_t>(T) * sizeof(float));
+  std::memcpy(opt_states_host, h->io_host + 3 + 2 * T, 3 * static_cast<size_t>(T + 1) * sizeof(float));
+  return BNV_OK;
+}
+
+const float* bnv_mppi_partial(const bnv_mppi* h) { return h ? h->shard_partial : nullptr; }
+int32_t bnv_mppi_partial_len(const bnv_mppi* h) { return h ? 2 + 2 * h->P.T : 0; }
+
+int bnv_mppi_finalize(bnv_mppi* h, const float* gathered_partials_dev, float* u_out_dev, float* opt_states_dev,
+                      void* stream) {
+  if (!h || !gathered_partials_dev || !u_out_dev || !opt_states_dev) return fail(BNV_ERR_INVALID, "null argument");
+  if (!h->problem_set || h->iteration == 0) return fail(BNV_ERR_STATE, "finalize needs a preceding forward");
+  if (!h->P.state) return fail(BNV_ERR_STATE, "finalize needs a preceding forward");
+  BNV_CUDA(cudaSetDevice(h->cfg.device));
+  bnv::EngineParams P = h->P;
+  P.u_out = u_out_dev;
+  P.opt_rec = opt_states_dev;
+  bnv::finalize_kernel<<<1, bnv::kFinalizeThreads, h->finalize_smem, static_cast<cudaStream_t>(stream)>>>(
+      P, gathered_partials_dev);
+  BNV_CUDA(cudaGetLastError());
+  h->launches++;
+  h->have_weights = true;
+  return BNV_OK;
+}
+
+int bnv_mppi_top_samples(bnv_mppi* h, int32_t n, float* states_out_dev, float* weights_out_dev, void* stream) {
+  if (!h || !states_out_dev || !weights_out_dev) return fail(BNV_ERR_INVALID, "null argument");
+  if (!h->P.record) return fail(BNV_ERR_STATE, "top_samples needs BNV_FLAG_RECORD_STATES");
+  if (!h->have_weights) return fail(BNV_ERR_STATE, "top_samples needs a completed forward");
+  if (n < 1 || n > h->Kl) return fail(BNV_ERR_INVALID, "num_samples %d outside [1, %d]", n, h->Kl);  // mppi.py:229
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  BNV_CUDA(cudaSetDevice(h->cfg.device));
+  int n_pad = 1;
+  while (n_pad < n) n_pad <<= 1;
+  if (h->top_idx_cap < static_cast<size_t>(n)) {
+    BNV_CUDA(cudaStreamSynchronize(s));
+    if (h->top_idx) BNV_CUDA(cudaFree(h->top_idx));
+    h->top_idx = nullptr;
+    BNV_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->top_idx), sizeof(int) * n));
+    h->top_idx_cap = n;
+  }
+  unsigned long long* pairs_global = nullptr;
+  size_t smem = static_cast<size_t>(n_pad) * 8;
+  if (n_pad > bnv::kTopnSmemPairs) {
+    if (h->top_pairs_cap < static_cast<size_t>(n_pad)) {
+      BNV_CUDA(cudaStreamSynchronize(s));
+      if (h->top_pairs) BNV_CUDA(cudaFree(h->top_pairs));
+      h->top_pairs = nullptr;
+      BNV_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->top_pairs), sizeof(unsigned long long) * n_pad));
+      h->top_pairs_cap = n_pad;
+    }
+    pairs_global = h->top_pairs;
+    smem = 0;
+  }
+  BNV_CUDA(cudaFuncSetAttribute(bnv::topn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                bnv::kTopnSmemPairs * 8));
+  bnv::topn_select_kernel<<<1, bnv::kTopnThreads, smem, s>>>(h->weights, h->Kl, n, n_pad, pairs_global,
+                                                              weights_out_dev, h->top_idx);
+  BNV_CUDA(cudaGetLastError());
+  bnv::gather_rows_kernel<<<n, 128, 0, s>>>(h->rec, h->top_idx, 3 * (h->P.T + 1), states_out_dev);
+  BNV_CUDA(cudaGetLastError());
+  h->launches += 2;
+  return BNV_OK;
+}
+
+float* bnv_mppi_weights(bnv_mppi* h) { return h ? h->weights : nullptr; }
+float* bnv_mppi_costs(bnv_mppi* h) { return h ? h->costs : nullptr; }
+float* bnv_mppi_states(bnv_mppi* h) { return h ? h->rec : nullptr; }
+float* bnv_mppi_noise(bnv_mppi* h) { return h ? h->noise : nullptr; }
+float* bnv_mppi_u_prev(bnv_mppi* h) { return h ? h->u_prev : nullptr; }
+int32_t bnv_mppi_local_samples(const bnv_mppi* h) { return h ? h->Kl : 0; }
+int32_t bnv_mppi_sample_offset(const bnv_mppi* h) { return h ? h->k_offset : 0; }
+
+int bnv_mppi_reset(bnv_mppi* h, void* stream) {
+  if (!h) return fail(BNV_ERR_INVALID, "null argument");
+  BNV_CUDA(cudaSetDevice(h->cfg.device));
+  BNV_CUDA(cudaMemsetAsync(h->u_prev, 0, sizeof(float) * h->P.T * 2, static_cast<cudaStream_t>(stream)));
+  h->iteration = 0;
+  h->have_weights = false;
+  return BNV_OK;
+}
+
+uint64_t bnv_mppi_launch_count(const bnv_mppi* h) { return h ? h->launches : 0; }
+
+int bnv_mppi_kernel_timing(bnv_mppi* h, int32_t max_launches) {
+  if (!h || max_launches < 0) return fail(BNV_ERR_INVALID, "bad argument");
+  BNV_CUDA(cudaSetDevice(h->cfg.device));
+  while (h->ev.size() < 2 * static_cast<size_t>(max_launches)) {
+    cudaEvent_t e;
+    BNV_CUDA(cudaEventCreate(&e));
+    h->ev.push_back(e);
+  }
+  h->timing = max_launches > 0;
+  h->ev_used = 0;
+  return BNV_OK;
+}
+
+int bnv_mppi_kernel_time(bnv_mppi* h, double* total_ms, uint64_t* launches) {
+  if (!h || !total_ms || !launches) return fail(BNV_ERR_INVALID, "null argument");
+  BNV_CUDA(cudaSetDevice(h->cfg.device));
+  double sum = 0.0;
+  for (size_t i = 0; i + 1 < h->ev_used; i += 2) {
+    float ms = 0.0f;
+    BNV_CUDA(cudaEventSynchronize(h->ev[i + 1]));
+    BNV_CUDA(cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]));
+    sum += ms;
+  }
+  *total_ms = sum;
+  *launches = h->ev_used / 2;
+  h->ev_used = 0;
+  return BNV_OK;
+}
+
+int bnv_debug_sincos(const float* theta_dev, float* sin_dev, float* cos_dev, int32_t n, void* stream) {
+  if (!theta_dev || !sin_dev || !cos_dev || n < 0) return fail(BNV_ERR_INVALID, "bad argument");
+  if (n == 0) return BNV_OK;
+  bnv::sincos_debug_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(theta_dev, sin_dev, cos_dev, n);
+  BNV_CUDA(cudaGetLastError());
+  return BNV_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,74 @@
+"""Sample-sharding plumbing for the multi-GPU path.
+
+Samples are split over ranks by global index; the map, state and mean sequence are replicated.  The only
+exchange per control iteration is an all-gather of each shard's softmax partial ``(m, s, U[T,2])``
+(2 + 2T floats); every rank then performs the same log-sum-exp merge inside ``bnv_mppi_finalize``.
+``torch.distributed`` (NCCL on GPUs, gloo in the CPU tests) is the transport; nothing here computes.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(num_samples: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Global sample interval [begin, end) owned by ``rank`` -- same formula as bnv_mppi_create()."""
+    if world_size < 1 or not (0 <= rank < world_size):
+        raise ValueError(f"rank {rank} / world_size {world_size} invalid")
+    if num_samples < world_size:
+        raise ValueError("fewer samples than shards")
+    return rank * num_samples // world_size, (rank + 1) * num_samples // world_size
+
+
+@dataclass
+class ShardInfo:
+    rank: int = 0
+    world_size: int = 1
+    group: Optional[object] = None
+
+    @classmethod
+    def from_group(cls, group) -> "ShardInfo":
+        """``None`` means a single, unsharded solver even if torch.distributed happens to be initialised."""
+        if group is None:
+            return cls()
+        if not dist.is_available() or not dist.is_initialized():
+            raise RuntimeError("process_group given but torch.distributed is not initialised")
+        return cls(rank=dist.get_rank(group), world_size=dist.get_world_size(group), group=group)
+
+
+def gather_shard_partials(partial: torch.Tensor, gathered: torch.Tensor, shard: ShardInfo) -> torch.Tensor:
+    """All-gather the per-shard ``(m, s, U)`` vectors into ``gathered`` [world, 2+2T] (rank-major)."""
+    if shard.world_size == 1:
+        gathered.copy_(partial.view(1, -1))
+        return gathered
+    if gathered.is_cuda:
+        dist.all_gather_into_tensor(gathered, partial, group=shard.group)
+    else:  # gloo
+        parts = [gathered[r] for r in range(shard.world_size)]
+        dist.all_gather(parts, partial, group=shard.group)
+    return gathered
+
+
+def merge_top_candidates(states: torch.Tensor, weights: torch.Tensor, n: int, shard: ShardInfo
+                         ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Global top-n from per-shard top lists (each already sorted descending); off the critical path."""
+    w = shard.world_size
+    n_local = torch.tensor([weights.shape[0]], device=weights.device, dtype=torch.int64)
+    sizes = [torch.zeros_like(n_local) for _ in range(w)]
+    dist.all_gather(sizes, n_local, group=shard.group)
+    cap = int(max(int(s.item()) for s in sizes))
+    pad_w = torch.full((cap,), -1.0, device=weights.device, dtype=weights.dtype)
+    pad_w[: weights.shape[0]] = weights
+    pad_s = torch.zeros((cap,) + tuple(states.shape[1:]), device=states.device, dtype=states.dtype)
+    pad_s[: states.shape[0]] = states
+    all_w = [torch.empty_like(pad_w) for _ in range(w)]
+    all_s = [torch.empty_like(pad_s) for _ in range(w)]
+    dist.all_gather(all_w, pad_w, group=shard.group)
+    dist.all_gather(all_s, pad_s, group=shard.group)
+    cat_w, cat_s = torch.cat(all_w), torch.cat(all_s)
+    top = torch.topk(cat_w, n)
+    return cat_s[top.indices], top.values

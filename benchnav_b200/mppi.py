@@ -1,0 +1,269 @@
+"""Host-side mirror of the reference planner class, running on the sm_100a engine.
+
+``MPPI`` keeps the constructor signature and the ``forward`` / ``get_top_samples`` contract of the
+reference ``MPPI(nn.Module)`` (src/planners/local_planners/mppi.py:17-240) so that Tutorial 3.3 and
+``test/test_mppi.py:160-185`` run unchanged, and reads -- never replaces -- the reference's own
+``UnicycleModel`` / ``Objectives`` / ``GridMap`` objects (duck-typed: anything exposing the same
+attributes works).  All numerics happen in ``libbnvmppi.so`` through the C ABI (``_cabi.py``); PyTorch is
+used for device memory, streams and ``torch.distributed`` only.  There is no CPU path: constructing the
+solver without a CUDA device raises.
+
+Differences from the reference that a caller can observe (all documented in DESIGN.md):
+  * ``device`` must name a CUDA device; the reference silently falls back to CPU (mppi.py:69-72).
+  * the noise stream: ``noise_source="philox"`` (default) draws inside the engine from a counter-based
+    generator keyed by (seed, global sample, iteration); ``noise_source="torch"`` draws with
+    ``torch.empty(K,T,2).normal_()`` on the CUDA generator exactly like the reference's
+    ``MultivariateNormal.rsample`` on CUDA (mppi.py:149-151), throw-away constructor draw included;
+    ``forward(state, noise=...)`` injects the sigma-scaled noise (parity tests).
+  * ``solve`` is an alias of ``forward`` (north_star names it; the reference has only ``forward``).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import inspect
+from typing import Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _cabi
+from .dist import ShardInfo, gather_shard_partials, merge_top_candidates
+
+
+class _DevView:
+    """Zero-copy view of an engine-owned device buffer via ``__cuda_array_interface__``."""
+
+    def __init__(self, ptr: int, shape: Tuple[int, ...], owner) -> None:
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+        self._owner = owner  # keep the handle alive while the view exists
+
+
+def _introspect_problem(dynamics, objectives):
+    """Pull what ``forward`` reads through ``dynamics``/``objectives`` out of the objects."""
+    try:
+        grid_map = dynamics._grid_map
+        model_config = dynamics._model_config
+        risks = dynamics._traversability_model._risks
+        goal = objectives._goal_pos
+        thr = objectives._stuck_threshold
+        g, res = int(grid_map.grid_size), float(grid_map.resolution)
+        x_lim, y_lim = tuple(grid_map.x_limits), tuple(grid_map.y_limits)
+    except AttributeError as exc:  # not UnicycleModel + Objectives shaped
+        raise TypeError("benchnav_b200.MPPI needs UnicycleModel-like dynamics and Objectives-like objectives "
+                        f"(missing attribute: {exc})") from exc
+    if getattr(model_config, "mode", None) != "inference":
+        # observation mode makes transit return a tuple and breaks the reference as well (robot_model.py:97-98)
+        raise ValueError("dynamics must use ModelConfig(mode='inference')")
+    if risks is None or not torch.is_tensor(risks) or risks.dim() != 2 or risks.shape[0] != g or risks.shape[1] != g:
+        raise ValueError("dynamics._traversability_model._risks must be a [grid_size, grid_size] tensor")
+    dt = 0.1
+    try:
+        dflt = inspect.signature(dynamics.transit).parameters["delta_t"].default
+        if isinstance(dflt, (int, float)):
+            dt = float(dflt)  # MPPI never passes delta_t (mppi.py:163): rollouts use transit's default
+    except (KeyError, TypeError, ValueError, AttributeError):
+        pass
+    return risks, g, res, x_lim, y_lim, goal, float(thr), dt
+
+
+class MPPI(nn.Module):
+    """Model Predictive Path Integral control (Williams et al., T-RO 2017) on one or more B200s."""
+
+    def __init__(self, horizon: int, num_samples: int, dim_state: int, dim_control: int, dynamics, objectives,
+                 sigmas: torch.Tensor, lambda_: float, device=torch.device("cuda"), dtype=torch.float32,
+                 seed: int = 42, *, noise_source: str = "philox", record_states: bool = True,
+                 process_group=None) -> None:
+        super().__init__()
+        torch.manual_seed(seed)  # mppi.py:55
+        # same shape checks (and exception type) as mppi.py:58-66
+        assert dynamics.min_action.shape == (dim_control,), "minimum actions must be a tensor of shape (dim_control,)"
+        assert dynamics.max_action.shape == (dim_control,), "maximum actions must be a tensor of shape (dim_control,)"
+        assert sigmas.shape == (dim_control,), "sigmas must be a tensor of shape (dim_control,)"
+        if dim_state != 3 or dim_control != 2:
+            raise ValueError("the engine implements the unicycle model: dim_state=3, dim_control=2")
+        if dtype != torch.float32:
+            raise ValueError("the engine computes in float32 (the reference's default dtype)")
+        if noise_source not in ("philox", "torch"):
+            raise ValueError("noise_source must be 'philox' or 'torch'")
+        dev = torch.device(device)
+        if dev.type != "cuda" or not torch.cuda.is_available():
+            raise RuntimeError("benchnav_b200.MPPI runs on CUDA (sm_100a) only; there is no CPU fallback")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        self._device, self._dtype = dev, dtype
+        self._horizon, self._num_samples = int(horizon), int(num_samples)
+        self._dim_state, self._dim_control = dim_state, dim_control
+        self._dynamics, self._objectives = dynamics, objectives
+        self._lambda = float(lambda_)
+        self._noise_source = noise_source
+        self._u_min = dynamics.min_action.clone().detach().to(dev, dtype)
+        self._u_max = dynamics.max_action.clone().detach().to(dev, dtype)
+        self._sigmas = sigmas.clone().detach().to(dev, dtype)
+        self._shard = ShardInfo.from_group(process_group)
+        self._lib = _cabi.load()
+
+        risks, g, res, x_lim, y_lim, goal, thr, dt = _introspect_problem(dynamics, objectives)
+        cfg = _cabi.MppiCfg(num_samples=self._num_samples, horizon=self._horizon, lambda_=self._lambda, dt=dt,
+                            seed=int(seed) & 0xFFFFFFFFFFFFFFFF, rank=self._shard.rank,
+                            world_size=self._shard.world_size, device=dev.index,
+                            flags=_cabi.BNV_FLAG_RECORD_STATES if record_states else 0)
+        sig, lo, hi = (t.detach().cpu().to(torch.float32).tolist() for t in (sigmas, dynamics.min_action, dynamics.max_action))
+        for i in range(2):
+            cfg.sigma[i], cfg.u_min[i], cfg.u_max[i] = sig[i], lo[i], hi[i]
+        self._handle = C.c_void_p()
+        _cabi.check(self._lib.bnv_mppi_create(C.byref(self._handle), C.byref(cfg)))
+        self._record_states = bool(record_states)
+        self._local_samples = int(self._lib.bnv_mppi_local_samples(self._handle))
+        self._sample_offset = int(self._lib.bnv_mppi_sample_offset(self._handle))
+        self._sample_shape = torch.Size([self._local_samples, self._horizon])
+        self._risk_dev: Optional[torch.Tensor] = None
+        self._risk_key = None
+        self._goal_host = (C.c_float * 2)()
+        self._sync_problem(force=True)
+
+        # engine-owned state exposed under the reference's attribute names (zero-copy views)
+        k, t = self._local_samples, self._horizon
+        view = lambda ptr, shape: torch.as_tensor(_DevView(ptr, shape, self), device=dev)  # noqa: E731
+        self._weights = view(self._lib.bnv_mppi_weights(self._handle), (k,))
+        self._costs = view(self._lib.bnv_mppi_costs(self._handle), (k,))
+        self._previous_action_seq = view(self._lib.bnv_mppi_u_prev(self._handle), (t, 2))
+        self._engine_noise = view(self._lib.bnv_mppi_noise(self._handle), (k, t, 2))
+        self._state_seq_batch = (view(self._lib.bnv_mppi_states(self._handle), (k, t + 1, 3))
+                                 if record_states else None)
+        self._action_noises = self._engine_noise
+        if noise_source == "torch":
+            self._action_noises = self._draw_torch_noise()  # the reference's throw-away draw, mppi.py:105-107
+        plen = int(self._lib.bnv_mppi_partial_len(self._handle))
+        self._partial = view(self._lib.bnv_mppi_partial(self._handle), (plen,))
+        self._gathered = (torch.empty(self._shard.world_size, plen, device=dev, dtype=torch.float32)
+                          if self._shard.world_size > 1 else None)
+        self._state_dev = torch.zeros(3, device=dev, dtype=torch.float32)
+
+    # ------------------------------------------------------------------ plumbing
+    def _draw_torch_noise(self) -> torch.Tensor:
+        """MultivariateNormal(0, diag(sigma^2)).rsample on CUDA == sigma * empty(K,T,2).normal_() (mppi.py:149-151)."""
+        k, t = self._num_samples, self._horizon
+        eps = torch.empty(k, t, 2, device=self._device, dtype=torch.float32).normal_()
+        eps = eps[self._sample_offset:self._sample_offset + self._local_samples]
+        return (eps * self._sigmas).contiguous()
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self._device).cuda_stream
+
+    def _sync_problem(self, force: bool = False) -> None:
+        """(Re)upload the risk map / goal / threshold when the reference objects changed (cheap identity check)."""
+        dyn, obj = self._dynamics, self._objectives
+        risks, goal = dyn._traversability_model._risks, obj._goal_pos
+        quick = (id(risks), risks._version if torch.is_tensor(risks) else None, id(goal),
+                 goal._version if torch.is_tensor(goal) else None, obj._stuck_threshold, id(dyn._grid_map))
+        if not force and quick == self._risk_key:
+            return
+        risks, g, res, x_lim, y_lim, goal, thr, _ = _introspect_problem(dyn, obj)
+        goal_xy = torch.as_tensor(goal).detach().to("cpu", torch.float32).reshape(-1)[:2].tolist()
+        self._risk_dev = risks.detach().to(self._device, torch.float32).contiguous()
+        self._goal_host[0], self._goal_host[1] = goal_xy
+        with torch.cuda.device(self._device):
+            _cabi.check(self._lib.bnv_mppi_set_problem(
+                self._handle, self._risk_dev.data_ptr(), g, self._risk_dev.stride(0), res, x_lim[0], x_lim[1],
+                y_lim[0], y_lim[1], self._goal_host, thr, self._stream()))
+        self._risk_key = quick
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None) is not None and self._handle.value:
+                self._lib.bnv_mppi_destroy(self._handle)
+                self._handle = C.c_void_p()
+        except Exception:  # interpreter shutdown
+            pass
+
+    # ------------------------------------------------------------------ reference API
+    def forward(self, state: torch.Tensor, noise: Optional[torch.Tensor] = None
+                ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """One control iteration (mppi.py:130-219).
+
+        Returns ``(optimal_action_seq [T,2], optimal_state_seq [1,T+1,3])`` on the solver's device.
+        ``noise`` (optional, [K_local,T,2]) injects the sigma-scaled control noise of this shard.
+        """
+        if not torch.is_tensor(state):
+            state = torch.tensor(state, dtype=self._dtype)
+        assert state.shape == (self._dim_state,)
+        self._sync_problem()
+        with torch.cuda.device(self._device):
+            self._state_dev.copy_(state.detach(), non_blocking=True)
+            if noise is not None:
+                if noise.shape != (self._local_samples, self._horizon, 2):
+                    raise ValueError(f"noise must have shape {(self._local_samples, self._horizon, 2)}")
+                noise = noise.detach().to(self._device, torch.float32).contiguous()
+                self._action_noises = noise
+            elif self._noise_source == "torch":
+                noise = self._action_noises = self._draw_torch_noise()
+            else:
+                self._action_noises = self._engine_noise
+            u_opt = torch.empty(self._horizon, 2, device=self._device, dtype=torch.float32)
+            opt_states = torch.empty(1, self._horizon + 1, 3, device=self._device, dtype=torch.float32)
+            stream = self._stream()
+            _cabi.check(self._lib.bnv_mppi_forward(self._handle, self._state_dev.data_ptr(),
+                                                   noise.data_ptr() if noise is not None else None,
+                                                   u_opt.data_ptr(), opt_states.data_ptr(), stream))
+            if self._shard.world_size > 1:
+                gather_shard_partials(self._partial, self._gathered, self._shard)
+                _cabi.check(self._lib.bnv_mppi_finalize(self._handle, self._gathered.data_ptr(), u_opt.data_ptr(),
+                                                        opt_states.data_ptr(), stream))
+        return u_opt, opt_states
+
+    solve = forward  # north_star's name for the same call
+
+    def forward_host(self, state: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """``forward`` for a HOST state, returning HOST tensors: the ABI's host-buffer form
+        (``bnv_mppi_forward_host``): H2D of the state, the iteration, D2H of both results, one sync."""
+        if self._shard.world_size != 1 or self._noise_source != "philox":
+            out = self.forward(state)
+            return out[0].cpu(), out[1].cpu()
+        state = torch.as_tensor(state, dtype=torch.float32).detach().cpu().contiguous()
+        assert state.shape == (self._dim_state,)
+        self._sync_problem()
+        u_opt = torch.empty(self._horizon, 2, dtype=torch.float32)
+        opt_states = torch.empty(1, self._horizon + 1, 3, dtype=torch.float32)
+        self._action_noises = self._engine_noise
+        _cabi.check(self._lib.bnv_mppi_forward_host(self._handle, state.data_ptr(), None, u_opt.data_ptr(),
+                                                    opt_states.data_ptr(), self._stream()))
+        return u_opt, opt_states
+
+    def get_top_samples(self, num_samples: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Top ``num_samples`` rollouts by weight, descending (mppi.py:221-240)."""
+        assert num_samples <= self._num_samples
+        n_local = min(int(num_samples), self._local_samples)
+        states = torch.empty(n_local, self._horizon + 1, 3, device=self._device, dtype=torch.float32)
+        weights = torch.empty(n_local, device=self._device, dtype=torch.float32)
+        with torch.cuda.device(self._device):
+            _cabi.check(self._lib.bnv_mppi_top_samples(self._handle, n_local, states.data_ptr(), weights.data_ptr(),
+                                                       self._stream()))
+        if self._shard.world_size > 1:
+            return merge_top_candidates(states, weights, int(num_samples), self._shard)
+        return states, weights
+
+    # ------------------------------------------------------------------ extras
+    def reset(self) -> None:
+        """Zero the mean sequence and restart the engine's noise stream (a freshly built solver)."""
+        _cabi.check(self._lib.bnv_mppi_reset(self._handle, self._stream()))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.bnv_mppi_launch_count(self._handle))
+
+    def kernel_timing(self, max_launches: int) -> None:
+        """Record CUDA-event pairs around the rollout kernel of the next ``max_launches`` iterations."""
+        _cabi.check(self._lib.bnv_mppi_kernel_timing(self._handle, int(max_launches)))
+
+    def kernel_time(self) -> Tuple[float, int]:
+        """(summed rollout-kernel milliseconds, launches measured) since kernel_timing(); synchronises."""
+        ms, n = C.c_double(), C.c_uint64()
+        _cabi.check(self._lib.bnv_mppi_kernel_time(self._handle, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
+
+    @property
+    def costs(self) -> torch.Tensor:
+        """Per-sample costs of the last iteration (mppi.py:186-190; the reference does not keep them)."""
+        return self._costs

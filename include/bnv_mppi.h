@@ -1,0 +1,148 @@
+/*
+ * bnv_mppi.h -- C ABI of the B200-native MPPI engine (libbnvmppi.so, sm_100a).
+ *
+ * Drop-in boundary for ONE path of masafumiendo/benchnav: a control iteration of the MPPI local
+ * planner.  The reference has no FFI (it is pure Python/PyTorch); the entry points below are what a
+ * binding for that path would call, and each cites the reference code it replaces (paths relative to
+ * the reference repository root).  The Python mirror of the reference class that sits on top of this
+ * ABI is benchnav_b200/mppi.py; the ctypes stub is benchnav_b200/_cabi.py.
+ *
+ * Conventions
+ *   - every function returns 0 (BNV_OK) or a negative bnv_status; nothing throws across the ABI;
+ *     bnv_last_error() returns a thread-local, NUL-terminated description of the last failure.
+ *   - "dev" pointers are device pointers on the handle's CUDA device; the CALLER owns every buffer it
+ *     passes in, the handle owns its scratch (noise, recorded states, costs, weights, mean sequence).
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  All *_dev entry points
+ *     are asynchronous on that stream and never synchronise with the host.
+ *   - one handle per (device, host thread); handles are not re-entrant (same as the reference module).
+ *   - all arithmetic is IEEE fp32 in the reference's evaluation order (no fast-math, no FMA contraction
+ *     in the state update) -- see DESIGN.md "Parity arithmetic".
+ */
+#ifndef BNV_MPPI_H_
+#define BNV_MPPI_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BNV_ABI_VERSION 1
+
+typedef enum bnv_status {
+  BNV_OK = 0,
+  BNV_ERR_INVALID = -1,     /* bad argument (the reference would raise AssertionError/ValueError) */
+  BNV_ERR_CUDA = -2,        /* a CUDA runtime/driver call failed; see bnv_last_error() */
+  BNV_ERR_UNSUPPORTED = -3, /* valid request this build cannot serve (e.g. horizon too long for shared memory) */
+  BNV_ERR_STATE = -4        /* call order violated (forward before set_problem, top_samples before forward) */
+} bnv_status;
+
+/* bnv_mppi_cfg.flags */
+#define BNV_FLAG_RECORD_STATES 0x1u /* keep every sample's recorded state sequence (reference `_state_seq_batch`,
+                                       mppi.py:119-125); required by bnv_mppi_top_samples */
+
+/* Constructor arguments of the reference `MPPI.__init__` (src/planners/local_planners/mppi.py:23-36) plus
+ * the action bounds it copies from `dynamics.min_action/max_action` (mppi.py:83-88, robot_model.py:54-57),
+ * the rollout time step (`transit`'s default delta_t, robot_model.py:60) and the sample-shard geometry. */
+typedef struct bnv_mppi_cfg {
+  int32_t num_samples;    /* K: TOTAL samples over all shards (mppi.py:26) */
+  int32_t horizon;        /* T (mppi.py:25) */
+  float sigma[2];         /* noise std-dev per control dim (mppi.py:31) */
+  float lambda_;          /* temperature (mppi.py:32) */
+  float u_min[2];         /* robot_model.py:55 */
+  float u_max[2];         /* robot_model.py:56 */
+  float dt;               /* robot_model.py:60 */
+  uint64_t seed;          /* mppi.py:35; keys the in-kernel Philox stream */
+  int32_t rank;           /* this shard's index, 0 <= rank < world_size */
+  int32_t world_size;     /* number of sample shards (GPUs); 1 = single GPU */
+  int32_t device;         /* CUDA device ordinal */
+  uint32_t flags;         /* BNV_FLAG_* */
+} bnv_mppi_cfg;
+
+typedef struct bnv_mppi bnv_mppi; /* opaque solver handle */
+
+/* Library / ABI identification. */
+int bnv_abi_version(void);
+const char* bnv_last_error(void);
+
+/* MPPI.__init__ (mppi.py:23-128): validates, allocates the shard's buffers (noise [Kl,T,2], recorded
+ * states [Kl,T+1,3], costs/weights [Kl]) and zeroes the mean sequence (mppi.py:116).  Kl = this rank's
+ * share of K: global samples [rank*K/W, (rank+1)*K/W). */
+int bnv_mppi_create(bnv_mppi** out, const bnv_mppi_cfg* cfg);
+void bnv_mppi_destroy(bnv_mppi* h);
+
+/* What forward reads through `dynamics`/`objectives`: the risk map `TraversabilityModel._risks`
+ * (traversability_model.py:28-51; [G,G] fp32, row = y cell, `pitch` elements between rows), the GridMap
+ * geometry (grid_map.py:40-50) and `Objectives._goal_pos/_stuck_threshold` (objectives.py:25-27).
+ * Builds the engine's traversability map 1 - clamp(risk,0,1) (traversability_model.py:71-72) and its
+ * TMA descriptor.  Must be called again if the risk map's contents change. */
+int bnv_mppi_set_problem(bnv_mppi* h, const float* risk_dev, int32_t grid_size, int32_t pitch, float resolution,
+                         float x_min, float x_max, float y_min, float y_max, const float goal_xy[2],
+                         float stuck_threshold, void* stream);
+
+/* MPPI.forward (mppi.py:130-219), device buffers.
+ *   state_dev      [3]        current state (x, y, theta)
+ *   noise_dev      [Kl,T,2]   sigma-scaled control noise exactly as `_action_noises` (mppi.py:149-151) for
+ *                             this shard, or NULL to draw it in-kernel (Philox4x32-10 keyed by seed, global
+ *                             sample index and iteration count => independent of world_size)
+ *   u_out_dev      [T,2]      optimal control sequence (also kept as the next call's mean, mppi.py:217)
+ *   opt_states_dev [T+1,3]    recorded states of the optimal rollout (mppi.py:202-214)
+ * With world_size > 1 this runs the shard-local phase only (rollouts, costs, shard partial) and leaves
+ * u_out/opt_states untouched; exchange bnv_mppi_partial() across ranks and call bnv_mppi_finalize(). */
+int bnv_mppi_forward(bnv_mppi* h, const float* state_dev, const float* noise_dev, float* u_out_dev,
+                     float* opt_states_dev, void* stream);
+
+/* Same call with HOST buffers (the reference-facing form: `forward(state)` takes and returns tensors the
+ * caller reads on the host).  Copies state host->device, runs the iteration, copies u_out/opt_states
+ * device->host through pinned staging and synchronises `stream`.  world_size must be 1. */
+int bnv_mppi_forward_host(bnv_mppi* h, const float state_host[3], const float* noise_dev, float* u_out_host,
+                          float* opt_states_host, void* stream);
+
+/* Sample-sharded softmax (replaces the global torch.softmax of mppi.py:193-199).
+ * bnv_mppi_partial: device pointer to this shard's (m, s, U[T,2]) -- m = max_k(-c_k/lambda),
+ * s = sum_k exp(-c_k/lambda - m), U = sum_k exp(..) v[k] -- bnv_mppi_partial_len() floats, valid after
+ * bnv_mppi_forward on `stream`.  bnv_mppi_finalize: log-sum-exp merge of `world_size` gathered partials
+ * (rank-major), normalises this shard's weights, writes u_out/opt_states and the next mean sequence. */
+const float* bnv_mppi_partial(const bnv_mppi* h);
+int32_t bnv_mppi_partial_len(const bnv_mppi* h);
+int bnv_mppi_finalize(bnv_mppi* h, const float* gathered_partials_dev, float* u_out_dev, float* opt_states_dev,
+                      void* stream);
+
+/* MPPI.get_top_samples (mppi.py:221-240): the n highest-weight samples of this shard in descending
+ * weight order.  states_out_dev [n,T+1,3], weights_out_dev [n]. Needs BNV_FLAG_RECORD_STATES. */
+int bnv_mppi_top_samples(bnv_mppi* h, int32_t n, float* states_out_dev, float* weights_out_dev, void* stream);
+
+/* Module state the reference exposes as attributes (device pointers owned by the handle, shard-local):
+ *   weights  [Kl]        `_weights`            (mppi.py:193)
+ *   costs    [Kl]        per-sample cost        (mppi.py:186-190; not stored by the reference)
+ *   states   [Kl,T+1,3]  `_state_seq_batch`    (mppi.py:160-165), NULL without BNV_FLAG_RECORD_STATES
+ *   noise    [Kl,T,2]    `_action_noises`      (mppi.py:149-151) of the last in-kernel draw
+ *   u_prev   [T,2]       `_previous_action_seq` (mppi.py:116, :217) */
+float* bnv_mppi_weights(bnv_mppi* h);
+float* bnv_mppi_costs(bnv_mppi* h);
+float* bnv_mppi_states(bnv_mppi* h);
+float* bnv_mppi_noise(bnv_mppi* h);
+float* bnv_mppi_u_prev(bnv_mppi* h);
+int32_t bnv_mppi_local_samples(const bnv_mppi* h); /* Kl */
+int32_t bnv_mppi_sample_offset(const bnv_mppi* h); /* first global sample index of this shard */
+
+/* Zero the mean sequence and restart the noise stream (a fresh `MPPI(...)`, mppi.py:116). */
+int bnv_mppi_reset(bnv_mppi* h, void* stream);
+
+/* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
+uint64_t bnv_mppi_launch_count(const bnv_mppi* h);
+
+/* Measurement hook: record a CUDA-event pair around the rollout kernel of each of the next `max_launches`
+ * forward calls (0 disables); bnv_mppi_kernel_time() synchronises on them, returns the summed kernel time and
+ * the number of launches measured, and re-arms the recorder. */
+int bnv_mppi_kernel_timing(bnv_mppi* h, int32_t max_launches);
+int bnv_mppi_kernel_time(bnv_mppi* h, double* total_ms, uint64_t* launches);
+
+/* Test hook: evaluates the engine's in-range sin/cos (used by the state update in place of
+ * torch.cos/torch.sin, robot_model.py:86-87) on n device floats. */
+int bnv_debug_sincos(const float* theta_dev, float* sin_dev, float* cos_dev, int32_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BNV_MPPI_H_ */

@@ -1,0 +1,62 @@
+"""Host-side logic that needs no GPU: shard geometry, problem introspection, synthetic inputs."""
+
+import numpy as np
+import pytest
+import torch
+
+from benchnav_b200.dist import ShardInfo, shard_range
+from benchnav_b200.mppi import _introspect_problem
+from benchnav_b200.problem import GoalObjectives, GridSpec, UnicycleProblem
+from benchnav_b200.synthetic import benchmark_problem, make_terrain
+
+
+@pytest.mark.parametrize("k,w", [(16384, 1), (16384, 8), (131072, 8), (5001, 3), (8, 8), (1000, 7)])
+def test_shard_ranges_partition_the_samples(k, w):
+    spans = [shard_range(k, r, w) for r in range(w)]
+    assert spans[0][0] == 0 and spans[-1][1] == k
+    for (a0, a1), (b0, b1) in zip(spans[:-1], spans[1:]):
+        assert a1 == b0 and a1 > a0
+    sizes = [b - a for a, b in spans]
+    assert max(sizes) - min(sizes) <= 1
+
+
+def test_shard_range_rejects_bad_geometry():
+    with pytest.raises(ValueError):
+        shard_range(4, 0, 8)
+    with pytest.raises(ValueError):
+        shard_range(64, 3, 3)
+    assert ShardInfo.from_group(None) == ShardInfo(0, 1, None)
+
+
+def test_grid_limits_follow_the_reference_formula(golden_cases):
+    for case in golden_cases.values():
+        g = GridSpec(case["risk"].shape[0], float(case["resolution"]))
+        assert (g.x_limits[0], g.x_limits[1], g.y_limits[0], g.y_limits[1]) == tuple(case["limits"].tolist())
+
+
+def test_introspection_reads_reference_shaped_objects():
+    grid = GridSpec(32, 0.25)
+    risk = torch.rand(32, 32)
+    dyn = UnicycleProblem(grid, risk)
+    obj = GoalObjectives(dyn, torch.tensor([3, 5]), 0.3)  # integer goal as in test/test_mppi.py:133
+    risks, g, res, xl, yl, goal, thr, dt = _introspect_problem(dyn, obj)
+    assert g == 32 and res == 0.25 and xl == (0.0, 8.0) and thr == 0.3 and dt == 0.1
+    assert torch.equal(risks, risk)
+    dyn._model_config.mode = "observation"
+    with pytest.raises(ValueError):
+        _introspect_problem(dyn, obj)
+    with pytest.raises(TypeError):
+        _introspect_problem(object(), obj)
+
+
+def test_synthetic_problem_is_deterministic_and_sane():
+    a = make_terrain(64, 0.5, seed=3)
+    b = make_terrain(64, 0.5, seed=3)
+    for k in a:
+        assert torch.equal(a[k], b[k])
+    risk, start, goal, thr = benchmark_problem(256, 0.5, seed=0)
+    assert risk.shape == (256, 256) and risk.dtype == torch.float32
+    assert 0.0 <= float(risk.min()) and float(risk.max()) <= 1.0
+    assert float(risk[16, 16]) <= 0.2 + 1e-6  # start cell drivable
+    np.testing.assert_allclose(goal.numpy(), [48.0, 48.0])
+    assert 0.01 < float((1 - risk <= thr).float().mean()) < 0.5  # some, not all, cells are "stuck"

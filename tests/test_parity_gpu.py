@@ -1,0 +1,397 @@
+"""GPU parity tests: the sm_100a engine (through the C ABI, via benchnav_b200.MPPI) against
+(1) golden outputs of the reference itself (tests/golden/*.npz) and (2) the CPU oracle on seeded inputs.
+All tests here need a B200 (`-m gpu`)."""
+
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mppi_oracle as orc
+from tests.gpu_common import (TOL_U, assert_iteration_close, engine_outputs, make_solver, oracle_outputs,
+                              solver_from_golden)
+from tests.helpers import problem_from_golden
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = ["kat_g64_k1000_t25", "corner_wrap_g64_k512_t50", "ragged_g50_k777_t7", "cvar_g64_k512_t50",
+          "tiny_g8_k33_t1", "single_sample_g16_k1_t5"]
+
+
+def _golden_ref(case, i):
+    return {"u_opt": case[f"u_opt_{i}"], "opt_rec": case[f"opt_rec_{i}"], "rec": case[f"rec_{i}"],
+            "weights": case[f"weights_{i}"]}
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_golden_single_calls(golden_cases, name):
+    """Every recorded reference call, with the reference's own noise and mean sequence injected."""
+    case = golden_cases[name]
+    solver = solver_from_golden(case)
+    p = problem_from_golden(case)
+    for i in range(int(case["n_calls"])):
+        solver._previous_action_seq.copy_(torch.from_numpy(case[f"u_prev_{i}"]))
+        u, opt = solver.forward(torch.from_numpy(case[f"state_{i}"]), noise=torch.from_numpy(case[f"noise_{i}"]))
+        eng = engine_outputs(solver, u, opt)
+        ref = _golden_ref(case, i)
+        ref["costs"] = oracle_outputs(p, case[f"state_{i}"], case[f"u_prev_{i}"], case[f"noise_{i}"],
+                                      case["sigmas"], float(case["lam"]))["costs"]
+        assert_iteration_close(eng, ref, f"{name}[{i}]")
+        # the mean sequence for the next call is u*, unshifted (mppi.py:217)
+        np.testing.assert_array_equal(solver._previous_action_seq.cpu().numpy(), eng["u_opt"])
+
+
+@pytest.mark.parametrize("name", ["kat_g64_k1000_t25", "corner_wrap_g64_k512_t50", "cvar_g64_k512_t50"])
+def test_golden_chained_calls(golden_cases, name):
+    """Closed chain: the engine feeds its own u* forward, as the reference does across forward() calls."""
+    case = golden_cases[name]
+    solver = solver_from_golden(case)
+    for i in range(int(case["n_calls"])):
+        u, opt = solver.forward(torch.from_numpy(case[f"state_{i}"]), noise=torch.from_numpy(case[f"noise_{i}"]))
+        eng = engine_outputs(solver, u, opt)
+        du = np.abs(eng["u_opt"] - case[f"u_opt_{i}"]).max()
+        assert du <= (i + 1) * TOL_U, f"{name}[{i}] chained |du*| = {du}"
+
+
+def test_known_answer_against_fp64_truth(golden_cases):
+    """|u*_engine - u*_fp64| <= max(2e-3, 4 |u*_ref32 - u*_fp64|)  (SURVEY 8c)."""
+    case = golden_cases["kat_g64_k1000_t25"]
+    solver = solver_from_golden(case)
+    p = problem_from_golden(case)
+    u, opt = solver.forward(torch.from_numpy(case["state_0"]), noise=torch.from_numpy(case["noise_0"]))
+    truth = oracle_outputs(p, case["state_0"], case["u_prev_0"], case["noise_0"], case["sigmas"], float(case["lam"]),
+                           dtype=torch.float64)
+    ref_gap = np.abs(case["u_opt_0"] - truth["u_opt"]).max()
+    eng_gap = np.abs(u.cpu().numpy() - truth["u_opt"]).max()
+    assert eng_gap <= max(2e-3, 4 * ref_gap), (eng_gap, ref_gap)
+
+
+def test_state_is_not_mutated_and_device_state_accepted(golden_cases):
+    case = golden_cases["kat_g64_k1000_t25"]
+    solver = solver_from_golden(case)
+    st = torch.from_numpy(case["state_0"]).cuda()
+    keep = st.clone()
+    u1, o1 = solver.forward(st, noise=torch.from_numpy(case["noise_0"]))
+    assert torch.equal(st, keep)
+    assert u1.shape == (25, 2) and o1.shape == (1, 26, 3) and u1.is_cuda and o1.is_cuda
+    solver2 = solver_from_golden(case)
+    u2, o2 = solver2.solve(torch.from_numpy(case["state_0"]), noise=torch.from_numpy(case["noise_0"]))
+    assert torch.equal(u1, u2) and torch.equal(o1, o2)  # deterministic, host or device state
+
+
+def test_sincos_accuracy():
+    """The engine's in-range sin/cos: <= 2 ulp against float64 on |x| <= 64, exact at 0."""
+    from benchnav_b200 import _cabi
+
+    lib = _cabi.load()
+    g = torch.Generator().manual_seed(0)
+    x = torch.cat([torch.rand(200000, generator=g) * 7.0 - 3.5, torch.rand(50000, generator=g) * 128.0 - 64.0,
+                   torch.tensor([0.0, -0.0, 3.14159274, -3.14159274, 1.57079637, 0.78539819, 1e-8, 100.0, -1000.0])])
+    xd = x.cuda()
+    s, c = torch.empty_like(xd), torch.empty_like(xd)
+    _cabi.check(lib.bnv_debug_sincos(xd.data_ptr(), s.data_ptr(), c.data_ptr(), xd.numel(), None))
+    torch.cuda.synchronize()
+    x64 = x.double()
+    for got, want in ((s.cpu(), torch.sin(x64)), (c.cpu(), torch.cos(x64))):
+        w32 = want.float()
+        ulp = torch.maximum(torch.abs(torch.nextafter(w32, torch.full_like(w32, 10.0)) - w32),
+                            torch.full_like(w32, 2.0 ** -149)).double()
+        err = (got.double() - want).abs() / ulp
+        assert float(err.max()) <= 2.0, float(err.max())
+    assert float(s[250000]) == 0.0 and float(c[250000]) == 1.0
+
+
+@pytest.mark.parametrize("K,T,G,res", [(16384, 50, 256, 0.5), (5000, 50, 64, 0.5), (131072, 50, 512, 0.5),
+                                       (4096, 30, 64, 0.5)])
+def test_baseline_configs_against_oracle(K, T, G, res):
+    """BASELINE.json configs at full size (config 2 as one shard on one GPU), two chained iterations."""
+    from benchnav_b200.synthetic import benchmark_problem
+
+    risk, start, goal, thr = benchmark_problem(G, res, seed=0)
+    sig, lam = [0.5, 0.5], 0.5
+    solver = make_solver(risk, res, goal, thr, K, T, sig, lam)
+    p = orc.make_problem(risk, res, goal.tolist(), thr)
+    gen = torch.Generator().manual_seed(123)
+    u_prev = torch.zeros(T, 2)
+    for it in range(2):
+        noise = torch.randn(K, T, 2, generator=gen) * torch.tensor(sig)
+        solver._previous_action_seq.copy_(u_prev)
+        u, opt = solver.forward(start, noise=noise)
+        eng = engine_outputs(solver, u, opt)
+        ref = oracle_outputs(p, start, u_prev, noise, sig, lam)
+        assert_iteration_close(eng, ref, f"K{K}T{T}G{G} it{it}")
+        u_prev = torch.from_numpy(ref["u_opt"])
+
+
+def test_unaligned_noise_pointer_and_global_map_fallback():
+    """(a) injected noise whose pointer is only 8-byte aligned takes the non-bulk staging path;
+    (b) a reach window too large for shared memory falls back to looking up the global map."""
+    from benchnav_b200.synthetic import benchmark_problem
+
+    risk, start, goal, thr = benchmark_problem(64, 0.5, seed=3)
+    K, T, sig, lam = 300, 20, [0.4, 0.6], 0.7
+    gen = torch.Generator().manual_seed(5)
+    noise = torch.randn(K, T, 2, generator=gen) * torch.tensor(sig)
+    p = orc.make_problem(risk, 0.5, goal.tolist(), thr)
+    ref = oracle_outputs(p, start, torch.zeros(T, 2), noise, sig, lam)
+    solver = make_solver(risk, 0.5, goal, thr, K, T, sig, lam)
+    buf = torch.zeros(K * T * 2 + 2, device="cuda")
+    shifted = buf[2:].view(K, T, 2)  # data_ptr % 16 == 8
+    shifted.copy_(noise)
+    assert shifted.data_ptr() % 16 == 8
+    from benchnav_b200 import _cabi
+    u = torch.empty(T, 2, device="cuda")
+    opt = torch.empty(1, T + 1, 3, device="cuda")
+    st = start.cuda()
+    _cabi.check(solver._lib.bnv_mppi_forward(solver._handle, st.data_ptr(), shifted.data_ptr(), u.data_ptr(),
+                                             opt.data_ptr(), None))
+    assert_iteration_close(engine_outputs(solver, u, opt), ref, "unaligned noise")
+
+    # (b) 1 cm cells: reach = 50 * 1 * 0.1 / 0.01 = 500 cells -> no shared-memory window
+    g2 = 700
+    gen2 = torch.Generator().manual_seed(9)
+    risk2 = torch.rand(g2, g2, generator=gen2) * 0.6
+    start2, goal2 = torch.tensor([3.5, 3.5, 0.3]), torch.tensor([6.0, 6.0])
+    K2, T2 = 1000, 50
+    noise2 = torch.randn(K2, T2, 2, generator=gen2) * 0.5
+    p2 = orc.make_problem(risk2, 0.01, goal2.tolist(), 0.45)
+    ref2 = oracle_outputs(p2, start2, torch.zeros(T2, 2), noise2, [0.5, 0.5], 0.5)
+    s2 = make_solver(risk2, 0.01, goal2, 0.45, K2, T2, [0.5, 0.5], 0.5)
+    u2, o2 = s2.forward(start2, noise=noise2)
+    assert_iteration_close(engine_outputs(s2, u2, o2), ref2, "global-map fallback")
+
+
+def test_long_horizon_uses_fewer_warps_per_cta():
+    """T = 200 does not fit four warps' staging slabs in shared memory; the launcher narrows the CTA."""
+    gen = torch.Generator().manual_seed(2)
+    risk = torch.rand(128, 128, generator=gen) * 0.5
+    K, T = 200, 200
+    noise = torch.randn(K, T, 2, generator=gen) * 0.5
+    start, goal = torch.tensor([20.0, 20.0, 1.0]), torch.tensor([40.0, 45.0])
+    p = orc.make_problem(risk, 0.5, goal.tolist(), 0.3)
+    ref = oracle_outputs(p, start, torch.zeros(T, 2), noise, [0.5, 0.5], 0.5)
+    s = make_solver(risk, 0.5, goal, 0.3, K, T, [0.5, 0.5], 0.5)
+    u, o = s.forward(start, noise=noise)
+    assert_iteration_close(engine_outputs(s, u, o), ref, "T=200")
+
+
+def test_top_samples(golden_cases):
+    """get_top_samples (mppi.py:221-240): descending weights, rows gathered from the recorded states."""
+    case = golden_cases["kat_g64_k1000_t25"]
+    solver = solver_from_golden(case)
+    solver.forward(torch.from_numpy(case["state_0"]), noise=torch.from_numpy(case["noise_0"]))
+    w_all, rec_all = solver._weights.clone(), solver._state_seq_batch.clone()
+    for n in (1, 7, 500, 1000):
+        states, weights = solver.get_top_samples(n)
+        torch.cuda.synchronize()
+        want_s, want_w = orc.top_samples(rec_all.cpu(), w_all.cpu(), n)
+        np.testing.assert_array_equal(weights.cpu().numpy(), want_w.numpy())
+        w_np = want_w.numpy()
+        uniq = np.concatenate([[True], np.diff(w_np) != 0])
+        uniq[:-1] &= uniq[1:]
+        np.testing.assert_array_equal(states.cpu().numpy()[uniq], want_s.numpy()[uniq])
+        # every returned row is a recorded trajectory carrying exactly that weight
+        assert states.shape == (n, 26, 3)
+    # reference golden: same top weights within the weight tolerance
+    ts, tw = solver.get_top_samples(16)
+    np.testing.assert_allclose(tw.cpu().numpy(), case["top_weights_0"], atol=5e-3)
+    with pytest.raises(AssertionError):
+        solver.get_top_samples(1001)
+
+
+def test_top_samples_large_n_and_ties():
+    """n above the shared-memory sort capacity, with many exactly-zero (underflowed) weights."""
+    from benchnav_b200.synthetic import benchmark_problem
+
+    risk, start, goal, thr = benchmark_problem(64, 0.5, seed=1)
+    K, T = 40000, 10
+    s = make_solver(risk, 0.5, goal, thr, K, T, [0.5, 0.5], 0.05)
+    s.forward(start)
+    w = s._weights.clone().cpu()
+    for n in (20000, 40000):
+        st, tw = s.get_top_samples(n)
+        torch.cuda.synchronize()
+        want = torch.sort(w, descending=True).values[:n]
+        np.testing.assert_array_equal(tw.cpu().numpy(), want.numpy())
+
+
+def test_philox_noise_statistics_and_determinism():
+    from benchnav_b200.synthetic import benchmark_problem
+
+    risk, start, goal, thr = benchmark_problem(64, 0.5, seed=0)
+    K, T, sig = 20000, 51, [0.5, 0.25]  # odd horizon: last step pair is half used
+    a = make_solver(risk, 0.5, goal, thr, K, T, sig, 0.5, seed=7)
+    ua, _ = a.forward(start)
+    na = a._action_noises.clone()
+    assert na.shape == (K, T, 2)
+    x = na.cpu().double()
+    for j in range(2):
+        assert abs(float(x[..., j].mean())) < 4 * sig[j] / np.sqrt(K * T)
+        assert abs(float(x[..., j].std()) / sig[j] - 1.0) < 0.01
+        z = x[..., j] / sig[j]
+        assert abs(float((z ** 3).mean())) < 0.02 and abs(float((z ** 4).mean()) - 3.0) < 0.05
+    assert abs(float((x[..., 0] * x[..., 1]).mean())) < 1e-3
+    assert abs(float((x[:, :-1, 0] * x[:, 1:, 0]).mean())) < 1e-3  # no correlation between consecutive steps
+    assert abs(float((x[:-1, :, 0] * x[1:, :, 0]).mean())) < 1e-3  # nor between neighbouring samples
+    # same seed -> same stream; second iteration differs from the first; reset() restarts it
+    b = make_solver(risk, 0.5, goal, thr, K, T, sig, 0.5, seed=7)
+    ub, _ = b.forward(start)
+    assert torch.equal(b._action_noises, na) and torch.equal(ua, ub)
+    b.forward(start)
+    assert not torch.equal(b._action_noises, na)
+    b.reset()
+    ub2, _ = b.forward(start)
+    assert torch.equal(b._action_noises, na) and torch.equal(ub2, ua)
+    c = make_solver(risk, 0.5, goal, thr, K, T, sig, 0.5, seed=8)
+    c.forward(start)
+    assert not torch.equal(c._action_noises, na)
+
+
+def test_philox_iteration_against_oracle_with_its_own_noise():
+    """Production mode: noise drawn in-engine; the oracle replays the same noise."""
+    from benchnav_b200.synthetic import benchmark_problem
+
+    risk, start, goal, thr = benchmark_problem(256, 0.5, seed=0)
+    K, T, sig, lam = 16384, 50, [0.5, 0.5], 0.5
+    s = make_solver(risk, 0.5, goal, thr, K, T, sig, lam)
+    p = orc.make_problem(risk, 0.5, goal.tolist(), thr)
+    u_prev = torch.zeros(T, 2)
+    for it in range(3):
+        u, opt = s.forward(start)
+        eng = engine_outputs(s, u, opt)
+        ref = oracle_outputs(p, start, u_prev, s._action_noises.cpu(), sig, lam)
+        assert_iteration_close(eng, ref, f"philox it{it}")
+        u_prev = torch.from_numpy(eng["u_opt"])
+
+
+def test_forward_host_matches_forward():
+    from benchnav_b200.synthetic import benchmark_problem
+
+    risk, start, goal, thr = benchmark_problem(64, 0.5, seed=0)
+    a = make_solver(risk, 0.5, goal, thr, 2048, 25, [0.5, 0.5], 0.5, seed=3)
+    b = make_solver(risk, 0.5, goal, thr, 2048, 25, [0.5, 0.5], 0.5, seed=3)
+    for _ in range(3):
+        u1, o1 = a.forward(start)
+        u2, o2 = b.forward_host(start)
+        assert not u2.is_cuda and o2.shape == (1, 26, 3)
+        assert torch.equal(u1.cpu(), u2) and torch.equal(o1.cpu(), o2)
+
+
+def test_sharded_softmax_on_one_gpu():
+    """world_size 2 and 3 emulated on one device through the C ABI: shard-local forward, concatenated partials,
+    finalize on every shard == the single-shard iteration (same Philox stream by global sample index)."""
+    from benchnav_b200 import _cabi
+    from benchnav_b200.synthetic import benchmark_problem
+
+    lib = _cabi.load()
+    risk, start, goal, thr = benchmark_problem(64, 0.5, seed=0)
+    K, T = 5001, 25
+    single = make_solver(risk, 0.5, goal, thr, K, T, [0.5, 0.5], 0.5, seed=11)
+    u_ref, o_ref = single.forward(start)
+    w_ref, n_ref = single._weights.clone(), single._action_noises.clone()
+    risk_d, st_d = risk.cuda().contiguous(), start.cuda()
+    goal_c = (C.c_float * 2)(float(goal[0]), float(goal[1]))
+    for world in (2, 3):
+        handles, outs = [], []
+        for r in range(world):
+            cfg = _cabi.MppiCfg(num_samples=K, horizon=T, lambda_=0.5, dt=0.1, seed=11, rank=r, world_size=world,
+                                device=0, flags=_cabi.BNV_FLAG_RECORD_STATES)
+            for i in range(2):
+                cfg.sigma[i], cfg.u_min[i], cfg.u_max[i] = 0.5, (0.0, -1.0)[i], 1.0
+            h = C.c_void_p()
+            _cabi.check(lib.bnv_mppi_create(C.byref(h), C.byref(cfg)))
+            _cabi.check(lib.bnv_mppi_set_problem(h, risk_d.data_ptr(), 64, 64, 0.5, 0.0, 32.0, 0.0, 32.0, goal_c, thr,
+                                                 None))
+            _cabi.check(lib.bnv_mppi_forward(h, st_d.data_ptr(), None, None, None, None))
+            handles.append(h)
+        plen = lib.bnv_mppi_partial_len(handles[0])
+        gathered = torch.empty(world, plen, device="cuda")
+        for r, h in enumerate(handles):
+            src = torch.as_tensor(_view(lib.bnv_mppi_partial(h), (plen,)), device="cuda")
+            gathered[r].copy_(src)
+        offs = 0
+        for r, h in enumerate(handles):
+            u, o = torch.empty(T, 2, device="cuda"), torch.empty(1, T + 1, 3, device="cuda")
+            _cabi.check(lib.bnv_mppi_finalize(h, gathered.data_ptr(), u.data_ptr(), o.data_ptr(), None))
+            torch.cuda.synchronize()
+            kl = lib.bnv_mppi_local_samples(h)
+            assert lib.bnv_mppi_sample_offset(h) == offs
+            w = torch.as_tensor(_view(lib.bnv_mppi_weights(h), (kl,)), device="cuda")
+            nz = torch.as_tensor(_view(lib.bnv_mppi_noise(h), (kl, T, 2)), device="cuda")
+            assert torch.equal(nz, n_ref[offs:offs + kl])  # noise independent of the sharding
+            np.testing.assert_allclose(u.cpu().numpy(), u_ref.cpu().numpy(), atol=2e-6)
+            np.testing.assert_allclose(o.cpu().numpy(), o_ref.cpu().numpy(), atol=2e-5)
+            np.testing.assert_allclose(w.cpu().numpy(), w_ref[offs:offs + kl].cpu().numpy(), rtol=1e-4, atol=1e-9)
+            outs.append(u)
+            offs += kl
+        assert offs == K
+        for u in outs[1:]:
+            assert torch.equal(u, outs[0])  # every rank computes the identical merge
+        for h in handles:
+            lib.bnv_mppi_destroy(h)
+
+
+class _V:
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+def _view(ptr, shape):
+    return _V(ptr, shape)
+
+
+def test_size_independent_properties_at_full_size():
+    """Properties that need no oracle (BASELINE config 1 sizes): weights form a distribution, u* respects the
+    action bounds, final recorded states lie inside the map, and the iteration is bit-reproducible."""
+    from benchnav_b200.synthetic import benchmark_problem
+
+    risk, start, goal, thr = benchmark_problem(256, 0.5, seed=0)
+    K, T = 16384, 50
+    a = make_solver(risk, 0.5, goal, thr, K, T, [0.5, 0.5], 0.5, seed=1)
+    b = make_solver(risk, 0.5, goal, thr, K, T, [0.5, 0.5], 0.5, seed=1)
+    for _ in range(5):
+        ua, oa = a.forward(start)
+        ub, ob = b.forward(start)
+        assert torch.equal(ua, ub) and torch.equal(oa, ob) and torch.equal(a._weights, b._weights)
+        assert torch.equal(a._state_seq_batch, b._state_seq_batch)
+        w = a._weights
+        assert float(w.min()) >= 0.0 and abs(float(w.double().sum()) - 1.0) < 1e-5
+        assert float(ua[:, 0].min()) >= 0.0 and float(ua[:, 0].max()) <= 1.0 + 1e-6
+        assert float(ua[:, 1].abs().max()) <= 1.0 + 1e-6
+        last = a._state_seq_batch[:, -1, :]
+        assert float(last[:, :2].min()) >= 0.0 and float(last[:, :2].max()) <= 128.0
+        assert float(last[:, 2].min()) >= -np.pi - 1e-6 and float(last[:, 2].max()) < np.pi + 1e-6
+        # rollouts stay inside the reach bound the shared-memory window is sized from
+        reach = (a._state_seq_batch[:, :, :2] - start[:2].cuda()).abs().max()
+        assert float(reach) <= T * 1.0 * 0.1 + 1e-3
+
+
+def test_error_behaviour():
+    from benchnav_b200 import MPPI, _cabi
+    from benchnav_b200.problem import GoalObjectives, GridSpec, UnicycleProblem
+
+    lib = _cabi.load()
+    grid = GridSpec(16, 0.5)
+    dyn = UnicycleProblem(grid, torch.zeros(16, 16))
+    obj = GoalObjectives(dyn, torch.tensor([4.0, 4.0]), 0.3)
+    sig = torch.tensor([0.5, 0.5])
+    with pytest.raises(AssertionError):  # mppi.py:64-66
+        MPPI(10, 64, 3, 2, dyn, obj, torch.tensor([0.5, 0.5, 0.5]), 0.5)
+    with pytest.raises(RuntimeError):  # no CPU fallback
+        MPPI(10, 64, 3, 2, dyn, obj, sig, 0.5, device=torch.device("cpu"))
+    dyn_obs = UnicycleProblem(grid, torch.zeros(16, 16))
+    dyn_obs._model_config.mode = "observation"
+    with pytest.raises(ValueError):
+        MPPI(10, 64, 3, 2, dyn_obs, GoalObjectives(dyn_obs, torch.tensor([4.0, 4.0]), 0.3), sig, 0.5)
+    with pytest.raises(TypeError):
+        MPPI(10, 64, 3, 2, dyn, object(), sig, 0.5)
+    s = MPPI(10, 64, 3, 2, dyn, obj, sig, 0.5)
+    with pytest.raises(AssertionError):  # mppi.py:138
+        s.forward(torch.zeros(4))
+    with pytest.raises(_cabi.BnvError):  # top samples before any forward
+        s.get_top_samples(4)
+    h = C.c_void_p()
+    cfg = _cabi.MppiCfg(num_samples=0, horizon=5, world_size=1)
+    assert lib.bnv_mppi_create(C.byref(h), C.byref(cfg)) == -1 and b"num_samples" in lib.bnv_last_error()
