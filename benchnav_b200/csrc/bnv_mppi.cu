@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -56,6 +57,16 @@ EncodeTiledFn get_encode_tiled() {
 
 constexpr size_t kMaxDynSmem = 200 * 1024;   // leave headroom below the 227 KB per-CTA limit
 constexpr int kMaxPatchBytes = 64 * 1024;    // larger reach windows are looked up in the global map (L2)
+
+// BNV_DEBUG_DISABLE bitmask (debugging aid): 1 = no TMA window (global-map lookups), 2 = no bulk noise load,
+// 4 = no bulk recorded-state store.  All paths are regular product paths, selected otherwise by size/alignment.
+unsigned debug_disable() {
+  static const unsigned v = [] {
+    const char* e = std::getenv("BNV_DEBUG_DISABLE");
+    return e ? static_cast<unsigned>(std::strtoul(e, nullptr, 0)) : 0u;
+  }();
+  return v;
+}
 
 bool is_pow2_float(float v) {
   int e;
@@ -262,8 +273,9 @@ int bnv_mppi_set_problem(bnv_mppi* h, const float* risk_dev, int32_t grid_size, 
   const double reach_cells = static_cast<double>(P.T) * vmax * h->cfg.dt / resolution;
   const long long rho = static_cast<long long>(std::floor(reach_cells)) + 2;
   const long long side = 2 * rho + 1;
-  const long long pw = (side + 3) & ~3LL;
+  const long long pw = (side + 3 + 3) & ~3LL;  // +3: the window's x origin is rounded down to a multiple of 4 cells
   P.use_patch = (pw <= 256 && side <= 256 && pw * side * 4 <= kMaxPatchBytes) ? 1 : 0;
+  if (debug_disable() & 1u) P.use_patch = 0;
   if (P.use_patch) {
     P.rho = static_cast<int>(rho);
     P.patch_w = static_cast<int>(pw);
@@ -314,6 +326,8 @@ static int launch_forward(bnv_mppi* h, const float* state_dev, const float* nois
   }
   P.noise_bulk_ok = (reinterpret_cast<uintptr_t>(P.noise) & 15u) == 0 ? 1 : 0;
   P.rec_bulk_ok = (reinterpret_cast<uintptr_t>(P.rec) & 15u) == 0 ? 1 : 0;
+  if (debug_disable() & 2u) P.noise_bulk_ok = 0;
+  if (debug_disable() & 4u) P.rec_bulk_ok = 0;
   P.state = state_dev;
   h->P.state = state_dev;  // finalize (world_size > 1) re-reads the state of the iteration in flight
   P.u_out = u_out_dev;

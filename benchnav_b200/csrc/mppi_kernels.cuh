@@ -149,8 +149,11 @@ __device__ __forceinline__ WindowGeom window_for_state(const EngineParams& P, fl
   }
   int cx = min(max(cell_coord(sx, P.geom.x_min, P.geom), 0), P.G - 1);
   int cy = min(max(cell_coord(sy, P.geom.y_min, P.geom), 0), P.G - 1);
-  w.ox = max(0, min(cx - P.rho, P.G - P.patch_w));
-  w.oy = max(0, min(cy - P.rho, P.G - P.patch_h));
+  // The innermost TMA coordinate must be a multiple of 16 bytes (4 cells) -- an unaligned x origin raises an
+  // illegal-instruction fault on sm_100a -- so the origin is rounded down and patch_w carries 3 spare columns.
+  // The box may overhang the map on the high side: overhanging cells are zero-filled and never indexed.
+  w.ox = max(0, (cx - P.rho) & ~3);
+  w.oy = max(0, cy - P.rho);
   w.lo_x = w.ox;
   w.hi_x = min(P.G - 1, w.ox + P.patch_w - 1);
   w.lo_y = w.oy;
@@ -264,9 +267,11 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
   const WindowGeom wg = window_for_state(P, sx, sy);
   TauWindow win;
   if (P.use_patch) {
-    if (tid == 0) {
-      mbar_arrive_expect_tx(bar_patch, static_cast<uint32_t>(P.patch_w * P.patch_h * 4));
-      tma_load_2d(patch_s, &P.tau_map, wg.ox, wg.oy, bar_patch);
+    if (warp == 0) {
+      if (elect_one()) {
+        mbar_arrive_expect_tx(bar_patch, static_cast<uint32_t>(P.patch_w * P.patch_h * 4));
+        tma_load_2d(patch_s, &P.tau_map, wg.ox, wg.oy, bar_patch);
+      }
     }
     win.base = patch_s - (wg.oy * P.patch_w + wg.ox);
     win.pitch = P.patch_w;
@@ -465,9 +470,11 @@ __global__ void __launch_bounds__(kFinalizeThreads) finalize_kernel(const __grid
   const WindowGeom wg = window_for_state(P, sx, sy);
   TauWindow win;
   if (P.use_patch) {
-    if (tid == 0) {
-      mbar_arrive_expect_tx(bar_patch, static_cast<uint32_t>(P.patch_w * P.patch_h * 4));
-      tma_load_2d(patch_s, &P.tau_map, wg.ox, wg.oy, bar_patch);
+    if (tid < 32) {
+      if (elect_one()) {
+        mbar_arrive_expect_tx(bar_patch, static_cast<uint32_t>(P.patch_w * P.patch_h * 4));
+        tma_load_2d(patch_s, &P.tau_map, wg.ox, wg.oy, bar_patch);
+      }
     }
     win.base = patch_s - (wg.oy * P.patch_w + wg.ox);
     win.pitch = P.patch_w;
