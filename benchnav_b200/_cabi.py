@@ -67,9 +67,11 @@ _SIGNATURES = {
     "bnv_mppi_local_samples": (C.c_int32, [_VP]),
     "bnv_mppi_sample_offset": (C.c_int32, [_VP]),
     "bnv_mppi_reset": (C.c_int, [_VP, _VP]),
+    "bnv_mppi_draw_noise": (C.c_int, [_VP, C.c_uint64, _VP]),
     "bnv_mppi_launch_count": (C.c_uint64, [_VP]),
     "bnv_mppi_kernel_timing": (C.c_int, [_VP, C.c_int32]),
     "bnv_mppi_kernel_time": (C.c_int, [_VP, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+    "bnv_debug_timestamps": (C.c_int, [_VP, C.POINTER(C.c_longlong)]),
     "bnv_debug_sincos": (C.c_int, [_VP, _VP, _VP, C.c_int32, _VP]),
 }
 

@@ -55,7 +55,7 @@ EncodeTiledFn get_encode_tiled() {
   return fn;
 }
 
-constexpr size_t kMaxDynSmem = 200 * 1024;   // leave headroom below the 227 KB per-CTA limit
+constexpr size_t kMaxDynSmem = 220 * 1024;   // just below the 227 KB per-CTA limit
 constexpr int kMaxPatchBytes = 64 * 1024;    // larger reach windows are looked up in the global map (L2)
 
 // BNV_DEBUG_DISABLE bitmask (debugging aid): 1 = no TMA window (global-map lookups), 2 = no bulk noise load,
@@ -93,11 +93,17 @@ struct bnv_mppi {
   float* shard_partial = nullptr;
   float* io_dev = nullptr;  // [3] state + [2T] u_out + [3(T+1)] opt states, staging for forward_host
   unsigned int* ticket = nullptr;
+  float* stats = nullptr;
+  unsigned int epoch = 0;
+  int num_sms = 0;
+  bool coop_ok = true;
+  long long* dbg_ts = nullptr;
   int* top_idx = nullptr;
   unsigned long long* top_pairs = nullptr;
   size_t top_pairs_cap = 0, top_idx_cap = 0;
   float* io_host = nullptr;  // pinned mirror of io_dev
-  int grid = 0;
+  int grid = 0, warps = 0;
+  bool fast_angles = false;
   size_t rollout_smem = 0, finalize_smem = 0;
   // optional CUDA-event timing of the rollout kernel alone (bench.py's roofline)
   bool timing = false;
@@ -119,6 +125,8 @@ void free_all(bnv_mppi* h) {
   cudaFree(h->shard_partial);
   cudaFree(h->io_dev);
   cudaFree(h->ticket);
+  cudaFree(h->stats);
+  cudaFree(h->dbg_ts);
   cudaFree(h->top_idx);
   cudaFree(h->top_pairs);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
@@ -131,13 +139,47 @@ int configure_launch(bnv_mppi* h) {
   for (int w = bnv::kMaxWarps; w >= 1; w >>= 1) {
     bnv::RolloutSmem L = bnv::rollout_smem_layout(P.T, w, P.patch_w, P.patch_h, P.use_patch, P.record);
     if (static_cast<size_t>(L.total) <= kMaxDynSmem) {
-      P.warps = w;
+      h->warps = w;
       h->rollout_smem = L.total;
       h->grid = (h->Kl + w * 32 - 1) / (w * 32);
       return BNV_OK;
     }
   }
   return fail(BNV_ERR_UNSUPPORTED, "horizon %d does not fit the rollout kernel's shared-memory staging", P.T);
+}
+
+using RolloutFn = void (*)(bnv::EngineParams);
+using FinalizeFn = void (*)(bnv::EngineParams, const float*, int);
+
+// rollout_kernel<kPatch, kPow2, kRecord, kFastAngles, kPhilox>
+template <bool A, bool B, bool C, bool D>
+RolloutFn pick_rollout4(bool e) {
+  return e ? bnv::rollout_kernel<A, B, C, D, true> : bnv::rollout_kernel<A, B, C, D, false>;
+}
+template <bool A, bool B, bool C>
+RolloutFn pick_rollout3(bool d, bool e) {
+  return d ? pick_rollout4<A, B, C, true>(e) : pick_rollout4<A, B, C, false>(e);
+}
+template <bool A, bool B>
+RolloutFn pick_rollout2(bool c, bool d, bool e) {
+  return c ? pick_rollout3<A, B, true>(d, e) : pick_rollout3<A, B, false>(d, e);
+}
+template <bool A>
+RolloutFn pick_rollout1(bool b, bool c, bool d, bool e) {
+  return b ? pick_rollout2<A, true>(c, d, e) : pick_rollout2<A, false>(c, d, e);
+}
+RolloutFn pick_rollout(const bnv_mppi* h, bool philox) {
+  const bool a = h->P.use_patch, b = h->P.geom.res_pow2, c = h->P.record, d = h->fast_angles;
+  return a ? pick_rollout1<true>(b, c, d, philox) : pick_rollout1<false>(b, c, d, philox);
+}
+template <bool A, bool B>
+FinalizeFn pick_finalize2(bool c) {
+  return c ? bnv::finalize_kernel<A, B, true> : bnv::finalize_kernel<A, B, false>;
+}
+FinalizeFn pick_finalize(const bnv_mppi* h) {
+  const bool a = h->P.use_patch, b = h->P.geom.res_pow2, c = h->fast_angles;
+  if (a) return b ? pick_finalize2<true, true>(c) : pick_finalize2<true, false>(c);
+  return b ? pick_finalize2<false, true>(c) : pick_finalize2<false, false>(c);
 }
 
 }  // namespace
@@ -187,10 +229,11 @@ int bnv_mppi_create(bnv_mppi** out, const bnv_mppi_cfg* cfg) {
   alloc(reinterpret_cast<void**>(&h->part_u), sizeof(float) * max_grid * 2 * T);
   alloc(reinterpret_cast<void**>(&h->shard_partial), sizeof(float) * (2 + 2 * T));
   alloc(reinterpret_cast<void**>(&h->io_dev), sizeof(float) * io_floats);
-  alloc(reinterpret_cast<void**>(&h->ticket), sizeof(unsigned int));
+  alloc(reinterpret_cast<void**>(&h->ticket), 2 * sizeof(unsigned int));
+  alloc(reinterpret_cast<void**>(&h->stats), 4 * sizeof(float));
   if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&h->io_host), sizeof(float) * io_floats);
   if (e == cudaSuccess) e = cudaMemset(h->u_prev, 0, sizeof(float) * T * 2);  // mppi.py:116
-  if (e == cudaSuccess) e = cudaMemset(h->ticket, 0, sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMemset(h->ticket, 0, 2 * sizeof(unsigned int));
   if (e == cudaSuccess) e = cudaMemset(h->weights, 0, sizeof(float) * Kl);    // mppi.py:126-128
   if (e == cudaSuccess && record) e = cudaMemset(h->rec, 0, sizeof(float) * Kl * (T + 1) * 3);  // mppi.py:119-125
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -202,13 +245,21 @@ int bnv_mppi_create(bnv_mppi** out, const bnv_mppi_cfg* cfg) {
   bnv::EngineParams& P = h->P;
   P.bounds = {cfg->u_min[0], cfg->u_min[1], cfg->u_max[0], cfg->u_max[1], cfg->dt};
   P.lambda = cfg->lambda_;
+  P.inv_lambda = 1.0f / cfg->lambda_;
+  P.lambda_pow2 = is_pow2_float(cfg->lambda_) ? 1 : 0;
+  // branch-free steps need the heading to move by less than pi per step (see mppi_math.cuh)
+  h->fast_angles = cfg->dt * std::max(std::fabs(cfg->u_min[1]), std::fabs(cfg->u_max[1])) < 3.0f;
   P.icov0 = 1.0f / (cfg->sigma[0] * cfg->sigma[0]);  // inverse of diag(sigma^2), mppi.py:94-97
   P.icov1 = 1.0f / (cfg->sigma[1] * cfg->sigma[1]);
+  P.sigma0 = cfg->sigma[0];
+  P.sigma1 = cfg->sigma[1];
+  P.seed_lo = static_cast<uint32_t>(cfg->seed);
+  P.seed_hi = static_cast<uint32_t>(cfg->seed >> 32);
+  P.k_offset = h->k_offset;
   P.Kl = Kl;
   P.T = T;
   P.world = cfg->world_size;
   P.record = record ? 1 : 0;
-  P.noise = h->noise;
   P.u_prev = h->u_prev;
   P.rec = h->rec;
   P.costs = h->costs;
@@ -217,6 +268,16 @@ int bnv_mppi_create(bnv_mppi** out, const bnv_mppi_cfg* cfg) {
   P.part_u = h->part_u;
   P.shard_partial = h->shard_partial;
   P.ticket = h->ticket;
+  P.stats = h->stats;
+  cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, cfg->device);
+  int coop_attr = 0;
+  cudaDeviceGetAttribute(&coop_attr, cudaDevAttrCooperativeLaunch, cfg->device);
+  h->coop_ok = coop_attr != 0 && !(debug_disable() & 64u);
+  if (std::getenv("BNV_DEBUG_TS")) {
+    if (cudaMalloc(reinterpret_cast<void**>(&h->dbg_ts), 16 * sizeof(long long)) == cudaSuccess)
+      cudaMemset(h->dbg_ts, 0, 16 * sizeof(long long));
+  }
+  P.dbg_ts = h->dbg_ts;
   *out = h;
   return BNV_OK;
 }
@@ -298,10 +359,11 @@ int bnv_mppi_set_problem(bnv_mppi* h, const float* risk_dev, int32_t grid_size, 
   int rc = configure_launch(h);
   if (rc != BNV_OK) return rc;
   h->finalize_smem = 128 + (P.use_patch ? ((P.patch_w * P.patch_h + 31) / 32) * 32 * 4 : 0) + 2 * P.T * 4 + 16;
-  BNV_CUDA(cudaFuncSetAttribute(bnv::rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                static_cast<int>(h->rollout_smem)));
-  BNV_CUDA(cudaFuncSetAttribute(bnv::finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                static_cast<int>(h->finalize_smem)));
+  for (bool philox : {false, true})
+    BNV_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(pick_rollout(h, philox)),
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h->rollout_smem)));
+  BNV_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(pick_finalize(h)),
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h->finalize_smem)));
   h->problem_set = true;
   return BNV_OK;
 }
@@ -309,22 +371,12 @@ int bnv_mppi_set_problem(bnv_mppi* h, const float* risk_dev, int32_t grid_size, 
 static int launch_forward(bnv_mppi* h, const float* state_dev, const float* noise_dev, float* u_out_dev,
                           float* opt_states_dev, cudaStream_t s) {
   bnv::EngineParams P = h->P;
-  const int T = P.T;
-  if (!noise_dev) {
-    const long long work = static_cast<long long>(h->Kl) * ((T + 1) / 2);
-    const int blocks = static_cast<int>((work + 255) / 256);
-    bnv::noise_kernel<<<blocks, 256, 0, s>>>(h->noise, h->Kl, T, h->k_offset, static_cast<uint32_t>(h->cfg.seed),
-                                             static_cast<uint32_t>(h->cfg.seed >> 32),
-                                             static_cast<uint32_t>(h->iteration),
-                                             static_cast<uint32_t>(h->iteration >> 32), h->cfg.sigma[0],
-                                             h->cfg.sigma[1]);
-    BNV_CUDA(cudaGetLastError());
-    h->launches++;
-    P.noise = h->noise;
-  } else {
-    P.noise = noise_dev;
-  }
-  P.noise_bulk_ok = (reinterpret_cast<uintptr_t>(P.noise) & 15u) == 0 ? 1 : 0;
+  const bool philox = noise_dev == nullptr;
+  P.noise_in = noise_dev;
+  P.noise_out = h->noise;
+  P.iter_lo = static_cast<uint32_t>(h->iteration);
+  P.iter_hi = static_cast<uint32_t>(h->iteration >> 32);
+  P.noise_bulk_ok = (!philox && (reinterpret_cast<uintptr_t>(noise_dev) & 15u) == 0) ? 1 : 0;
   P.rec_bulk_ok = (reinterpret_cast<uintptr_t>(P.rec) & 15u) == 0 ? 1 : 0;
   if (debug_disable() & 2u) P.noise_bulk_ok = 0;
   if (debug_disable() & 4u) P.rec_bulk_ok = 0;
@@ -332,16 +384,31 @@ static int launch_forward(bnv_mppi* h, const float* state_dev, const float* nois
   h->P.state = state_dev;  // finalize (world_size > 1) re-reads the state of the iteration in flight
   P.u_out = u_out_dev;
   P.opt_rec = opt_states_dev;
+  // One CTA per SM (shared-memory bound): the grid is co-resident iff it has at most num_sms CTAs.  Then launch
+  // cooperatively (residency guaranteed by the driver) and use the deferred-store epilogue.
+  const bool coop = h->coop_ok && h->grid <= h->num_sms;
+  h->epoch = (h->epoch == 0xFFFFFFFFu) ? 1u : h->epoch + 1u;
+  P.epoch = h->epoch;
+  P.coop = coop ? 1 : 0;
   const bool timed = h->timing && h->ev_used + 2 <= h->ev.size();
   if (timed) BNV_CUDA(cudaEventRecord(h->ev[h->ev_used], s));
-  bnv::rollout_kernel<<<h->grid, P.warps * 32, h->rollout_smem, s>>>(P);
-  BNV_CUDA(cudaGetLastError());
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(h->grid);
+  cfg.blockDim = dim3(h->warps * 32);
+  cfg.dynamicSmemBytes = h->rollout_smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = coop ? 1 : 0;
+  BNV_CUDA(cudaLaunchKernelEx(&cfg, pick_rollout(h, philox), P));
   if (timed) {
     BNV_CUDA(cudaEventRecord(h->ev[h->ev_used + 1], s));
     h->ev_used += 2;
   }
   h->launches++;
-  h->iteration++;
+  if (philox) h->iteration++;
   h->have_weights = (P.world == 1);
   return BNV_OK;
 }
@@ -387,8 +454,8 @@ int bnv_mppi_finalize(bnv_mppi* h, const float* gathered_partials_dev, float* u_
   bnv::EngineParams P = h->P;
   P.u_out = u_out_dev;
   P.opt_rec = opt_states_dev;
-  bnv::finalize_kernel<<<1, bnv::kFinalizeThreads, h->finalize_smem, static_cast<cudaStream_t>(stream)>>>(
-      P, gathered_partials_dev);
+  pick_finalize(h)<<<1, bnv::kFinalizeThreads, h->finalize_smem, static_cast<cudaStream_t>(stream)>>>(
+      P, gathered_partials_dev, h->cfg.rank);
   BNV_CUDA(cudaGetLastError());
   h->launches++;
   h->have_weights = true;
@@ -452,6 +519,20 @@ int bnv_mppi_reset(bnv_mppi* h, void* stream) {
   return BNV_OK;
 }
 
+int bnv_mppi_draw_noise(bnv_mppi* h, uint64_t iteration, void* stream) {
+  if (!h) return fail(BNV_ERR_INVALID, "null argument");
+  BNV_CUDA(cudaSetDevice(h->cfg.device));
+  const int T = h->P.T;
+  const long long work = static_cast<long long>(h->Kl) * ((T + 1) / 2);
+  const int blocks = static_cast<int>((work + 255) / 256);
+  bnv::noise_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      h->noise, h->Kl, T, h->k_offset, static_cast<uint32_t>(h->cfg.seed), static_cast<uint32_t>(h->cfg.seed >> 32),
+      static_cast<uint32_t>(iteration), static_cast<uint32_t>(iteration >> 32), h->cfg.sigma[0], h->cfg.sigma[1]);
+  BNV_CUDA(cudaGetLastError());
+  h->launches++;
+  return BNV_OK;
+}
+
 uint64_t bnv_mppi_launch_count(const bnv_mppi* h) { return h ? h->launches : 0; }
 
 int bnv_mppi_kernel_timing(bnv_mppi* h, int32_t max_launches) {
@@ -480,6 +561,13 @@ int bnv_mppi_kernel_time(bnv_mppi* h, double* total_ms, uint64_t* launches) {
   *total_ms = sum;
   *launches = h->ev_used / 2;
   h->ev_used = 0;
+  return BNV_OK;
+}
+
+int bnv_debug_timestamps(bnv_mppi* h, long long out[16]) {
+  if (!h || !out) return fail(BNV_ERR_INVALID, "null argument");
+  if (!h->dbg_ts) return fail(BNV_ERR_STATE, "set BNV_DEBUG_TS=1 before creating the handle");
+  BNV_CUDA(cudaMemcpy(out, h->dbg_ts, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
   return BNV_OK;
 }
 

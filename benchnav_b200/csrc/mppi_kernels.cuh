@@ -1,16 +1,19 @@
 // sm_100a kernels of the MPPI control iteration (reference: src/planners/local_planners/mppi.py:130-240).
 //
-//   trav_map_kernel     risk map -> tau = 1 - clamp(risk,0,1), padded pitch          (traversability_model.py:71-72)
-//   noise_kernel        Philox4x32-10 + Box-Muller -> sigma-scaled noise [Kl,T,2]     (mppi.py:149-151)
-//   rollout_kernel      clamp, T-step unicycle rollout, costs, per-CTA softmax partial, (mppi.py:152-199)
-//                       last CTA: grid merge, weights, optimal rollout                (mppi.py:193-217)
+//   trav_map_kernel     risk map -> tau = 1 - clamp(risk,0,1), padded pitch            (traversability_model.py:71-72)
+//   rollout_kernel      noise draw (Philox, interleaved with the rollout), clamp, T-step unicycle rollout, costs,
+//                       per-CTA softmax partial; last CTA: grid merge, weights, optimal rollout (mppi.py:149-217)
+//   noise_kernel        the same Philox stream as a stand-alone kernel (tests / bnv_mppi_draw_noise)
 //   finalize_kernel     multi-GPU: merge gathered shard partials, weights, optimal rollout
-//   top-n kernels       radix select + sort + gather                                  (mppi.py:221-240)
+//   top-n kernels       radix select + sort + gather                                    (mppi.py:221-240)
 //
 // Work decomposition of rollout_kernel: one thread = one sample, state and running cost in registers;
-// one warp = 32 consecutive samples with its own noise slab (1-D bulk copy global->shared, own mbarrier)
-// and its own recorded-state slab (shared->global bulk store), so warps never synchronise inside the
-// T-loop; one CTA = kWarps warps sharing the traversability window staged by a 2-D TMA load.
+// one warp = 32 consecutive samples with its own slabs in shared memory -- noise (bulk-loaded from HBM when
+// injected, or produced in the loop and bulk-stored), clamped controls v, recorded states (bulk-stored) -- so
+// warps never synchronise inside the T-loop; one CTA = up to 4 warps (one per SM sub-partition) sharing the
+// traversability window staged by one 2-D TMA load.  At K = 16384 there is at most one warp per scheduler: the
+// kernel is bound by the per-step dependency chain, not by bandwidth, so the loop body is branch-free, keeps
+// every invariant in registers, and fills the chain's stall slots with the next step pair's Philox draw.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -32,16 +35,20 @@ struct alignas(64) EngineParams {
   GridGeom geom;
   Bounds bounds;
   float goal_x, goal_y, thr;
-  float lambda, icov0, icov1;  // temperature, 1/sigma^2 (diag of mppi.py:95 inverse covariance)
+  float lambda, inv_lambda, icov0, icov1;  // temperature, 1/sigma^2 (diag of mppi.py:95 inverse covariance)
+  int lambda_pow2;                        // lambda is a power of two: -c * (1/lambda) == -c / lambda exactly
+  float sigma0, sigma1;
+  uint32_t seed_lo, seed_hi, iter_lo, iter_hi;  // Philox key and iteration counter
+  int k_offset;                // global index of this shard's first sample
   int Kl, T;                   // shard-local samples, horizon
   int patch_w, patch_h, rho;   // staged window size (cells) and reach radius
   int use_patch;               // 0: window does not fit shared memory -> look up in the global map (L2)
-  int warps;                   // warps per rollout CTA
   int world;                   // number of sample shards
   int record;                  // keep recorded states
   int noise_bulk_ok, rec_bulk_ok;  // pointers 16 B aligned -> bulk copies allowed
   const float* state;   // [3]
-  const float* noise;   // [Kl][T][2]
+  const float* noise_in;  // injected noise [Kl][T][2] (kPhilox == false)
+  float* noise_out;     // engine noise buffer [Kl][T][2], written when kPhilox
   float* u_prev;        // [T][2]   mean sequence (read at start, replaced by u* at the end)
   float* rec;           // [Kl][T+1][3]
   float* costs;         // [Kl]
@@ -49,14 +56,27 @@ struct alignas(64) EngineParams {
   float* part_ms;       // [nCTA][2]   per-CTA (max score, sum exp)
   float* part_u;        // [nCTA][2T]  per-CTA sum exp * v
   float* shard_partial; // [2+2T]      (m, s, U) of this shard
-  unsigned int* ticket;
+  unsigned int* ticket;  // [0] arrival counter of the last-CTA election, [1] "merge done" epoch flag (coop)
+  float* stats;          // [2] (M, S) of the last merge, published to the waiting CTAs (coop)
+  unsigned int epoch;    // unique per launch
+  int coop;              // grid is co-resident (cooperative launch): deferred slab stores, in-register weights
   float* u_out;         // [T][2]
   float* opt_rec;       // [T+1][3]
+  long long* dbg_ts;    // optional [16] clock64 stamps of the last CTA (BNV_DEBUG_TS; null in production)
 };
+
+#define BNV_STAMP(i)                                                   \
+  do {                                                                 \
+    if (P.dbg_ts != nullptr && threadIdx.x == 0) P.dbg_ts[i] = clock64(); \
+  } while (0)
+#define BNV_STAMP_ANY(i, tid_)                                         \
+  do {                                                                 \
+    if (P.dbg_ts != nullptr && threadIdx.x == (tid_)) P.dbg_ts[i] = clock64(); \
+  } while (0)
 
 // Shared-memory carve-up of the rollout kernel (identical on host and device).
 struct RolloutSmem {
-  int off_patch, off_noise, off_rec, off_uprev, off_e, off_warpu, off_red, total;
+  int off_patch, off_noise, off_v, off_rec, off_uprev, off_coef, off_e, off_warpu, off_red, total;
 };
 __host__ __device__ inline RolloutSmem rollout_smem_layout(int T, int warps, int patch_w, int patch_h, int use_patch,
                                                            int record) {
@@ -67,9 +87,13 @@ __host__ __device__ inline RolloutSmem rollout_smem_layout(int T, int warps, int
   off += use_patch ? ((patch_w * patch_h * 4 + 127) / 128) * 128 : 0;
   s.off_noise = off;
   off += ((spb * 2 * T * 4 + 127) / 128) * 128;
+  s.off_v = off;
+  off += ((spb * 2 * T * 4 + 127) / 128) * 128;
   s.off_rec = off;
   off += record ? ((spb * 3 * (T + 1) * 4 + 127) / 128) * 128 : 0;
   s.off_uprev = off;
+  off += ((2 * T * 4 + 15) / 16) * 16;
+  s.off_coef = off;
   off += ((2 * T * 4 + 15) / 16) * 16;
   s.off_e = off;
   off += spb * 4;
@@ -98,7 +122,8 @@ __global__ void trav_map_kernel(const float* __restrict__ risk, int risk_pitch, 
 }
 
 // --------------------------------------------------------------------------------------------- noise
-// One thread = one (sample, step pair): 4 normals = noise[k][2p..2p+1][0..1].
+// Stand-alone draw of the engine's noise stream: one thread = one (sample, step pair) = noise[k][2p..2p+1][0..1].
+// Bit-identical to what rollout_kernel<kPhilox> produces in its loop (same noise_pair()).
 __global__ void __launch_bounds__(256) noise_kernel(float* __restrict__ noise, int Kl, int T, int k_offset,
                                                     uint32_t seed_lo, uint32_t seed_hi, uint32_t iter_lo,
                                                     uint32_t iter_hi, float sigma0, float sigma1) {
@@ -107,21 +132,11 @@ __global__ void __launch_bounds__(256) noise_kernel(float* __restrict__ noise, i
   if (gid >= static_cast<long long>(Kl) * pairs) return;
   int k = static_cast<int>(gid / pairs);
   int p = static_cast<int>(gid - static_cast<long long>(k) * pairs);
-  uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(k + k_offset), static_cast<uint32_t>(p), iter_lo, iter_hi),
-                          make_uint2(seed_lo, seed_hi));
-  float2 a = box_muller(r.x, r.y);
-  float2 b = box_muller(r.z, r.w);
+  const float4 n = noise_pair(static_cast<uint32_t>(k + k_offset), static_cast<uint32_t>(p), iter_lo, iter_hi,
+                              make_uint2(seed_lo, seed_hi), sigma0, sigma1);
   float* dst = noise + (static_cast<size_t>(k) * T + 2 * p) * 2;
-  if (2 * p + 1 < T) {
-    if ((T & 1) == 0) {
-      *reinterpret_cast<float4*>(dst) = make_float4(sigma0 * a.x, sigma1 * a.y, sigma0 * b.x, sigma1 * b.y);
-    } else {
-      *reinterpret_cast<float2*>(dst) = make_float2(sigma0 * a.x, sigma1 * a.y);
-      *reinterpret_cast<float2*>(dst + 2) = make_float2(sigma0 * b.x, sigma1 * b.y);
-    }
-  } else {
-    *reinterpret_cast<float2*>(dst) = make_float2(sigma0 * a.x, sigma1 * a.y);
-  }
+  *reinterpret_cast<float2*>(dst) = make_float2(n.x, n.y);
+  if (2 * p + 1 < T) *reinterpret_cast<float2*>(dst + 2) = make_float2(n.z, n.w);
 }
 
 // --------------------------------------------------------------------------------------------- helpers
@@ -147,8 +162,8 @@ __device__ __forceinline__ WindowGeom window_for_state(const EngineParams& P, fl
     w.hi_x = w.hi_y = P.G - 1;
     return w;
   }
-  int cx = min(max(cell_coord(sx, P.geom.x_min, P.geom), 0), P.G - 1);
-  int cy = min(max(cell_coord(sy, P.geom.y_min, P.geom), 0), P.G - 1);
+  int cx = min(max(cell_coord_rt(sx, P.geom.x_min, P.geom), 0), P.G - 1);
+  int cy = min(max(cell_coord_rt(sy, P.geom.y_min, P.geom), 0), P.G - 1);
   // The innermost TMA coordinate must be a multiple of 16 bytes (4 cells) -- an unaligned x origin raises an
   // illegal-instruction fault on sm_100a -- so the origin is rounded down and patch_w carries 3 spare columns.
   // The box may overhang the map on the high side: overhanging cells are zero-filled and never indexed.
@@ -161,75 +176,194 @@ __device__ __forceinline__ WindowGeom window_for_state(const EngineParams& P, fl
   return w;
 }
 
-// Score of a cost: x = -c / lambda (mppi.py:193), true division.
-__device__ __forceinline__ float score_of(float cost, float lambda) { return __fdiv_rn(-cost, lambda); }
+__device__ __forceinline__ StepConsts make_step_consts(const EngineParams& P, const WindowGeom& wg, const float* patch_s) {
+  StepConsts c;
+  c.x_min = P.geom.x_min; c.y_min = P.geom.y_min; c.x_max = P.geom.x_max; c.y_max = P.geom.y_max;
+  c.res = P.geom.res; c.inv_res = P.geom.inv_res; c.dt = P.bounds.dt;
+  c.gx = P.goal_x; c.gy = P.goal_y; c.thr = P.thr;
+  c.u_min0 = P.bounds.u_min0; c.u_min1 = P.bounds.u_min1; c.u_max0 = P.bounds.u_max0; c.u_max1 = P.bounds.u_max1;
+  c.lo_x = wg.lo_x; c.hi_x = wg.hi_x; c.lo_y = wg.lo_y; c.hi_y = wg.hi_y;
+  if (P.use_patch) {
+    c.pitch = P.patch_w;
+    c.win_addr = smem_u32(patch_s) - 4u * static_cast<uint32_t>(wg.oy * P.patch_w + wg.ox);
+    c.map = nullptr;
+  } else {
+    c.pitch = P.pitch;
+    c.win_addr = 0u;
+    c.map = P.tau;
+  }
+  c.finish();
+  return c;
+}
 
-// Last phase of an iteration, run by ONE CTA once (M, S, U) over all samples are known:
+// Score of a cost: x = -c / lambda (mppi.py:193), true division unless lambda is a power of two.
+__device__ __forceinline__ float score_of(float cost, const EngineParams& P) {
+  return P.lambda_pow2 ? __fmul_rn(-cost, P.inv_lambda) : __fdiv_rn(-cost, P.lambda);
+}
+
+// Batch-1 optimal rollout (mppi.py:202-214) by one thread: first step with the general math, the rest fast.
+template <bool kPatch, bool kPow2, bool kFastAngles>
+__device__ void optimal_rollout(const EngineParams& P, const StepConsts& c, const float* u_s, float sx, float sy,
+                                float sth) {
+  const int T = P.T;
+  float x = sx, y = sy, th = sth, xr, yr, thr;
+  float tau = lookup_tau<kPatch, kPow2, false>(c, x, y);
+  // transit re-clamps the action (robot_model.py:82-83): u* is a rounded weighted sum and may leave the bounds by an ulp
+  unicycle_step<false>(c, tau, clampf(u_s[0], c.u_min0, c.u_max0), clampf(u_s[1], c.u_min1, c.u_max1), x, y, th, xr, yr,
+                       thr);
+  float* out = P.opt_rec;
+  out[0] = xr; out[1] = yr; out[2] = thr;
+#pragma unroll 2
+  for (int t = 1; t < T; ++t) {
+    tau = lookup_tau<kPatch, kPow2, true>(c, x, y);
+    unicycle_step<kFastAngles>(c, tau, clampf(u_s[2 * t], c.u_min0, c.u_max0),
+                               clampf(u_s[2 * t + 1], c.u_min1, c.u_max1), x, y, th, xr, yr, thr);
+    out[3 * t + 0] = xr; out[3 * t + 1] = yr; out[3 * t + 2] = thr;
+  }
+  out[3 * T + 0] = x; out[3 * T + 1] = y; out[3 * T + 2] = th;
+}
+
+// weights[k] *= scale(k): four samples per load, kBatch loads in flight per thread (the values were written by
+// other SMs, so every load is an L2 round trip).  scale_of(g) gives the factor of CTA g's samples.
+template <typename ScaleFn>
+__device__ __forceinline__ void rescale_weights(float* weights, int Kl, int spb_shift, int wt, int wn, ScaleFn scale_of) {
+  const int n4 = Kl >> 2;
+  float4* w4 = reinterpret_cast<float4*>(weights);
+  constexpr int kBatch = 8;
+  for (int base = 0; base < n4; base += wn * kBatch) {
+    float4 ev[kBatch];
+#pragma unroll
+    for (int j = 0; j < kBatch; ++j) {
+      const int q = base + j * wn + wt;
+      if (q < n4) ev[j] = __ldcg(w4 + q);
+    }
+#pragma unroll
+    for (int j = 0; j < kBatch; ++j) {
+      const int q = base + j * wn + wt;
+      if (q < n4) {
+        const float a = scale_of((q << 2) >> spb_shift);  // spb is a multiple of 4: a float4 never straddles CTAs
+        w4[q] = make_float4(ev[j].x * a, ev[j].y * a, ev[j].z * a, ev[j].w * a);
+      }
+    }
+  }
+  for (int kk = (n4 << 2) + wt; kk < Kl; kk += wn) weights[kk] = __ldcg(weights + kk) * scale_of(kk >> spb_shift);
+}
+
+// Last phase of a sharded iteration, run by ONE CTA of finalize_kernel once (M, S, U) over all shards are known:
 // u* = U / S (mppi.py:196-199), next mean sequence (mppi.py:217), weights (mppi.py:193) and the batch-1
 // optimal rollout (mppi.py:202-214).  `u_s` (shared, 2T floats) holds U on entry and u* on exit.
-__device__ void finish_iteration(const EngineParams& P, const TauWindow& win, float M, float S, float* u_s,
+// `weights` holds exp(score - M_shard) per sample on entry; `w_scale` turns that into softmax weights.
+template <bool kPatch, bool kPow2, bool kFastAngles>
+__device__ void finish_iteration(const EngineParams& P, const StepConsts& c, float S, float w_scale, float* u_s,
                                  float sx, float sy, float sth) {
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int T = P.T;
-  for (int c = tid; c < 2 * T; c += nthr) {
-    float u = __fdiv_rn(u_s[c], S);
-    u_s[c] = u;
-    P.u_out[c] = u;
-    P.u_prev[c] = u;
+  for (int i = tid; i < 2 * T; i += nthr) {
+    float u = __fdiv_rn(u_s[i], S);
+    u_s[i] = u;
+    P.u_out[i] = u;
+    P.u_prev[i] = u;
   }
   __syncthreads();
-  if (tid == 0) {
-    float x = sx, y = sy, th = sth;
-    float tau = lookup_tau(win, P.geom, x, y);
-    for (int t = 0; t < T; ++t) {
-      float xr, yr, thr;
-      unicycle_step(P.geom, P.bounds, tau, u_s[2 * t], u_s[2 * t + 1], x, y, th, xr, yr, thr);
-      P.opt_rec[3 * t + 0] = xr;
-      P.opt_rec[3 * t + 1] = yr;
-      P.opt_rec[3 * t + 2] = thr;
-      tau = lookup_tau(win, P.geom, x, y);
-    }
-    P.opt_rec[3 * T + 0] = x;
-    P.opt_rec[3 * T + 1] = y;
-    P.opt_rec[3 * T + 2] = th;
-  }
-  // weights w_k = exp(x_k - M) / S over the shard (mppi.py:193).  With more than one warp the serial optimal
-  // rollout keeps warp 0 busy and the other warps normalise underneath it; loads are batched for MLP.
+  if (tid == 0) optimal_rollout<kPatch, kPow2, kFastAngles>(P, c, u_s, sx, sy, sth);
+  // With more than one warp the serial optimal rollout keeps warp 0 busy and the other warps rescale underneath it.
   const bool split = nthr > 32;
   if (split && tid < 32) return;
   if (!split) __syncwarp();
-  const int wt = split ? tid - 32 : tid, wn = split ? nthr - 32 : nthr;
-  const float inv_s = __fdiv_rn(1.0f, S);
-  constexpr int kBatch = 8;
-  for (int base = 0; base < P.Kl; base += wn * kBatch) {
-    float c[kBatch];
-#pragma unroll
-    for (int j = 0; j < kBatch; ++j) {
-      int k = base + j * wn + wt;
-      c[j] = (k < P.Kl) ? __ldcg(P.costs + k) : 0.0f;
-    }
-#pragma unroll
-    for (int j = 0; j < kBatch; ++j) {
-      int k = base + j * wn + wt;
-      if (k < P.Kl) P.weights[k] = expf(score_of(c[j], P.lambda) - M) * inv_s;
-    }
-  }
+  rescale_weights(P.weights, P.Kl, 0, split ? tid - 32 : tid, split ? nthr - 32 : nthr,
+                  [w_scale](int) { return w_scale; });
 }
 
 // --------------------------------------------------------------------------------------------- rollout
+// Slabs -> HBM: recorded states (and the drawn noise), one bulk store per warp slab; asynchronous, the caller
+// waits for the shared-memory reads (bulk_wait_read_all) before the CTA exits.
+template <bool kRecord, bool kPhilox>
+__device__ __forceinline__ void store_slabs(const EngineParams& P, float* rec_s, float* nz_w, int warp, int lane,
+                                            int warp_first, int warp_rows, uint32_t nz_bytes) {
+  if (warp_rows <= 0 || !(kRecord || kPhilox)) return;
+  const int T = P.T;
+  float* rec_g = P.rec + static_cast<size_t>(warp_first) * 3 * (T + 1);
+  const uint32_t rec_bytes = static_cast<uint32_t>(warp_rows) * 3u * (T + 1) * 4u;
+  float* rec_w = rec_s + warp * 32 * 3 * (T + 1);
+  float* nz_g = P.noise_out + static_cast<size_t>(warp_first) * 2 * T;
+  const bool rec_bulk = kRecord && P.rec_bulk_ok && (rec_bytes & 15u) == 0u;
+  const bool out_bulk = kPhilox && (nz_bytes & 15u) == 0u;  // the engine's buffer is 256 B aligned
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (elect_one()) {
+    if (rec_bulk) bulk_store_s2g(rec_g, rec_w, rec_bytes);
+    if (out_bulk) bulk_store_s2g(nz_g, nz_w, nz_bytes);
+    bulk_commit();
+  }
+  if (kRecord && !rec_bulk)
+    for (int i = lane; i < warp_rows * 3 * (T + 1); i += 32) rec_g[i] = rec_w[i];
+  if (kPhilox && !out_bulk)
+    for (int i = lane; i < warp_rows * 2 * T; i += 32) nz_g[i] = nz_w[i];
+}
+
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned int atom_add_acq_rel_gpu(unsigned int* p, unsigned int v) {
+  unsigned int old;
+  asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// One rollout step of one sample (mppi.py:152-165, :174-182): control from mean + noise, unicycle step, recorded
+// state, shared lookup for the stage cost and the next step, cost accumulation.
+struct SampleState {
+  float x, y, th, tau, stage_sum, act_sum;
+};
+
+template <bool kPatch, bool kPow2, bool kRecord, bool kFastStep>
+__device__ __forceinline__ void sample_step(SampleState& s, const StepConsts& C, int t, float nx, float ny,
+                                            const float* uprev_s, const float* coef_s, float* vrow, float* rrow) {
+  const float2 up = *reinterpret_cast<const float2*>(uprev_s + 2 * t);
+  const float2 cf = *reinterpret_cast<const float2*>(coef_s + 2 * t);
+  const float v0 = clampf(__fadd_rn(up.x, nx), C.u_min0, C.u_max0);  // mppi.py:152-157
+  const float v1 = clampf(__fadd_rn(up.y, ny), C.u_min1, C.u_max1);
+  *reinterpret_cast<float2*>(vrow + 2 * t) = make_float2(v0, v1);    // kept for the weighted control sum
+  float xr, yr, thr;
+  unicycle_step<kFastStep>(C, s.tau, v0, v1, s.x, s.y, s.th, xr, yr, thr);
+  if (kRecord) {
+    rrow[3 * t + 0] = xr;
+    rrow[3 * t + 1] = yr;
+    rrow[3 * t + 2] = thr;
+  }
+  // one lookup serves the stage cost of the recorded (raw) position and the next dynamics step
+  s.tau = lookup_tau<kPatch, kPow2, true>(C, s.x, s.y);
+  s.stage_sum = __fadd_rn(s.stage_sum, goal_and_stuck_cost(C, xr, yr, s.tau));
+  s.act_sum = __fadd_rn(s.act_sum, fmaf(cf.x, v0, __fmul_rn(cf.y, v1)));  // mppi.py:178-182
+}
+
+// kPatch: traversability window staged in shared memory by TMA (else looked up in the global map);
+// kPow2: resolution is a power of two (multiply instead of divide in the cell index);
+// kRecord: keep every sample's recorded states; kFastAngles: dt * max|omega| < pi (branch-free steps 1..T-1);
+// kPhilox: draw the noise in the loop (else it is injected and bulk-loaded from HBM).
+template <bool kPatch, bool kPow2, bool kRecord, bool kFastAngles, bool kPhilox>
 __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid_constant__ EngineParams P) {
   extern __shared__ __align__(128) unsigned char smem[];
+  const long long t_start = clock64();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int T = P.T;
-  const int spb = P.warps * 32;
-  const RolloutSmem L = rollout_smem_layout(T, P.warps, P.patch_w, P.patch_h, P.use_patch, P.record);
+  const int nwarps = blockDim.x >> 5;
+  const int spb = nwarps * 32;
+  const RolloutSmem L = rollout_smem_layout(T, nwarps, P.patch_w, P.patch_h, kPatch, kRecord);
   uint64_t* bar_patch = reinterpret_cast<uint64_t*>(smem);
   uint64_t* bar_noise = reinterpret_cast<uint64_t*>(smem) + 1;  // [kMaxWarps]
   int* last_flag = reinterpret_cast<int*>(smem + 64);
   float* patch_s = reinterpret_cast<float*>(smem + L.off_patch);
   float* noise_s = reinterpret_cast<float*>(smem + L.off_noise);
+  float* v_s = reinterpret_cast<float*>(smem + L.off_v);
   float* rec_s = reinterpret_cast<float*>(smem + L.off_rec);
   float* uprev_s = reinterpret_cast<float*>(smem + L.off_uprev);
+  float* coef_s = reinterpret_cast<float*>(smem + L.off_coef);
   float* e_s = reinterpret_cast<float*>(smem + L.off_e);
   float* warpu_s = reinterpret_cast<float*>(smem + L.off_warpu);
   float* red_s = reinterpret_cast<float*>(smem + L.off_red);
@@ -244,200 +378,317 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
     mbar_init(bar_patch, 1);
     for (int w = 0; w < kMaxWarps; ++w) mbar_init(bar_noise + w, 1);
     fence_mbar_init();
-    if (P.use_patch) prefetch_tensormap(&P.tau_map);
+    if (kPatch) prefetch_tensormap(&P.tau_map);
   }
   __syncthreads();
 
-  // ---- stage this warp's noise slab: rows [warp_first, warp_first+warp_rows) x 2T floats, contiguous in HBM
+  // ---- injected noise: stage this warp's slab, rows [warp_first, warp_first+warp_rows) x 2T floats, contiguous in HBM
   float* nz_w = noise_s + warp * 32 * 2 * T;
-  const float* nz_g = P.noise + static_cast<size_t>(warp_first) * 2 * T;
+  float* v_w = v_s + warp * 32 * 2 * T;
   const uint32_t nz_bytes = static_cast<uint32_t>(warp_rows) * 2u * T * 4u;
   const bool nz_bulk = P.noise_bulk_ok && ((nz_bytes & 15u) == 0u) && warp_rows > 0;
-  if (nz_bulk) {
-    if (lane == 0) {
-      mbar_arrive_expect_tx(bar_noise + warp, nz_bytes);
-      bulk_load_g2s(nz_w, nz_g, nz_bytes, bar_noise + warp);
+  if (!kPhilox) {
+    const float* nz_g = P.noise_in + static_cast<size_t>(warp_first) * 2 * T;
+    if (nz_bulk) {
+      if (elect_one()) {
+        mbar_arrive_expect_tx(bar_noise + warp, nz_bytes);
+        bulk_load_g2s(nz_w, nz_g, nz_bytes, bar_noise + warp);
+      }
+    } else {
+      for (int i = lane; i < warp_rows * 2 * T; i += 32) nz_w[i] = nz_g[i];
     }
-  } else {
-    for (int i = lane; i < warp_rows * 2 * T; i += 32) nz_w[i] = nz_g[i];
   }
+  // v rows of a ragged warp that carry no sample: keep them finite (the weighted-sum pass multiplies them by 0)
+  for (int i = warp_rows * 2 * T + lane; i < 32 * 2 * T; i += 32) v_w[i] = 0.0f;
 
   // ---- state, window geometry, traversability window via TMA
-  const float sx = P.state[0], sy = P.state[1], sth = P.state[2];
+  const float sx = __ldg(P.state), sy = __ldg(P.state + 1), sth = __ldg(P.state + 2);
   const WindowGeom wg = window_for_state(P, sx, sy);
-  TauWindow win;
-  if (P.use_patch) {
+  if (kPatch) {
     if (warp == 0) {
       if (elect_one()) {
         mbar_arrive_expect_tx(bar_patch, static_cast<uint32_t>(P.patch_w * P.patch_h * 4));
         tma_load_2d(patch_s, &P.tau_map, wg.ox, wg.oy, bar_patch);
       }
     }
-    win.base = patch_s - (wg.oy * P.patch_w + wg.ox);
-    win.pitch = P.patch_w;
-  } else {
-    win.base = P.tau;
-    win.pitch = P.pitch;
   }
-  win.lo_x = wg.lo_x;
-  win.hi_x = wg.hi_x;
-  win.lo_y = wg.lo_y;
-  win.hi_y = wg.hi_y;
+  StepConsts C = make_step_consts(P, wg, patch_s);
 
-  for (int c = tid; c < 2 * T; c += blockDim.x) uprev_s[c] = P.u_prev[c];
+  // first step pair of the Philox stream: drawn while the TMA window and the mean sequence are in flight
+  const uint32_t kg = static_cast<uint32_t>(k + P.k_offset);
+  const uint2 key = make_uint2(P.seed_lo, P.seed_hi);
+  float sig0 = P.sigma0, sig1 = P.sigma1;
+  float4 nz_cur = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (kPhilox) nz_cur = noise_pair(kg, 0u, P.iter_lo, P.iter_hi, key, sig0, sig1);
+
+  // mean sequence and the per-step action-cost coefficients u_prev[t] Sigma^-1 (mppi.py:178-181)
+  for (int i = tid; i < 2 * T; i += blockDim.x) {
+    const float u = P.u_prev[i];
+    uprev_s[i] = u;
+    coef_s[i] = __fmul_rn(u, (i & 1) ? P.icov1 : P.icov0);
+  }
   __syncthreads();
-  if (P.use_patch) mbar_wait(bar_patch, 0);
-  if (nz_bulk) mbar_wait(bar_noise + warp, 0);
-  else __syncwarp();
+  if (kPatch) mbar_wait(bar_patch, 0);
+  if (!kPhilox) {
+    if (nz_bulk) mbar_wait(bar_noise + warp, 0);
+    else __syncwarp();
+  }
+  C.pin_all();
+  pin(sig0);
+  pin(sig1);
+  const long long t_loop0 = clock64();
 
   // ---- T-step rollout, one sample per thread
   float cost = FLT_MAX;
-  const float* nrow = nz_w + lane * 2 * T;
+  float* nrow = nz_w + lane * 2 * T;
+  float* vrow = v_w + lane * 2 * T;
   float* rrow = rec_s + (warp * 32 + lane) * 3 * (T + 1);
   if (valid) {
-    float x = sx, y = sy, th = sth;
-    float tau = lookup_tau(win, P.geom, x, y);
-    float stage_sum = 0.0f, act_sum = 0.0f;
-    for (int t = 0; t < T; ++t) {
-      const float2 n = *reinterpret_cast<const float2*>(nrow + 2 * t);
-      const float2 up = *reinterpret_cast<const float2*>(uprev_s + 2 * t);
-      const float v0 = clampf(__fadd_rn(up.x, n.x), P.bounds.u_min0, P.bounds.u_max0);  // mppi.py:152-157
-      const float v1 = clampf(__fadd_rn(up.y, n.y), P.bounds.u_min1, P.bounds.u_max1);
-      float xr, yr, thr;
-      unicycle_step(P.geom, P.bounds, tau, v0, v1, x, y, th, xr, yr, thr);
-      if (P.record) {
-        rrow[3 * t + 0] = xr;
-        rrow[3 * t + 1] = yr;
-        rrow[3 * t + 2] = thr;
+    SampleState s;
+    s.x = sx; s.y = sy; s.th = sth; s.stage_sum = 0.0f; s.act_sum = 0.0f;
+    s.tau = lookup_tau<kPatch, kPow2, false>(C, s.x, s.y);
+    // Steps are processed in pairs (one Philox call yields both steps' noise).  The pair after the current one is
+    // drawn in the same straight-line block as the current pair's steps -- unconditionally, so that there is no
+    // branch and ptxas can interleave its ~100 independent instructions into the stall slots of the dependency
+    // chain (this warp is alone on its scheduler).  Step 0 takes the general math (arbitrary initial heading);
+    // an odd horizon's last step is peeled off the pair loop.
+    const int nfull = T >> 1;
+    auto fetch_pair = [&](int p) -> float4 {  // noise of steps 2p, 2p+1; advances the Philox pipeline
+      float4 nz;
+      if (kPhilox) {
+        nz = nz_cur;
+        nz_cur = noise_pair(kg, static_cast<uint32_t>(p + 1), P.iter_lo, P.iter_hi, key, sig0, sig1);
+      } else {
+        const float2 a = *reinterpret_cast<const float2*>(nrow + 4 * p);
+        const float2 b = *reinterpret_cast<const float2*>(nrow + 4 * p + 2);
+        nz = make_float4(a.x, a.y, b.x, b.y);
       }
-      // one lookup serves the stage cost of the recorded (raw) position and the next dynamics step
-      tau = lookup_tau(win, P.geom, x, y);
-      stage_sum = __fadd_rn(stage_sum, goal_and_stuck_cost(xr, yr, P.goal_x, P.goal_y, tau, P.thr));
-      const float act = __fadd_rn(__fmul_rn(__fmul_rn(up.x, P.icov0), v0), __fmul_rn(__fmul_rn(up.y, P.icov1), v1));
-      act_sum = __fadd_rn(act_sum, __fmul_rn(P.lambda, act));  // mppi.py:178-182, :189
+      return nz;
+    };
+    if (nfull >= 1) {
+      const float4 nz = fetch_pair(0);
+      if (kPhilox) {
+        *reinterpret_cast<float2*>(nrow) = make_float2(nz.x, nz.y);
+        *reinterpret_cast<float2*>(nrow + 2) = make_float2(nz.z, nz.w);
+      }
+      sample_step<kPatch, kPow2, kRecord, false>(s, C, 0, nz.x, nz.y, uprev_s, coef_s, vrow, rrow);
+      sample_step<kPatch, kPow2, kRecord, kFastAngles>(s, C, 1, nz.z, nz.w, uprev_s, coef_s, vrow, rrow);
+      for (int p = 1; p < nfull; ++p) {
+        const float4 nq = fetch_pair(p);
+        if (kPhilox) {
+          *reinterpret_cast<float2*>(nrow + 4 * p) = make_float2(nq.x, nq.y);
+          *reinterpret_cast<float2*>(nrow + 4 * p + 2) = make_float2(nq.z, nq.w);
+        }
+        sample_step<kPatch, kPow2, kRecord, kFastAngles>(s, C, 2 * p, nq.x, nq.y, uprev_s, coef_s, vrow, rrow);
+        sample_step<kPatch, kPow2, kRecord, kFastAngles>(s, C, 2 * p + 1, nq.z, nq.w, uprev_s, coef_s, vrow, rrow);
+      }
     }
-    if (P.record) {
-      rrow[3 * T + 0] = x;
-      rrow[3 * T + 1] = y;
-      rrow[3 * T + 2] = th;
+    if (T & 1) {  // last (or only) step of an odd horizon: first half of pair nfull
+      float2 nl;
+      if (kPhilox) {
+        nl = make_float2(nz_cur.x, nz_cur.y);
+        *reinterpret_cast<float2*>(nrow + 4 * nfull) = nl;
+      } else {
+        nl = *reinterpret_cast<const float2*>(nrow + 4 * nfull);
+      }
+      if (nfull == 0) sample_step<kPatch, kPow2, kRecord, false>(s, C, 0, nl.x, nl.y, uprev_s, coef_s, vrow, rrow);
+      else sample_step<kPatch, kPow2, kRecord, kFastAngles>(s, C, T - 1, nl.x, nl.y, uprev_s, coef_s, vrow, rrow);
     }
-    const float terminal = goal_and_stuck_cost(x, y, P.goal_x, P.goal_y, tau, P.thr);  // mppi.py:184
-    cost = __fadd_rn(__fadd_rn(stage_sum, terminal), act_sum);                         // mppi.py:186-190
+    if (kRecord) { rrow[3 * T + 0] = s.x; rrow[3 * T + 1] = s.y; rrow[3 * T + 2] = s.th; }
+    const float terminal = goal_and_stuck_cost(C, s.x, s.y, s.tau);                            // mppi.py:184
+    cost = __fadd_rn(__fadd_rn(s.stage_sum, terminal), __fmul_rn(P.lambda, s.act_sum));         // mppi.py:186-190
     P.costs[k] = cost;
   }
-
-  // ---- recorded states: shared -> HBM, one bulk store per warp slab, drains behind the epilogue
-  if (P.record && warp_rows > 0) {
-    float* rec_g = P.rec + static_cast<size_t>(warp_first) * 3 * (T + 1);
-    const uint32_t rec_bytes = static_cast<uint32_t>(warp_rows) * 3u * (T + 1) * 4u;
-    float* rec_w = rec_s + warp * 32 * 3 * (T + 1);
-    if (P.rec_bulk_ok && (rec_bytes & 15u) == 0u) {
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        bulk_store_s2g(rec_g, rec_w, rec_bytes);
-        bulk_commit();
-      }
-    } else {
-      __syncwarp();
-      for (int i = lane; i < warp_rows * 3 * (T + 1); i += 32) rec_g[i] = rec_w[i];
-    }
-  }
+  const long long t_loop1 = clock64();
 
   // ---- per-CTA softmax partial: m = max score, s = sum exp(score - m), U[c] = sum exp(score - m) * v[k][c]
-  const float score = valid ? score_of(cost, P.lambda) : -FLT_MAX;
+  const float score = valid ? score_of(cost, P) : -FLT_MAX;
   float wm = warp_max(score);
   if (lane == 0) red_s[warp] = wm;
   __syncthreads();
   float m_cta = red_s[0];
-  for (int w = 1; w < P.warps; ++w) m_cta = fmaxf(m_cta, red_s[w]);
-  const float e = valid ? expf(score - m_cta) : 0.0f;
+  for (int w = 1; w < nwarps; ++w) m_cta = fmaxf(m_cta, red_s[w]);
+  const float e = valid ? __expf(score - m_cta) : 0.0f;
   e_s[tid] = e;
   float ws = warp_sum(e);
   if (lane == 0) red_s[8 + warp] = ws;
   __syncwarp();
-  // each warp: columns over lanes, its own 32 samples
-  for (int c = lane; c < 2 * T; c += 32) {
-    const float up = uprev_s[c];
-    const float lo = (c & 1) ? P.bounds.u_min1 : P.bounds.u_min0;
-    const float hi = (c & 1) ? P.bounds.u_max1 : P.bounds.u_max0;
-    float acc = 0.0f;
-#pragma unroll 8
-    for (int r = 0; r < warp_rows; ++r) {
-      const float v = clampf(__fadd_rn(up, nz_w[r * 2 * T + c]), lo, hi);
-      acc = fmaf(e_s[warp * 32 + r], v, acc);
+  // each warp: columns over lanes, its own 32 samples; v_w holds the clamped controls, e_s the un-normalised weights
+  {
+    const float4* e4 = reinterpret_cast<const float4*>(e_s + warp * 32);
+    for (int c = lane; c < 2 * T; c += 32) {
+      const float* col = v_w + c;
+      float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f, acc3 = 0.0f;
+#pragma unroll
+      for (int r4 = 0; r4 < 8; ++r4) {  // rows past warp_rows carry e = 0 and zeros
+        const float4 ev = e4[r4];
+        acc0 = fmaf(ev.x, col[(4 * r4 + 0) * 2 * T], acc0);
+        acc1 = fmaf(ev.y, col[(4 * r4 + 1) * 2 * T], acc1);
+        acc2 = fmaf(ev.z, col[(4 * r4 + 2) * 2 * T], acc2);
+        acc3 = fmaf(ev.w, col[(4 * r4 + 3) * 2 * T], acc3);
+      }
+      warpu_s[warp * 2 * T + c] = (acc0 + acc1) + (acc2 + acc3);
     }
-    warpu_s[warp * 2 * T + c] = acc;
   }
   __syncthreads();
   float s_cta = 0.0f;
-  for (int w = 0; w < P.warps; ++w) s_cta += red_s[8 + w];
+  for (int w = 0; w < nwarps; ++w) s_cta += red_s[8 + w];
   for (int c = tid; c < 2 * T; c += blockDim.x) {
     float acc = 0.0f;
-    for (int w = 0; w < P.warps; ++w) acc += warpu_s[w * 2 * T + c];
+    for (int w = 0; w < nwarps; ++w) acc += warpu_s[w * 2 * T + c];
     P.part_u[static_cast<size_t>(blockIdx.x) * 2 * T + c] = acc;
   }
   if (tid == 0) {
     P.part_ms[2 * blockIdx.x + 0] = m_cta;
     P.part_ms[2 * blockIdx.x + 1] = s_cta;
   }
+  // Two epilogue schedules.  coop (the whole grid is co-resident; cooperative launch): the slab stores (17 MB over
+  // the grid) are held back until the last CTA has merged the partials -- issued earlier, their burst through
+  // L2 was measured to stretch the merge's loads from ~0.8k to ~3k cycles each -- and every CTA normalises its own
+  // weights from registers once (M, S) are published.  Otherwise (more CTAs than SMs): stores go out at once and
+  // the last CTA rescales all weights.
+  const bool coop = P.coop != 0;
+  if (!coop) {
+    if (valid) P.weights[k] = e;  // exp(score - m_cta); rescaled by the last CTA
+    store_slabs<kRecord, kPhilox>(P, rec_s, nz_w, warp, lane, warp_first, warp_rows, nz_bytes);
+  }
+  const long long t_part = clock64();
 
-  // ---- grid-wide merge by the last CTA to finish (atomic ticket)
-  __threadfence();
+  // ---- grid-wide merge by the last CTA to finish (atomic ticket).  The CTA barrier orders every thread's writes
+  // before thread 0's acq_rel atomic (cumulativity): the release half publishes this CTA's partial, the acquire
+  // half (in the CTA that draws the last ticket) makes every other CTA's partial visible to the loads below.
   __syncthreads();
   if (tid == 0) {
-    unsigned int prev = atomicAdd(P.ticket, 1u);
+    unsigned int prev = atom_add_acq_rel_gpu(P.ticket, 1u);
     *last_flag = (prev == gridDim.x - 1) ? 1 : 0;
   }
   __syncthreads();
-  if (*last_flag) {
-    __threadfence();
+  const bool is_last = *last_flag != 0;
+  float M = 0.0f, S = 1.0f;
+  if (is_last) {
+    if (P.dbg_ts != nullptr && tid == 0) {
+      P.dbg_ts[0] = t_start; P.dbg_ts[1] = t_loop0; P.dbg_ts[2] = t_loop1; P.dbg_ts[3] = t_part;
+    }
+    BNV_STAMP(4);
     const int nblk = gridDim.x;
-    // global max score and sum: M = max_g m_g, S = sum_g exp(m_g - M) s_g
-    float lm = -FLT_MAX;
-    for (int g = tid; g < nblk; g += blockDim.x) lm = fmaxf(lm, __ldcg(P.part_ms + 2 * g));
-    lm = warp_max(lm);
-    if (lane == 0) red_s[16 + warp] = lm;
-    __syncthreads();
-    float M = red_s[16];
-    for (int w = 1; w < P.warps; ++w) M = fmaxf(M, red_s[16 + w]);
-    float lsum = 0.0f;
-    for (int g = tid; g < nblk; g += blockDim.x)
-      lsum += expf(__ldcg(P.part_ms + 2 * g) - M) * __ldcg(P.part_ms + 2 * g + 1);
-    lsum = warp_sum(lsum);
-    if (lane == 0) red_s[24 + warp] = lsum;
-    // U[c] = sum_g a_g U_g[c]: warps split g, lanes split columns; all loads independent
     const int ncol = 2 * T;
-    for (int c0 = 0; c0 < ncol; c0 += 128) {
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int g = warp; g < nblk; g += P.warps) {
-        const float a = expf(__ldcg(P.part_ms + 2 * g) - M);
-        const float* row = P.part_u + static_cast<size_t>(g) * ncol + c0;
+    float* a_s = v_s;  // per-CTA rescale factors exp(m_g - M); the v slab is dead by now
+    const int a_cap = (spb * 2 * T) / 2;
+    float* grp_s = v_s + a_cap;  // [ngrp][ncol] partial column sums
+    // Fast path (2T a multiple of 4, one float4 column unit per thread, every a_g in shared memory): everything the
+    // merge needs from other SMs -- (m_g, s_g) and this thread's share of the U_g rows -- is requested up front and
+    // consumed from registers, so the merge costs one L2 round trip.  Fixed assignment and fixed-order sums keep
+    // the result bit-reproducible.
+    constexpr int kMsCache = 8, kMergeBatch = 32;
+    const int nunit = ncol >> 2;
+    const bool fast_merge = (ncol & 3) == 0 && nunit <= static_cast<int>(blockDim.x) && nblk <= a_cap &&
+                            nblk <= kMsCache * static_cast<int>(blockDim.x);
+    int ngrp = 1;
+    if (fast_merge) {
+      ngrp = min(min(static_cast<int>(blockDim.x) / nunit, a_cap / ncol), nblk);
+      float2 ms[kMsCache];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          int c = lane + 32 * j;
-          if (c0 + c < ncol) acc[j] = fmaf(a, __ldcg(row + c), acc[j]);
+      for (int j = 0; j < kMsCache; ++j) {
+        const int g = tid + j * static_cast<int>(blockDim.x);
+        ms[j] = make_float2(-FLT_MAX, 0.0f);
+        if (g < nblk) ms[j] = __ldcg(reinterpret_cast<const float2*>(P.part_ms) + g);
+      }
+      const int unit = tid % nunit, grp = tid / nunit;
+      const int cnt = (grp < ngrp) ? (nblk - grp + ngrp - 1) / ngrp : 0;  // CTAs grp, grp + ngrp, ... owned by this thread
+      const float4* src = reinterpret_cast<const float4*>(P.part_u + static_cast<size_t>(grp) * ncol) + unit;
+      const size_t stride4 = static_cast<size_t>(ngrp) * nunit;
+      float4 pv[kMergeBatch];
+#pragma unroll
+      for (int j = 0; j < kMergeBatch; ++j) {
+        pv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < cnt) pv[j] = __ldcg(src + j * stride4);
+      }
+      float lm = -FLT_MAX;
+#pragma unroll
+      for (int j = 0; j < kMsCache; ++j) lm = fmaxf(lm, ms[j].x);
+      BNV_STAMP(12);
+      lm = warp_max(lm);
+      if (lane == 0) red_s[16 + warp] = lm;
+      __syncthreads();
+      BNV_STAMP(13);
+      M = red_s[16];
+      for (int w = 1; w < nwarps; ++w) M = fmaxf(M, red_s[16 + w]);
+      float lsum = 0.0f;
+#pragma unroll
+      for (int j = 0; j < kMsCache; ++j) {
+        const int g = tid + j * static_cast<int>(blockDim.x);
+        if (g < nblk) {
+          const float a = __expf(ms[j].x - M);
+          a_s[g] = a;
+          lsum = fmaf(a, ms[j].y, lsum);
         }
       }
-      __syncthreads();  // warpu_s reuse across c0 chunks / previous phase
+      lsum = warp_sum(lsum);
+      if (lane == 0) red_s[24 + warp] = lsum;
+      __syncthreads();
+      BNV_STAMP(14);
+      if (cnt > 0) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float* ap = a_s + grp;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        int c = lane + 32 * j;
-        if (c0 + c < ncol) warpu_s[warp * ncol + c0 + c] = acc[j];
+        for (int j = 0; j < kMergeBatch; ++j) {
+          if (j < cnt) {
+            const float a = ap[j * ngrp];
+            acc.x = fmaf(a, pv[j].x, acc.x);
+            acc.y = fmaf(a, pv[j].y, acc.y);
+            acc.z = fmaf(a, pv[j].z, acc.z);
+            acc.w = fmaf(a, pv[j].w, acc.w);
+          }
+        }
+        for (int j = kMergeBatch; j < cnt; ++j) {  // more CTAs than one batch covers (K beyond ~500k samples)
+          const float a = ap[j * ngrp];
+          const float4 v4 = __ldcg(src + j * stride4);
+          acc.x = fmaf(a, v4.x, acc.x);
+          acc.y = fmaf(a, v4.y, acc.y);
+          acc.z = fmaf(a, v4.z, acc.z);
+          acc.w = fmaf(a, v4.w, acc.w);
+        }
+        *reinterpret_cast<float4*>(grp_s + grp * ncol + unit * 4) = acc;
+      }
+    } else {
+      // general path (odd horizons, very long horizons, very many CTAs): plain loops, a_g recomputed on the fly
+      float lm = -FLT_MAX;
+      for (int g = tid; g < nblk; g += blockDim.x) lm = fmaxf(lm, __ldcg(P.part_ms + 2 * g));
+      lm = warp_max(lm);
+      if (lane == 0) red_s[16 + warp] = lm;
+      __syncthreads();
+      M = red_s[16];
+      for (int w = 1; w < nwarps; ++w) M = fmaxf(M, red_s[16 + w]);
+      float lsum = 0.0f;
+      for (int g = tid; g < nblk; g += blockDim.x)
+        lsum = fmaf(__expf(__ldcg(P.part_ms + 2 * g) - M), __ldcg(P.part_ms + 2 * g + 1), lsum);
+      lsum = warp_sum(lsum);
+      if (lane == 0) red_s[24 + warp] = lsum;
+      for (int c = tid; c < ncol; c += blockDim.x) {
+        float acc = 0.0f;
+        for (int g = 0; g < nblk; ++g)
+          acc = fmaf(__expf(__ldcg(P.part_ms + 2 * g) - M), __ldcg(P.part_u + static_cast<size_t>(g) * ncol + c), acc);
+        grp_s[c] = acc;
       }
     }
+    BNV_STAMP(15);
     __syncthreads();
-    float S = 0.0f;
-    for (int w = 0; w < P.warps; ++w) S += red_s[24 + w];
+    S = 0.0f;
+    for (int w = 0; w < nwarps; ++w) S += red_s[24 + w];
     for (int c = tid; c < ncol; c += blockDim.x) {
       float acc = 0.0f;
-      for (int w = 0; w < P.warps; ++w) acc += warpu_s[w * ncol + c];
-      uprev_s[c] = acc;  // U (un-normalised)
+      for (int gq = 0; gq < ngrp; ++gq) acc += grp_s[gq * ncol + c];
+      uprev_s[c] = (P.world == 1) ? __fdiv_rn(acc, S) : acc;  // u* = U / S (mppi.py:196-199), or U for the exchange
     }
     __syncthreads();
+    BNV_STAMP(5);
     if (tid == 0) *P.ticket = 0u;  // re-arm for the next launch
     if (P.world == 1) {
-      finish_iteration(P, win, M, S, uprev_s, sx, sy, sth);
+      for (int i = tid; i < ncol; i += blockDim.x) {
+        const float u = uprev_s[i];
+        P.u_out[i] = u;
+        P.u_prev[i] = u;  // next call's mean sequence, unshifted (mppi.py:217)
+      }
     } else {
       if (tid == 0) {
         P.shard_partial[0] = M;
@@ -445,60 +696,94 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
       }
       for (int c = tid; c < ncol; c += blockDim.x) P.shard_partial[2 + c] = uprev_s[c];
     }
+    if (coop) {  // publish (M, S) and release the other CTAs
+      if (tid == 0) {
+        P.stats[0] = M;
+        P.stats[1] = S;
+      }
+      __syncthreads();
+      if (tid == 0) st_release_gpu(P.ticket + 1, P.epoch);
+    }
+    BNV_STAMP(6);
+    if (!coop) {
+      // the other warps rescale every sample's weight underneath warp 0's serial optimal rollout:
+      // weights[k] = exp(score_k - m_cta) * exp(m_cta - M) / S (softmax, mppi.py:193; 1/S deferred when sharded)
+      const float inv_s = (P.world == 1) ? __fdiv_rn(1.0f, S) : 1.0f;
+      const bool own_thread = (P.world == 1) && blockDim.x > 32;
+      auto scale_of = [&](int g) { return fast_merge ? a_s[g] : __expf(__ldcg(P.part_ms + 2 * g) - M); };
+      if (P.world == 1 && tid == 0) optimal_rollout<kPatch, kPow2, kFastAngles>(P, C, uprev_s, sx, sy, sth);
+      BNV_STAMP(7);
+      if (!(own_thread && tid < 32)) {
+        if (!own_thread) __syncwarp();
+        rescale_weights(P.weights, P.Kl, 31 - __clz(spb), own_thread ? tid - 32 : tid,
+                        own_thread ? static_cast<int>(blockDim.x) - 32 : static_cast<int>(blockDim.x),
+                        [&](int g) { return scale_of(g) * inv_s; });
+      }
+    }
+  } else if (coop) {
+    // wait for the last CTA's merge (all CTAs are co-resident: cooperative launch), then pick up (M, S)
+    if (tid == 0) {
+      while (ld_acquire_gpu(P.ticket + 1) != P.epoch) __nanosleep(32);
+    }
+    __syncthreads();
+    M = __ldcg(P.stats);
+    S = __ldcg(P.stats + 1);
+  }
+  if (coop) {
+    // softmax weight of this thread's sample straight from registers (mppi.py:193; 1/S deferred when sharded)
+    if (valid) P.weights[k] = e * __expf(m_cta - M) * ((P.world == 1) ? __fdiv_rn(1.0f, S) : 1.0f);
+    store_slabs<kRecord, kPhilox>(P, rec_s, nz_w, warp, lane, warp_first, warp_rows, nz_bytes);
+    if (is_last && P.world == 1 && tid == 0) optimal_rollout<kPatch, kPow2, kFastAngles>(P, C, uprev_s, sx, sy, sth);
+    if (is_last) BNV_STAMP(7);
   }
   // shared memory must stay allocated until the bulk stores have read it
-  if (P.record && lane == 0) bulk_wait_read_all();
+  if (kRecord || kPhilox) bulk_wait_read_all();
+  if (is_last) BNV_STAMP_ANY(10, 32);
 }
 
 // --------------------------------------------------------------------------------------------- finalize (multi-GPU)
 // gathered: [world][2+2T] shard partials, identical on every rank -> every rank computes the same u*.
-// Block 0 runs finish_iteration for this shard (weights of the local samples, outputs, optimal rollout).
+// One CTA: merges, rescales this shard's weights (they hold exp(score - M_shard)), writes the outputs and runs
+// the optimal rollout.
+template <bool kPatch, bool kPow2, bool kFastAngles>
 __global__ void __launch_bounds__(kFinalizeThreads) finalize_kernel(const __grid_constant__ EngineParams P,
-                                                                    const float* __restrict__ gathered) {
+                                                                    const float* __restrict__ gathered, int rank) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x;
   const int T = P.T, ncol = 2 * T, plen = 2 + 2 * T;
   uint64_t* bar_patch = reinterpret_cast<uint64_t*>(smem);
   float* patch_s = reinterpret_cast<float*>(smem + 128);
-  float* u_s = patch_s + (P.use_patch ? ((P.patch_w * P.patch_h + 31) / 32) * 32 : 0);
+  float* u_s = patch_s + (kPatch ? ((P.patch_w * P.patch_h + 31) / 32) * 32 : 0);
   if (tid == 0) {
     mbar_init(bar_patch, 1);
     fence_mbar_init();
   }
   __syncthreads();
-  const float sx = P.state[0], sy = P.state[1], sth = P.state[2];
+  const float sx = __ldg(P.state), sy = __ldg(P.state + 1), sth = __ldg(P.state + 2);
   const WindowGeom wg = window_for_state(P, sx, sy);
-  TauWindow win;
-  if (P.use_patch) {
+  if (kPatch) {
     if (tid < 32) {
       if (elect_one()) {
         mbar_arrive_expect_tx(bar_patch, static_cast<uint32_t>(P.patch_w * P.patch_h * 4));
         tma_load_2d(patch_s, &P.tau_map, wg.ox, wg.oy, bar_patch);
       }
     }
-    win.base = patch_s - (wg.oy * P.patch_w + wg.ox);
-    win.pitch = P.patch_w;
-  } else {
-    win.base = P.tau;
-    win.pitch = P.pitch;
   }
-  win.lo_x = wg.lo_x;
-  win.hi_x = wg.hi_x;
-  win.lo_y = wg.lo_y;
-  win.hi_y = wg.hi_y;
-
+  StepConsts C = make_step_consts(P, wg, patch_s);
   float M = -FLT_MAX;
   for (int g = 0; g < P.world; ++g) M = fmaxf(M, gathered[g * plen]);
   float S = 0.0f;
-  for (int g = 0; g < P.world; ++g) S += expf(gathered[g * plen] - M) * gathered[g * plen + 1];
+  for (int g = 0; g < P.world; ++g) S = fmaf(__expf(gathered[g * plen] - M), gathered[g * plen + 1], S);
   for (int c = tid; c < ncol; c += blockDim.x) {
     float acc = 0.0f;
-    for (int g = 0; g < P.world; ++g) acc = fmaf(expf(gathered[g * plen] - M), gathered[g * plen + 2 + c], acc);
+    for (int g = 0; g < P.world; ++g) acc = fmaf(__expf(gathered[g * plen] - M), gathered[g * plen + 2 + c], acc);
     u_s[c] = acc;
   }
+  const float w_scale = __fdiv_rn(__expf(gathered[rank * plen] - M), S);
   __syncthreads();
-  if (P.use_patch) mbar_wait(bar_patch, 0);
-  finish_iteration(P, win, M, S, u_s, sx, sy, sth);
+  if (kPatch) mbar_wait(bar_patch, 0);
+  C.pin_all();
+  finish_iteration<kPatch, kPow2, kFastAngles>(P, C, S, w_scale, u_s, sx, sy, sth);
 }
 
 // --------------------------------------------------------------------------------------------- top-n
@@ -594,7 +879,7 @@ __global__ void gather_rows_kernel(const float* __restrict__ rec, const int* __r
 // --------------------------------------------------------------------------------------------- debug
 __global__ void sincos_debug_kernel(const float* __restrict__ th, float* __restrict__ s, float* __restrict__ c, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) sincos_heading(th[i], &s[i], &c[i]);
+  if (i < n) sincos_heading<false>(th[i], &s[i], &c[i]);
 }
 
 }  // namespace bnv

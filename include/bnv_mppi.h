@@ -129,6 +129,12 @@ int32_t bnv_mppi_sample_offset(const bnv_mppi* h); /* first global sample index 
 /* Zero the mean sequence and restart the noise stream (a fresh `MPPI(...)`, mppi.py:116). */
 int bnv_mppi_reset(bnv_mppi* h, void* stream);
 
+/* Fill the handle's noise buffer (bnv_mppi_noise) with the engine's Philox stream for the given iteration
+ * index using the stand-alone noise kernel.  bnv_mppi_forward(noise_dev = NULL) draws the same values inside the
+ * rollout kernel for iteration 0, 1, 2, ... since creation / bnv_mppi_reset; this entry point exists so that the
+ * stream can be inspected or pre-drawn. */
+int bnv_mppi_draw_noise(bnv_mppi* h, uint64_t iteration, void* stream);
+
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 uint64_t bnv_mppi_launch_count(const bnv_mppi* h);
 
@@ -137,6 +143,10 @@ uint64_t bnv_mppi_launch_count(const bnv_mppi* h);
  * the number of launches measured, and re-arms the recorder. */
 int bnv_mppi_kernel_timing(bnv_mppi* h, int32_t max_launches);
 int bnv_mppi_kernel_time(bnv_mppi* h, double* total_ms, uint64_t* launches);
+
+/* Debug hook: clock64() stamps taken by the last CTA of the most recent rollout kernel (phase boundaries;
+ * see mppi_kernels.cuh BNV_STAMP).  Only recorded when the handle was created with BNV_DEBUG_TS set. */
+int bnv_debug_timestamps(bnv_mppi* h, long long out[16]);
 
 /* Test hook: evaluates the engine's in-range sin/cos (used by the state update in place of
  * torch.cos/torch.sin, robot_model.py:86-87) on n device floats. */

@@ -1,0 +1,30 @@
+"""Print clock64 phase stamps of the last CTA of the rollout kernel (debug aid; BNV_DEBUG_TS=1)."""
+import ctypes as C
+import os
+import sys
+
+os.environ["BNV_DEBUG_TS"] = "1"
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from benchnav_b200 import MPPI, _cabi
+from benchnav_b200.problem import GoalObjectives, GridSpec, UnicycleProblem
+from benchnav_b200.synthetic import benchmark_problem
+
+K, T, G = int(sys.argv[1]) if len(sys.argv) > 1 else 16384, 50, 256
+risk, start, goal, thr = benchmark_problem(G, 0.5, seed=0)
+dyn = UnicycleProblem(GridSpec(G, 0.5), risk)
+s = MPPI(T, K, 3, 2, dyn, GoalObjectives(dyn, goal, thr), torch.tensor([0.5, 0.5]), 0.5, device=torch.device("cuda"))
+st = start.cuda()
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+names = ["start", "loop0", "loop1", "partial", "last:enter", "last:merged", "last:u_out", "last:opt_done", "last:w_begin",
+         "last:w_done", "last:exit", "m:fence", "m:ms_loaded", "m:M_sync", "m:S_sync", "m:fma_done"]
+for it in range(6):
+    if it >= 3:
+        flush.fill_(it)
+    s.forward(st)
+    torch.cuda.synchronize()
+    ts = (C.c_longlong * 16)()
+    _cabi.check(s._lib.bnv_debug_timestamps(s._handle, ts))
+    t0 = ts[0]
+    print(("cold " if it >= 3 else "warm ") + " ".join(f"{n}={ts[i] - t0}" for i, n in enumerate(names)))

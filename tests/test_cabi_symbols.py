@@ -40,9 +40,15 @@ def test_sm100a_only_sass_with_tma_and_bulk_copies():
     """The shipped cubin is sm_100a and the rollout kernel really uses TMA (UTMALDG) and bulk copies (UBLKCP)."""
     sass = subprocess.run(["cuobjdump", "-sass", build.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in sass
-    body = sass[sass.index("rollout_kernel"):]
-    body = body[: body.index("Function :", 10)] if "Function :" in body[10:] else body
-    assert "UTMALDG.2D" in body and "UBLKCP" in body
+    funcs = sass.split("Function : ")[1:]
+    rollouts = [f for f in funcs if "rollout_kernel" in f.splitlines()[0]]
+    assert len(rollouts) == 32  # kPatch x kPow2 x kRecord x kFastAngles x kPhilox
+    for f in rollouts:
+        name = f.splitlines()[0]
+        patch = "rollout_kernelILb1E" in name
+        assert ("UTMALDG.2D" in f) == patch, name  # the TMA window load exists exactly in the kPatch variants
+        assert "UBLKCP" in f, name                 # bulk slab copies
+        assert "HMMA" not in f and "UTCHMMA" not in f  # no tensor cores on this path
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-box behaviour")

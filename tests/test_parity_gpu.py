@@ -248,6 +248,24 @@ def test_philox_noise_statistics_and_determinism():
     assert not torch.equal(c._action_noises, na)
 
 
+def test_in_loop_noise_equals_standalone_noise_kernel():
+    """The noise drawn inside the rollout loop is bit-identical to the stand-alone noise kernel's stream
+    (bnv_mppi_draw_noise) for the same (seed, iteration), including an odd horizon and a ragged sample count."""
+    from benchnav_b200 import _cabi
+    from benchnav_b200.synthetic import benchmark_problem
+
+    risk, start, goal, thr = benchmark_problem(64, 0.5, seed=0)
+    for K, T in ((4099, 50), (777, 7), (33, 1)):
+        s = make_solver(risk, 0.5, goal, thr, K, T, [0.5, 0.25], 0.5, seed=1234)
+        for it in range(3):
+            s.forward(start)
+            torch.cuda.synchronize()
+            in_loop = s._action_noises.clone()
+            _cabi.check(s._lib.bnv_mppi_draw_noise(s._handle, it, None))
+            torch.cuda.synchronize()
+            assert torch.equal(s._action_noises, in_loop), (K, T, it)
+
+
 def test_philox_iteration_against_oracle_with_its_own_noise():
     """Production mode: noise drawn in-engine; the oracle replays the same noise."""
     from benchnav_b200.synthetic import benchmark_problem
