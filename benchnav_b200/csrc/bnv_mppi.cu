@@ -358,7 +358,7 @@ int bnv_mppi_set_problem(bnv_mppi* h, const float* risk_dev, int32_t grid_size, 
   }
   int rc = configure_launch(h);
   if (rc != BNV_OK) return rc;
-  h->finalize_smem = 128 + (P.use_patch ? ((P.patch_w * P.patch_h + 31) / 32) * 32 * 4 : 0) + 2 * P.T * 4 + 16;
+  h->finalize_smem = 128 + (P.use_patch ? ((P.patch_w * P.patch_h + 31) / 32) * 32 * 4 : 0) + 2 * (2 * P.T + 4) * 4 + 16;
   for (bool philox : {false, true})
     BNV_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(pick_rollout(h, philox)),
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h->rollout_smem)));
@@ -401,7 +401,7 @@ static int launch_forward(bnv_mppi* h, const float* state_dev, const float* nois
   attr[0].id = cudaLaunchAttributeCooperative;
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = coop ? 1 : 0;
+  cfg.numAttrs = (coop && !(debug_disable() & 128u)) ? 1 : 0;  // bit 128: measurement aid, plain launch of the coop path
   BNV_CUDA(cudaLaunchKernelEx(&cfg, pick_rollout(h, philox), P));
   if (timed) {
     BNV_CUDA(cudaEventRecord(h->ev[h->ev_used + 1], s));

@@ -94,7 +94,7 @@ __host__ __device__ inline RolloutSmem rollout_smem_layout(int T, int warps, int
   s.off_uprev = off;
   off += ((2 * T * 4 + 15) / 16) * 16;
   s.off_coef = off;
-  off += ((2 * T * 4 + 15) / 16) * 16;
+  off += 4 * T * 4;  // float4 per step
   s.off_e = off;
   off += spb * 4;
   s.off_warpu = off;
@@ -202,22 +202,24 @@ __device__ __forceinline__ float score_of(float cost, const EngineParams& P) {
 }
 
 // Batch-1 optimal rollout (mppi.py:202-214) by one thread: first step with the general math, the rest fast.
+// `uc_s` holds u* already clamped to the action bounds: transit re-clamps the action (robot_model.py:82-83) and
+// u*, a rounded weighted sum, may leave the bounds by an ulp.
 template <bool kPatch, bool kPow2, bool kFastAngles>
-__device__ void optimal_rollout(const EngineParams& P, const StepConsts& c, const float* u_s, float sx, float sy,
+__device__ void optimal_rollout(const EngineParams& P, const StepConsts& c, const float* uc_s, float sx, float sy,
                                 float sth) {
   const int T = P.T;
   float x = sx, y = sy, th = sth, xr, yr, thr;
   float tau = lookup_tau<kPatch, kPow2, false>(c, x, y);
-  // transit re-clamps the action (robot_model.py:82-83): u* is a rounded weighted sum and may leave the bounds by an ulp
-  unicycle_step<false>(c, tau, clampf(u_s[0], c.u_min0, c.u_max0), clampf(u_s[1], c.u_min1, c.u_max1), x, y, th, xr, yr,
-                       thr);
+  const float2* u2 = reinterpret_cast<const float2*>(uc_s);
+  float2 u = u2[0];
+  unicycle_step<false>(c, tau, u.x, u.y, x, y, th, xr, yr, thr);
   float* out = P.opt_rec;
   out[0] = xr; out[1] = yr; out[2] = thr;
 #pragma unroll 2
   for (int t = 1; t < T; ++t) {
     tau = lookup_tau<kPatch, kPow2, true>(c, x, y);
-    unicycle_step<kFastAngles>(c, tau, clampf(u_s[2 * t], c.u_min0, c.u_max0),
-                               clampf(u_s[2 * t + 1], c.u_min1, c.u_max1), x, y, th, xr, yr, thr);
+    u = u2[t];
+    unicycle_step<kFastAngles>(c, tau, u.x, u.y, x, y, th, xr, yr, thr);
     out[3 * t + 0] = xr; out[3 * t + 1] = yr; out[3 * t + 2] = thr;
   }
   out[3 * T + 0] = x; out[3 * T + 1] = y; out[3 * T + 2] = th;
@@ -258,14 +260,16 @@ __device__ void finish_iteration(const EngineParams& P, const StepConsts& c, flo
                                  float sx, float sy, float sth) {
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int T = P.T;
+  float* uc_s = u_s + ((2 * T + 3) & ~3);  // clamped copy for the optimal rollout
   for (int i = tid; i < 2 * T; i += nthr) {
     float u = __fdiv_rn(u_s[i], S);
     u_s[i] = u;
+    uc_s[i] = clampf(u, (i & 1) ? c.u_min1 : c.u_min0, (i & 1) ? c.u_max1 : c.u_max0);
     P.u_out[i] = u;
     P.u_prev[i] = u;
   }
   __syncthreads();
-  if (tid == 0) optimal_rollout<kPatch, kPow2, kFastAngles>(P, c, u_s, sx, sy, sth);
+  if (tid == 0) optimal_rollout<kPatch, kPow2, kFastAngles>(P, c, uc_s, sx, sy, sth);
   // With more than one warp the serial optimal rollout keeps warp 0 busy and the other warps rescale underneath it.
   const bool split = nthr > 32;
   if (split && tid < 32) return;
@@ -318,16 +322,16 @@ __device__ __forceinline__ void st_release_gpu(unsigned int* p, unsigned int v) 
 // One rollout step of one sample (mppi.py:152-165, :174-182): control from mean + noise, unicycle step, recorded
 // state, shared lookup for the stage cost and the next step, cost accumulation.
 struct SampleState {
-  float x, y, th, tau, stage_sum, act_sum;
+  float x, y, th, tau, stage_sum, act0, act1;
 };
 
+// ucf_s[t] = (u_prev[t][0], u_prev[t][1], u_prev[t][0] / sigma0^2, u_prev[t][1] / sigma1^2): one 16-byte load per step.
 template <bool kPatch, bool kPow2, bool kRecord, bool kFastStep>
 __device__ __forceinline__ void sample_step(SampleState& s, const StepConsts& C, int t, float nx, float ny,
-                                            const float* uprev_s, const float* coef_s, float* vrow, float* rrow) {
-  const float2 up = *reinterpret_cast<const float2*>(uprev_s + 2 * t);
-  const float2 cf = *reinterpret_cast<const float2*>(coef_s + 2 * t);
-  const float v0 = clampf(__fadd_rn(up.x, nx), C.u_min0, C.u_max0);  // mppi.py:152-157
-  const float v1 = clampf(__fadd_rn(up.y, ny), C.u_min1, C.u_max1);
+                                            const float4* ucf_s, float* vrow, float* rrow) {
+  const float4 uc = ucf_s[t];
+  const float v0 = clampf(__fadd_rn(uc.x, nx), C.u_min0, C.u_max0);  // mppi.py:152-157
+  const float v1 = clampf(__fadd_rn(uc.y, ny), C.u_min1, C.u_max1);
   *reinterpret_cast<float2*>(vrow + 2 * t) = make_float2(v0, v1);    // kept for the weighted control sum
   float xr, yr, thr;
   unicycle_step<kFastStep>(C, s.tau, v0, v1, s.x, s.y, s.th, xr, yr, thr);
@@ -339,7 +343,8 @@ __device__ __forceinline__ void sample_step(SampleState& s, const StepConsts& C,
   // one lookup serves the stage cost of the recorded (raw) position and the next dynamics step
   s.tau = lookup_tau<kPatch, kPow2, true>(C, s.x, s.y);
   s.stage_sum = __fadd_rn(s.stage_sum, goal_and_stuck_cost(C, xr, yr, s.tau));
-  s.act_sum = __fadd_rn(s.act_sum, fmaf(cf.x, v0, __fmul_rn(cf.y, v1)));  // mppi.py:178-182
+  s.act0 = fmaf(uc.z, v0, s.act0);  // u_prev[t]^T Sigma^-1 v (mppi.py:178-182), one running sum per control dim
+  s.act1 = fmaf(uc.w, v1, s.act1);
 }
 
 // kPatch: traversability window staged in shared memory by TMA (else looked up in the global map);
@@ -425,8 +430,11 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
   for (int i = tid; i < 2 * T; i += blockDim.x) {
     const float u = P.u_prev[i];
     uprev_s[i] = u;
-    coef_s[i] = __fmul_rn(u, (i & 1) ? P.icov1 : P.icov0);
+    float* uc = coef_s + 4 * (i >> 1) + (i & 1);
+    uc[0] = u;
+    uc[2] = __fmul_rn(u, (i & 1) ? P.icov1 : P.icov0);
   }
+  const float4* ucf_s = reinterpret_cast<const float4*>(coef_s);
   __syncthreads();
   if (kPatch) mbar_wait(bar_patch, 0);
   if (!kPhilox) {
@@ -445,7 +453,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
   float* rrow = rec_s + (warp * 32 + lane) * 3 * (T + 1);
   if (valid) {
     SampleState s;
-    s.x = sx; s.y = sy; s.th = sth; s.stage_sum = 0.0f; s.act_sum = 0.0f;
+    s.x = sx; s.y = sy; s.th = sth; s.stage_sum = 0.0f; s.act0 = 0.0f; s.act1 = 0.0f;
     s.tau = lookup_tau<kPatch, kPow2, false>(C, s.x, s.y);
     // Steps are processed in pairs (one Philox call yields both steps' noise).  The pair after the current one is
     // drawn in the same straight-line block as the current pair's steps -- unconditionally, so that there is no
@@ -471,16 +479,16 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
         *reinterpret_cast<float2*>(nrow) = make_float2(nz.x, nz.y);
         *reinterpret_cast<float2*>(nrow + 2) = make_float2(nz.z, nz.w);
       }
-      sample_step<kPatch, kPow2, kRecord, false>(s, C, 0, nz.x, nz.y, uprev_s, coef_s, vrow, rrow);
-      sample_step<kPatch, kPow2, kRecord, kFastAngles>(s, C, 1, nz.z, nz.w, uprev_s, coef_s, vrow, rrow);
+      sample_step<kPatch, kPow2, kRecord, false>(s, C, 0, nz.x, nz.y, ucf_s, vrow, rrow);
+      sample_step<kPatch, kPow2, kRecord, kFastAngles>(s, C, 1, nz.z, nz.w, ucf_s, vrow, rrow);
       for (int p = 1; p < nfull; ++p) {
         const float4 nq = fetch_pair(p);
         if (kPhilox) {
           *reinterpret_cast<float2*>(nrow + 4 * p) = make_float2(nq.x, nq.y);
           *reinterpret_cast<float2*>(nrow + 4 * p + 2) = make_float2(nq.z, nq.w);
         }
-        sample_step<kPatch, kPow2, kRecord, kFastAngles>(s, C, 2 * p, nq.x, nq.y, uprev_s, coef_s, vrow, rrow);
-        sample_step<kPatch, kPow2, kRecord, kFastAngles>(s, C, 2 * p + 1, nq.z, nq.w, uprev_s, coef_s, vrow, rrow);
+        sample_step<kPatch, kPow2, kRecord, kFastAngles>(s, C, 2 * p, nq.x, nq.y, ucf_s, vrow, rrow);
+        sample_step<kPatch, kPow2, kRecord, kFastAngles>(s, C, 2 * p + 1, nq.z, nq.w, ucf_s, vrow, rrow);
       }
     }
     if (T & 1) {  // last (or only) step of an odd horizon: first half of pair nfull
@@ -491,12 +499,12 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
       } else {
         nl = *reinterpret_cast<const float2*>(nrow + 4 * nfull);
       }
-      if (nfull == 0) sample_step<kPatch, kPow2, kRecord, false>(s, C, 0, nl.x, nl.y, uprev_s, coef_s, vrow, rrow);
-      else sample_step<kPatch, kPow2, kRecord, kFastAngles>(s, C, T - 1, nl.x, nl.y, uprev_s, coef_s, vrow, rrow);
+      if (nfull == 0) sample_step<kPatch, kPow2, kRecord, false>(s, C, 0, nl.x, nl.y, ucf_s, vrow, rrow);
+      else sample_step<kPatch, kPow2, kRecord, kFastAngles>(s, C, T - 1, nl.x, nl.y, ucf_s, vrow, rrow);
     }
     if (kRecord) { rrow[3 * T + 0] = s.x; rrow[3 * T + 1] = s.y; rrow[3 * T + 2] = s.th; }
     const float terminal = goal_and_stuck_cost(C, s.x, s.y, s.tau);                            // mppi.py:184
-    cost = __fadd_rn(__fadd_rn(s.stage_sum, terminal), __fmul_rn(P.lambda, s.act_sum));         // mppi.py:186-190
+    cost = __fadd_rn(__fadd_rn(s.stage_sum, terminal), __fmul_rn(P.lambda, s.act0 + s.act1));   // mppi.py:186-190
     P.costs[k] = cost;
   }
   const long long t_loop1 = clock64();
@@ -675,10 +683,17 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
     __syncthreads();
     S = 0.0f;
     for (int w = 0; w < nwarps; ++w) S += red_s[24 + w];
+    if (coop && tid == 0) {  // publish (M, S) and release the waiting CTAs as early as possible
+      P.stats[0] = M;
+      P.stats[1] = S;
+      st_release_gpu(P.ticket + 1, P.epoch);
+    }
     for (int c = tid; c < ncol; c += blockDim.x) {
       float acc = 0.0f;
       for (int gq = 0; gq < ngrp; ++gq) acc += grp_s[gq * ncol + c];
-      uprev_s[c] = (P.world == 1) ? __fdiv_rn(acc, S) : acc;  // u* = U / S (mppi.py:196-199), or U for the exchange
+      const float u = (P.world == 1) ? __fdiv_rn(acc, S) : acc;  // u* = U / S (mppi.py:196-199), or U for the exchange
+      uprev_s[c] = u;
+      warpu_s[c] = clampf(u, (c & 1) ? C.u_min1 : C.u_min0, (c & 1) ? C.u_max1 : C.u_max0);  // for the optimal rollout
     }
     __syncthreads();
     BNV_STAMP(5);
@@ -696,14 +711,6 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
       }
       for (int c = tid; c < ncol; c += blockDim.x) P.shard_partial[2 + c] = uprev_s[c];
     }
-    if (coop) {  // publish (M, S) and release the other CTAs
-      if (tid == 0) {
-        P.stats[0] = M;
-        P.stats[1] = S;
-      }
-      __syncthreads();
-      if (tid == 0) st_release_gpu(P.ticket + 1, P.epoch);
-    }
     BNV_STAMP(6);
     if (!coop) {
       // the other warps rescale every sample's weight underneath warp 0's serial optimal rollout:
@@ -711,7 +718,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
       const float inv_s = (P.world == 1) ? __fdiv_rn(1.0f, S) : 1.0f;
       const bool own_thread = (P.world == 1) && blockDim.x > 32;
       auto scale_of = [&](int g) { return fast_merge ? a_s[g] : __expf(__ldcg(P.part_ms + 2 * g) - M); };
-      if (P.world == 1 && tid == 0) optimal_rollout<kPatch, kPow2, kFastAngles>(P, C, uprev_s, sx, sy, sth);
+      if (P.world == 1 && tid == 0) optimal_rollout<kPatch, kPow2, kFastAngles>(P, C, warpu_s, sx, sy, sth);
       BNV_STAMP(7);
       if (!(own_thread && tid < 32)) {
         if (!own_thread) __syncwarp();
@@ -733,7 +740,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
     // softmax weight of this thread's sample straight from registers (mppi.py:193; 1/S deferred when sharded)
     if (valid) P.weights[k] = e * __expf(m_cta - M) * ((P.world == 1) ? __fdiv_rn(1.0f, S) : 1.0f);
     store_slabs<kRecord, kPhilox>(P, rec_s, nz_w, warp, lane, warp_first, warp_rows, nz_bytes);
-    if (is_last && P.world == 1 && tid == 0) optimal_rollout<kPatch, kPow2, kFastAngles>(P, C, uprev_s, sx, sy, sth);
+    if (is_last && P.world == 1 && tid == 0) optimal_rollout<kPatch, kPow2, kFastAngles>(P, C, warpu_s, sx, sy, sth);
     if (is_last) BNV_STAMP(7);
   }
   // shared memory must stay allocated until the bulk stores have read it

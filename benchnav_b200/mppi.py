@@ -191,7 +191,11 @@ class MPPI(nn.Module):
         assert state.shape == (self._dim_state,)
         self._sync_problem()
         with torch.cuda.device(self._device):
-            self._state_dev.copy_(state.detach(), non_blocking=True)
+            if (state.device == self._device and state.dtype == torch.float32 and state.is_contiguous()):
+                state_dev = state.detach()  # already resident: the engine reads it in place (stream-ordered)
+            else:
+                self._state_dev.copy_(state.detach(), non_blocking=True)
+                state_dev = self._state_dev
             if noise is not None:
                 if noise.shape != (self._local_samples, self._horizon, 2):
                     raise ValueError(f"noise must have shape {(self._local_samples, self._horizon, 2)}")
@@ -204,7 +208,7 @@ class MPPI(nn.Module):
             u_opt = torch.empty(self._horizon, 2, device=self._device, dtype=torch.float32)
             opt_states = torch.empty(1, self._horizon + 1, 3, device=self._device, dtype=torch.float32)
             stream = self._stream()
-            _cabi.check(self._lib.bnv_mppi_forward(self._handle, self._state_dev.data_ptr(),
+            _cabi.check(self._lib.bnv_mppi_forward(self._handle, state_dev.data_ptr(),
                                                    noise.data_ptr() if noise is not None else None,
                                                    u_opt.data_ptr(), opt_states.data_ptr(), stream))
             if self._shard.world_size > 1:
