@@ -207,7 +207,7 @@ def run_native(args) -> None:
     dyn = UnicycleProblem(GridSpec(grid, RESOLUTION), risk)
     obj = GoalObjectives(dyn, goal, thr)
     solver = MPPI(HORIZON, k_total, 3, 2, dyn, obj, torch.tensor(SIGMAS), LAMBDA, device=dev, seed=SEED,
-                  process_group=group)
+                  process_group=group, exchange=args.exchange)
     state_dev = start.to(dev)
     state_pinned = start.clone().pin_memory()
     flush = torch.empty(FLUSH_BYTES, dtype=torch.uint8, device=dev)
@@ -300,7 +300,9 @@ def run_native(args) -> None:
         "config": {"workload": f"BASELINE configs[1]: {grid}x{grid} synthetic terrain, K={K_PER_GPU} samples/GPU "
                                f"(total {k_total}), T={HORIZON}, full contract (in-engine Philox noise kept, recorded "
                                f"states + weights written)",
-                   "grid": grid, "num_samples_total": k_total, "horizon": HORIZON, "parallelism": f"sample-shard x{world}",
+                   "grid": grid, "num_samples_total": k_total, "horizon": HORIZON, "parallelism": f"sample-shard x{world}" + ("" if world == 1 else
+                                   (", fused P2P mailbox exchange in-kernel" if solver._fused_exchange else
+                                    ", NCCL all-gather + finalize kernel")),
                    "l2": "flushed between timed steps (256 MiB write); per-step CUDA-event pairs",
                    "control_iters_per_sec": control_rate, "back_to_back_ms_per_step": hot_ms,
                    "rollout_steps_per_sec": control_rate * k_total * HORIZON},
@@ -329,6 +331,8 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=20000)
     ap.add_argument("--warmup", type=int, default=100)
     ap.add_argument("--impl", choices=("native", "reference"), default="native")
+    ap.add_argument("--exchange", choices=("p2p", "nccl"), default="p2p",
+                    help="multi-GPU softmax exchange: fused over NVLink peer memory (default) or NCCL all-gather")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -54,7 +54,10 @@ _SIGNATURES = {
     "bnv_mppi_set_problem": (C.c_int, [_VP, _VP, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float,
                                        C.c_float, C.POINTER(C.c_float), C.c_float, _VP]),
     "bnv_mppi_forward": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP]),
+    "bnv_mppi_forward_state": (C.c_int, [_VP, C.POINTER(C.c_float), _VP, _VP, _VP, _VP]),
     "bnv_mppi_forward_host": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP]),
+    "bnv_mppi_mailbox_handle": (C.c_int, [_VP, C.POINTER(C.c_ubyte)]),
+    "bnv_mppi_attach_peers": (C.c_int, [_VP, C.POINTER(C.c_ubyte)]),
     "bnv_mppi_partial": (_VP, [_VP]),
     "bnv_mppi_partial_len": (C.c_int32, [_VP]),
     "bnv_mppi_finalize": (C.c_int, [_VP, _VP, _VP, _VP, _VP]),

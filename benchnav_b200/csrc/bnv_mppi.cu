@@ -98,6 +98,13 @@ struct bnv_mppi {
   int num_sms = 0;
   bool coop_ok = true;
   long long* dbg_ts = nullptr;
+  // fused multi-GPU exchange: this rank's mailbox, the peers' mailboxes mapped through CUDA IPC
+  float* mbox = nullptr;
+  size_t mbox_floats = 0;
+  std::vector<void*> peer_ptrs;       // host copy; entry [rank] is mbox itself
+  float** peer_mbox_dev = nullptr;    // device array of the same pointers
+  bool peers_attached = false;
+  unsigned int xchg_seq = 0;
   int* top_idx = nullptr;
   unsigned long long* top_pairs = nullptr;
   size_t top_pairs_cap = 0, top_idx_cap = 0;
@@ -127,6 +134,10 @@ void free_all(bnv_mppi* h) {
   cudaFree(h->ticket);
   cudaFree(h->stats);
   cudaFree(h->dbg_ts);
+  for (size_t r = 0; r < h->peer_ptrs.size(); ++r)
+    if (h->peers_attached && static_cast<int>(r) != h->cfg.rank && h->peer_ptrs[r]) cudaIpcCloseMemHandle(h->peer_ptrs[r]);
+  cudaFree(h->peer_mbox_dev);
+  cudaFree(h->mbox);
   cudaFree(h->top_idx);
   cudaFree(h->top_pairs);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
@@ -231,7 +242,13 @@ int bnv_mppi_create(bnv_mppi** out, const bnv_mppi_cfg* cfg) {
   alloc(reinterpret_cast<void**>(&h->io_dev), sizeof(float) * io_floats);
   alloc(reinterpret_cast<void**>(&h->ticket), 2 * sizeof(unsigned int));
   alloc(reinterpret_cast<void**>(&h->stats), 4 * sizeof(float));
-  if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&h->io_host), sizeof(float) * io_floats);
+  if (cfg->world_size > 1) {  // mailbox: 2 parities x world slots x (m, s, U[2T], flag, pad)
+    h->mbox_floats = 2 * static_cast<size_t>(cfg->world_size) * (2 + 2 * static_cast<size_t>(T) + 2);
+    alloc(reinterpret_cast<void**>(&h->mbox), sizeof(float) * h->mbox_floats);
+    alloc(reinterpret_cast<void**>(&h->peer_mbox_dev), sizeof(float*) * cfg->world_size);
+    if (e == cudaSuccess) e = cudaMemset(h->mbox, 0, sizeof(float) * h->mbox_floats);
+  }
+  if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&h->io_host), sizeof(float) * io_floats, cudaHostAllocMapped);
   if (e == cudaSuccess) e = cudaMemset(h->u_prev, 0, sizeof(float) * T * 2);  // mppi.py:116
   if (e == cudaSuccess) e = cudaMemset(h->ticket, 0, 2 * sizeof(unsigned int));
   if (e == cudaSuccess) e = cudaMemset(h->weights, 0, sizeof(float) * Kl);    // mppi.py:126-128
@@ -256,6 +273,8 @@ int bnv_mppi_create(bnv_mppi** out, const bnv_mppi_cfg* cfg) {
   P.seed_lo = static_cast<uint32_t>(cfg->seed);
   P.seed_hi = static_cast<uint32_t>(cfg->seed >> 32);
   P.k_offset = h->k_offset;
+  P.rank = cfg->rank;
+  P.peer_mbox = nullptr;
   P.Kl = Kl;
   P.T = T;
   P.world = cfg->world_size;
@@ -368,8 +387,14 @@ int bnv_mppi_set_problem(bnv_mppi* h, const float* risk_dev, int32_t grid_size, 
   return BNV_OK;
 }
 
-static int launch_forward(bnv_mppi* h, const float* state_dev, const float* noise_dev, float* u_out_dev,
-                          float* opt_states_dev, cudaStream_t s) {
+static int launch_forward(bnv_mppi* h, const float* state_dev, const float* state_host, const float* noise_dev,
+                          float* u_out_dev, float* opt_states_dev, cudaStream_t s) {
+  if (state_host) {  // state travels by value in the launch packet; remembered for finalize (world_size > 1)
+    for (int i = 0; i < 3; ++i) h->P.state_val[i] = state_host[i];
+    h->P.state_inline = 1;
+  } else {
+    h->P.state_inline = 0;
+  }
   bnv::EngineParams P = h->P;
   const bool philox = noise_dev == nullptr;
   P.noise_in = noise_dev;
@@ -390,6 +415,11 @@ static int launch_forward(bnv_mppi* h, const float* state_dev, const float* nois
   h->epoch = (h->epoch == 0xFFFFFFFFu) ? 1u : h->epoch + 1u;
   P.epoch = h->epoch;
   P.coop = coop ? 1 : 0;
+  if (h->peers_attached) {
+    h->xchg_seq = (h->xchg_seq == 0xFFFFFFFFu) ? 1u : h->xchg_seq + 1u;  // advances in lock-step on every rank
+    P.xchg_seq = h->xchg_seq;
+    P.peer_mbox = h->peer_mbox_dev;
+  }
   const bool timed = h->timing && h->ev_used + 2 <= h->ev.size();
   if (timed) BNV_CUDA(cudaEventRecord(h->ev[h->ev_used], s));
   cudaLaunchConfig_t cfg{};
@@ -409,7 +439,7 @@ static int launch_forward(bnv_mppi* h, const float* state_dev, const float* nois
   }
   h->launches++;
   if (philox) h->iteration++;
-  h->have_weights = (P.world == 1);
+  h->have_weights = (P.world == 1) || h->peers_attached;
   return BNV_OK;
 }
 
@@ -417,9 +447,20 @@ int bnv_mppi_forward(bnv_mppi* h, const float* state_dev, const float* noise_dev
                      float* opt_states_dev, void* stream) {
   if (!h || !state_dev) return fail(BNV_ERR_INVALID, "null argument");
   if (!h->problem_set) return fail(BNV_ERR_STATE, "bnv_mppi_set_problem must be called before forward");
-  if (h->cfg.world_size == 1 && (!u_out_dev || !opt_states_dev)) return fail(BNV_ERR_INVALID, "null output buffer");
+  if ((h->cfg.world_size == 1 || h->peers_attached) && (!u_out_dev || !opt_states_dev))
+    return fail(BNV_ERR_INVALID, "null output buffer");
   BNV_CUDA(cudaSetDevice(h->cfg.device));
-  return launch_forward(h, state_dev, noise_dev, u_out_dev, opt_states_dev, static_cast<cudaStream_t>(stream));
+  return launch_forward(h, state_dev, nullptr, noise_dev, u_out_dev, opt_states_dev, static_cast<cudaStream_t>(stream));
+}
+
+int bnv_mppi_forward_state(bnv_mppi* h, const float state_host[3], const float* noise_dev, float* u_out_dev,
+                           float* opt_states_dev, void* stream) {
+  if (!h || !state_host) return fail(BNV_ERR_INVALID, "null argument");
+  if (!h->problem_set) return fail(BNV_ERR_STATE, "bnv_mppi_set_problem must be called before forward");
+  if ((h->cfg.world_size == 1 || h->peers_attached) && (!u_out_dev || !opt_states_dev))
+    return fail(BNV_ERR_INVALID, "null output buffer");
+  BNV_CUDA(cudaSetDevice(h->cfg.device));
+  return launch_forward(h, nullptr, state_host, noise_dev, u_out_dev, opt_states_dev, static_cast<cudaStream_t>(stream));
 }
 
 int bnv_mppi_forward_host(bnv_mppi* h, const float state_host[3], const float* noise_dev, float* u_out_host,
@@ -430,15 +471,55 @@ int bnv_mppi_forward_host(bnv_mppi* h, const float state_host[3], const float* n
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   BNV_CUDA(cudaSetDevice(h->cfg.device));
   const int T = h->P.T;
-  const size_t n_out = 2 * static_cast<size_t>(T) + 3 * static_cast<size_t>(T + 1);
-  std::memcpy(h->io_host, state_host, 3 * sizeof(float));
-  BNV_CUDA(cudaMemcpyAsync(h->io_dev, h->io_host, 3 * sizeof(float), cudaMemcpyHostToDevice, s));
-  int rc = launch_forward(h, h->io_dev, noise_dev, h->io_dev + 3, h->io_dev + 3 + 2 * T, s);
+  // Host -> device: the 12-byte state rides in the kernel's launch packet.  Device -> host: the kernel stores u* and
+  // the optimal state sequence straight into the handle's pinned, device-mapped staging buffer (zero-copy over
+  // PCIe); one stream synchronisation makes them visible, then they are copied out to the caller's buffers.
+  float* out_dev = nullptr;
+  BNV_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&out_dev), h->io_host, 0));
+  int rc = launch_forward(h, nullptr, state_host, noise_dev, out_dev + 3, out_dev + 3 + 2 * T, s);
   if (rc != BNV_OK) return rc;
-  BNV_CUDA(cudaMemcpyAsync(h->io_host + 3, h->io_dev + 3, n_out * sizeof(float), cudaMemcpyDeviceToHost, s));
   BNV_CUDA(cudaStreamSynchronize(s));
   std::memcpy(u_out_host, h->io_host + 3, 2 * static_cast<size_t>(T) * sizeof(float));
   std::memcpy(opt_states_host, h->io_host + 3 + 2 * T, 3 * static_cast<size_t>(T + 1) * sizeof(float));
+  return BNV_OK;
+}
+
+int bnv_mppi_mailbox_handle(bnv_mppi* h, unsigned char out[64]) {
+  if (!h || !out) return fail(BNV_ERR_INVALID, "null argument");
+  if (!h->mbox) return fail(BNV_ERR_STATE, "no mailbox: world_size is 1");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+  BNV_CUDA(cudaSetDevice(h->cfg.device));
+  cudaIpcMemHandle_t hd;
+  BNV_CUDA(cudaIpcGetMemHandle(&hd, h->mbox));
+  std::memcpy(out, &hd, 64);
+  return BNV_OK;
+}
+
+int bnv_mppi_attach_peers(bnv_mppi* h, const unsigned char* handles) {
+  if (!h || !handles) return fail(BNV_ERR_INVALID, "null argument");
+  if (!h->mbox) return fail(BNV_ERR_STATE, "no mailbox: world_size is 1");
+  if (h->peers_attached) return fail(BNV_ERR_STATE, "peers already attached");
+  BNV_CUDA(cudaSetDevice(h->cfg.device));
+  const int W = h->cfg.world_size;
+  h->peer_ptrs.assign(W, nullptr);
+  for (int r = 0; r < W; ++r) {
+    if (r == h->cfg.rank) {
+      h->peer_ptrs[r] = h->mbox;
+      continue;
+    }
+    cudaIpcMemHandle_t hd;
+    std::memcpy(&hd, handles + 64 * static_cast<size_t>(r), 64);
+    cudaError_t e = cudaIpcOpenMemHandle(&h->peer_ptrs[r], hd, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      for (int q = 0; q < r; ++q)
+        if (q != h->cfg.rank && h->peer_ptrs[q]) cudaIpcCloseMemHandle(h->peer_ptrs[q]);
+      h->peer_ptrs.clear();
+      return fail(BNV_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(e));
+    }
+  }
+  BNV_CUDA(cudaMemcpy(h->peer_mbox_dev, h->peer_ptrs.data(), sizeof(float*) * W, cudaMemcpyHostToDevice));
+  h->peers_attached = true;
+  h->xchg_seq = 0;
   return BNV_OK;
 }
 
@@ -448,8 +529,9 @@ int32_t bnv_mppi_partial_len(const bnv_mppi* h) { return h ? 2 + 2 * h->P.T : 0;
 int bnv_mppi_finalize(bnv_mppi* h, const float* gathered_partials_dev, float* u_out_dev, float* opt_states_dev,
                       void* stream) {
   if (!h || !gathered_partials_dev || !u_out_dev || !opt_states_dev) return fail(BNV_ERR_INVALID, "null argument");
-  if (!h->problem_set || h->iteration == 0) return fail(BNV_ERR_STATE, "finalize needs a preceding forward");
-  if (!h->P.state) return fail(BNV_ERR_STATE, "finalize needs a preceding forward");
+  if (h->peers_attached) return fail(BNV_ERR_STATE, "peers attached: forward already exchanged and finalised");
+  if (!h->problem_set) return fail(BNV_ERR_STATE, "finalize needs a preceding forward");
+  if (!h->P.state && !h->P.state_inline) return fail(BNV_ERR_STATE, "finalize needs a preceding forward");
   BNV_CUDA(cudaSetDevice(h->cfg.device));
   bnv::EngineParams P = h->P;
   P.u_out = u_out_dev;

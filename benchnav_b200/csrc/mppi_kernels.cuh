@@ -46,7 +46,9 @@ struct alignas(64) EngineParams {
   int world;                   // number of sample shards
   int record;                  // keep recorded states
   int noise_bulk_ok, rec_bulk_ok;  // pointers 16 B aligned -> bulk copies allowed
-  const float* state;   // [3]
+  const float* state;   // [3] device-resident current state, or
+  float state_val[3];   // ... the same three floats passed by value in the launch packet (state_inline != 0)
+  int state_inline;
   const float* noise_in;  // injected noise [Kl][T][2] (kPhilox == false)
   float* noise_out;     // engine noise buffer [Kl][T][2], written when kPhilox
   float* u_prev;        // [T][2]   mean sequence (read at start, replaced by u* at the end)
@@ -60,6 +62,9 @@ struct alignas(64) EngineParams {
   float* stats;          // [2] (M, S) of the last merge, published to the waiting CTAs (coop)
   unsigned int epoch;    // unique per launch
   int coop;              // grid is co-resident (cooperative launch): deferred slab stores, in-register weights
+  float* const* peer_mbox;  // [world] device pointers to every rank's mailbox (peer memory over NVLink), or null
+  unsigned int xchg_seq;    // exchange sequence number (same on every rank), selects the mailbox parity
+  int rank;
   float* u_out;         // [T][2]
   float* opt_rec;       // [T+1][3]
   long long* dbg_ts;    // optional [16] clock64 stamps of the last CTA (BNV_DEBUG_TS; null in production)
@@ -315,6 +320,14 @@ __device__ __forceinline__ unsigned int atom_add_acq_rel_gpu(unsigned int* p, un
   asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
   return old;
 }
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void st_release_gpu(unsigned int* p, unsigned int v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -407,7 +420,9 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
   for (int i = warp_rows * 2 * T + lane; i < 32 * 2 * T; i += 32) v_w[i] = 0.0f;
 
   // ---- state, window geometry, traversability window via TMA
-  const float sx = __ldg(P.state), sy = __ldg(P.state + 1), sth = __ldg(P.state + 2);
+  const float sx = P.state_inline ? P.state_val[0] : __ldg(P.state);
+  const float sy = P.state_inline ? P.state_val[1] : __ldg(P.state + 1);
+  const float sth = P.state_inline ? P.state_val[2] : __ldg(P.state + 2);
   const WindowGeom wg = window_for_state(P, sx, sy);
   if (kPatch) {
     if (warp == 0) {
@@ -683,42 +698,84 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
     __syncthreads();
     S = 0.0f;
     for (int w = 0; w < nwarps; ++w) S += red_s[24 + w];
+    for (int c = tid; c < ncol; c += blockDim.x) {
+      float acc = 0.0f;
+      for (int gq = 0; gq < ngrp; ++gq) acc += grp_s[gq * ncol + c];
+      uprev_s[c] = acc;  // U of this shard, un-normalised
+    }
+    __syncthreads();
+    // ---- sharded softmax, fused exchange over NVLink peer memory: every rank's last CTA writes its shard partial
+    // (M, S, U) into its slot of every peer's mailbox, raises the slot's flag (release.sys), waits for the W flags of
+    // its own mailbox and merges the W partials in rank order -- identical arithmetic on every rank, so every rank
+    // holds the same u*.  Mailboxes are double-buffered by the parity of the exchange sequence number: a rank can
+    // be at most one iteration ahead of the slowest peer.
+    const bool fused = P.world > 1 && P.peer_mbox != nullptr;
+    float m_shard = M;  // reference of the per-sample exponentials already computed on this shard
+    if (fused) {
+      const int W = P.world, plen = 2 + ncol, slot = plen + 2;
+      const size_t my_slot = (static_cast<size_t>(P.xchg_seq & 1u) * W + P.rank) * slot;
+      for (int r = 0; r < W; ++r) {
+        float* dst = P.peer_mbox[r] + my_slot;
+        for (int c = tid; c < ncol; c += blockDim.x) dst[2 + c] = uprev_s[c];
+        if (tid == 0) {
+          dst[0] = M;
+          dst[1] = S;
+        }
+      }
+      __syncthreads();
+      if (tid < W) {
+        unsigned int* flag = reinterpret_cast<unsigned int*>(P.peer_mbox[tid] + my_slot + plen);
+        st_release_sys(flag, P.xchg_seq);
+        const float* mine = P.peer_mbox[P.rank] + (static_cast<size_t>(P.xchg_seq & 1u) * W + tid) * slot;
+        while (ld_acquire_sys(reinterpret_cast<const unsigned int*>(mine + plen)) != P.xchg_seq) __nanosleep(64);
+      }
+      __syncthreads();
+      const float* box = P.peer_mbox[P.rank] + static_cast<size_t>(P.xchg_seq & 1u) * W * slot;
+      float Mg = -FLT_MAX;
+      for (int r = 0; r < W; ++r) Mg = fmaxf(Mg, __ldcg(box + r * slot));
+      float Sg = 0.0f;
+      for (int r = 0; r < W; ++r) Sg = fmaf(__expf(__ldcg(box + r * slot) - Mg), __ldcg(box + r * slot + 1), Sg);
+      for (int c = tid; c < ncol; c += blockDim.x) {
+        float acc = 0.0f;
+        for (int r = 0; r < W; ++r) acc = fmaf(__expf(__ldcg(box + r * slot) - Mg), __ldcg(box + r * slot + 2 + c), acc);
+        uprev_s[c] = acc;
+      }
+      M = Mg;
+      S = Sg;
+      __syncthreads();
+    }
+    const bool complete = P.world == 1 || fused;  // (M, S, U) now cover every sample of the solver
     if (coop && tid == 0) {  // publish (M, S) and release the waiting CTAs as early as possible
       P.stats[0] = M;
       P.stats[1] = S;
       st_release_gpu(P.ticket + 1, P.epoch);
     }
-    for (int c = tid; c < ncol; c += blockDim.x) {
-      float acc = 0.0f;
-      for (int gq = 0; gq < ngrp; ++gq) acc += grp_s[gq * ncol + c];
-      const float u = (P.world == 1) ? __fdiv_rn(acc, S) : acc;  // u* = U / S (mppi.py:196-199), or U for the exchange
-      uprev_s[c] = u;
-      warpu_s[c] = clampf(u, (c & 1) ? C.u_min1 : C.u_min0, (c & 1) ? C.u_max1 : C.u_max0);  // for the optimal rollout
-    }
-    __syncthreads();
-    BNV_STAMP(5);
-    if (tid == 0) *P.ticket = 0u;  // re-arm for the next launch
-    if (P.world == 1) {
-      for (int i = tid; i < ncol; i += blockDim.x) {
-        const float u = uprev_s[i];
-        P.u_out[i] = u;
-        P.u_prev[i] = u;  // next call's mean sequence, unshifted (mppi.py:217)
+    if (complete) {
+      for (int c = tid; c < ncol; c += blockDim.x) {
+        const float u = __fdiv_rn(uprev_s[c], S);  // u* = U / S (mppi.py:196-199)
+        uprev_s[c] = u;
+        warpu_s[c] = clampf(u, (c & 1) ? C.u_min1 : C.u_min0, (c & 1) ? C.u_max1 : C.u_max0);  // for the optimal rollout
+        P.u_out[c] = u;
+        P.u_prev[c] = u;  // next call's mean sequence, unshifted (mppi.py:217)
       }
-    } else {
+    } else {  // unfused sharding: hand the shard partial to the host-side exchange + finalize_kernel
       if (tid == 0) {
         P.shard_partial[0] = M;
         P.shard_partial[1] = S;
       }
       for (int c = tid; c < ncol; c += blockDim.x) P.shard_partial[2 + c] = uprev_s[c];
     }
+    __syncthreads();
+    BNV_STAMP(5);
+    if (tid == 0) *P.ticket = 0u;  // re-arm for the next launch
     BNV_STAMP(6);
     if (!coop) {
       // the other warps rescale every sample's weight underneath warp 0's serial optimal rollout:
-      // weights[k] = exp(score_k - m_cta) * exp(m_cta - M) / S (softmax, mppi.py:193; 1/S deferred when sharded)
-      const float inv_s = (P.world == 1) ? __fdiv_rn(1.0f, S) : 1.0f;
-      const bool own_thread = (P.world == 1) && blockDim.x > 32;
-      auto scale_of = [&](int g) { return fast_merge ? a_s[g] : __expf(__ldcg(P.part_ms + 2 * g) - M); };
-      if (P.world == 1 && tid == 0) optimal_rollout<kPatch, kPow2, kFastAngles>(P, C, warpu_s, sx, sy, sth);
+      // weights[k] = exp(score_k - m_cta) * exp(m_cta - M) / S (softmax, mppi.py:193; 1/S deferred when unfused-sharded)
+      const float inv_s = complete ? __fdiv_rn(__expf(m_shard - M), S) : 1.0f;
+      const bool own_thread = complete && blockDim.x > 32;
+      auto scale_of = [&](int g) { return fast_merge ? a_s[g] : __expf(__ldcg(P.part_ms + 2 * g) - m_shard); };
+      if (complete && tid == 0) optimal_rollout<kPatch, kPow2, kFastAngles>(P, C, warpu_s, sx, sy, sth);
       BNV_STAMP(7);
       if (!(own_thread && tid < 32)) {
         if (!own_thread) __syncwarp();
@@ -737,10 +794,11 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
     S = __ldcg(P.stats + 1);
   }
   if (coop) {
-    // softmax weight of this thread's sample straight from registers (mppi.py:193; 1/S deferred when sharded)
-    if (valid) P.weights[k] = e * __expf(m_cta - M) * ((P.world == 1) ? __fdiv_rn(1.0f, S) : 1.0f);
+    // softmax weight of this thread's sample straight from registers (mppi.py:193; 1/S deferred when unfused-sharded)
+    const bool complete = P.world == 1 || P.peer_mbox != nullptr;
+    if (valid) P.weights[k] = e * __expf(m_cta - M) * (complete ? __fdiv_rn(1.0f, S) : 1.0f);
     store_slabs<kRecord, kPhilox>(P, rec_s, nz_w, warp, lane, warp_first, warp_rows, nz_bytes);
-    if (is_last && P.world == 1 && tid == 0) optimal_rollout<kPatch, kPow2, kFastAngles>(P, C, warpu_s, sx, sy, sth);
+    if (is_last && complete && tid == 0) optimal_rollout<kPatch, kPow2, kFastAngles>(P, C, warpu_s, sx, sy, sth);
     if (is_last) BNV_STAMP(7);
   }
   // shared memory must stay allocated until the bulk stores have read it
@@ -766,7 +824,9 @@ __global__ void __launch_bounds__(kFinalizeThreads) finalize_kernel(const __grid
     fence_mbar_init();
   }
   __syncthreads();
-  const float sx = __ldg(P.state), sy = __ldg(P.state + 1), sth = __ldg(P.state + 2);
+  const float sx = P.state_inline ? P.state_val[0] : __ldg(P.state);
+  const float sy = P.state_inline ? P.state_val[1] : __ldg(P.state + 1);
+  const float sth = P.state_inline ? P.state_val[2] : __ldg(P.state + 2);
   const WindowGeom wg = window_for_state(P, sx, sy);
   if (kPatch) {
     if (tid < 32) {

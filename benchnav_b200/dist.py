@@ -53,6 +53,32 @@ def gather_shard_partials(partial: torch.Tensor, gathered: torch.Tensor, shard: 
     return gathered
 
 
+def attach_peer_mailboxes(lib, handle, shard: ShardInfo) -> bool:
+    """Exchange the CUDA IPC handles of the ranks' mailboxes and map the peers' (bnv_mppi_attach_peers).
+
+    Collective: every rank of the group must call it.  Returns True when EVERY rank could map all peers -- then the
+    engine exchanges the softmax partials inside the rollout kernel over NVLink peer memory; otherwise all ranks
+    fall back to the all-gather + finalize pair."""
+    import ctypes as C
+
+    from . import _cabi
+
+    mine = (C.c_ubyte * 64)()
+    _cabi.check(lib.bnv_mppi_mailbox_handle(handle, mine))
+    gathered = [None] * shard.world_size
+    dist.all_gather_object(gathered, bytes(mine), group=shard.group)
+    blob = (C.c_ubyte * (64 * shard.world_size)).from_buffer_copy(b"".join(gathered))
+    ok = lib.bnv_mppi_attach_peers(handle, blob) == _cabi.BNV_OK
+    votes = [None] * shard.world_size
+    dist.all_gather_object(votes, bool(ok), group=shard.group)
+    if not all(votes):
+        if ok:
+            raise RuntimeError("peer mailboxes attached on this rank but not on every rank; rebuild the solver with "
+                               "exchange='nccl'")
+        return False
+    return True
+
+
 def merge_top_candidates(states: torch.Tensor, weights: torch.Tensor, n: int, shard: ShardInfo
                          ) -> Tuple[torch.Tensor, torch.Tensor]:
     """Global top-n from per-shard top lists (each already sorted descending); off the critical path."""

@@ -28,7 +28,7 @@ import torch
 import torch.nn as nn
 
 from . import _cabi
-from .dist import ShardInfo, gather_shard_partials, merge_top_candidates
+from .dist import ShardInfo, attach_peer_mailboxes, gather_shard_partials, merge_top_candidates
 
 
 class _DevView:
@@ -74,7 +74,7 @@ class MPPI(nn.Module):
     def __init__(self, horizon: int, num_samples: int, dim_state: int, dim_control: int, dynamics, objectives,
                  sigmas: torch.Tensor, lambda_: float, device=torch.device("cuda"), dtype=torch.float32,
                  seed: int = 42, *, noise_source: str = "philox", record_states: bool = True,
-                 process_group=None) -> None:
+                 process_group=None, exchange: str = "p2p") -> None:
         super().__init__()
         torch.manual_seed(seed)  # mppi.py:55
         # same shape checks (and exception type) as mppi.py:58-66
@@ -87,6 +87,8 @@ class MPPI(nn.Module):
             raise ValueError("the engine computes in float32 (the reference's default dtype)")
         if noise_source not in ("philox", "torch"):
             raise ValueError("noise_source must be 'philox' or 'torch'")
+        if exchange not in ("p2p", "nccl"):
+            raise ValueError("exchange must be 'p2p' (fused, NVLink peer memory) or 'nccl' (all-gather + finalize)")
         dev = torch.device(device)
         if dev.type != "cuda" or not torch.cuda.is_available():
             raise RuntimeError("benchnav_b200.MPPI runs on CUDA (sm_100a) only; there is no CPU fallback")
@@ -140,6 +142,9 @@ class MPPI(nn.Module):
         self._gathered = (torch.empty(self._shard.world_size, plen, device=dev, dtype=torch.float32)
                           if self._shard.world_size > 1 else None)
         self._state_dev = torch.zeros(3, device=dev, dtype=torch.float32)
+        self._fused_exchange = False
+        if self._shard.world_size > 1 and exchange == "p2p":
+            self._fused_exchange = attach_peer_mailboxes(self._lib, self._handle, self._shard)
 
     # ------------------------------------------------------------------ plumbing
     def _draw_torch_noise(self) -> torch.Tensor:
@@ -191,11 +196,15 @@ class MPPI(nn.Module):
         assert state.shape == (self._dim_state,)
         self._sync_problem()
         with torch.cuda.device(self._device):
-            if (state.device == self._device and state.dtype == torch.float32 and state.is_contiguous()):
-                state_dev = state.detach()  # already resident: the engine reads it in place (stream-ordered)
-            else:
-                self._state_dev.copy_(state.detach(), non_blocking=True)
-                state_dev = self._state_dev
+            state_ptr, state_host = None, None
+            if state.device.type == "cuda":
+                if state.device == self._device and state.dtype == torch.float32 and state.is_contiguous():
+                    state_ptr = state.detach().data_ptr()  # already resident: read in place (stream-ordered)
+                else:
+                    self._state_dev.copy_(state.detach(), non_blocking=True)
+                    state_ptr = self._state_dev.data_ptr()
+            else:  # host state: three floats by value in the launch packet, no device copy
+                state_host = (C.c_float * 3)(*state.detach().to(torch.float32).tolist())
             if noise is not None:
                 if noise.shape != (self._local_samples, self._horizon, 2):
                     raise ValueError(f"noise must have shape {(self._local_samples, self._horizon, 2)}")
@@ -208,10 +217,14 @@ class MPPI(nn.Module):
             u_opt = torch.empty(self._horizon, 2, device=self._device, dtype=torch.float32)
             opt_states = torch.empty(1, self._horizon + 1, 3, device=self._device, dtype=torch.float32)
             stream = self._stream()
-            _cabi.check(self._lib.bnv_mppi_forward(self._handle, state_dev.data_ptr(),
-                                                   noise.data_ptr() if noise is not None else None,
-                                                   u_opt.data_ptr(), opt_states.data_ptr(), stream))
-            if self._shard.world_size > 1:
+            noise_ptr = noise.data_ptr() if noise is not None else None
+            if state_host is None:
+                _cabi.check(self._lib.bnv_mppi_forward(self._handle, state_ptr, noise_ptr, u_opt.data_ptr(),
+                                                       opt_states.data_ptr(), stream))
+            else:
+                _cabi.check(self._lib.bnv_mppi_forward_state(self._handle, state_host, noise_ptr, u_opt.data_ptr(),
+                                                             opt_states.data_ptr(), stream))
+            if self._shard.world_size > 1 and not self._fused_exchange:
                 gather_shard_partials(self._partial, self._gathered, self._shard)
                 _cabi.check(self._lib.bnv_mppi_finalize(self._handle, self._gathered.data_ptr(), u_opt.data_ptr(),
                                                         opt_states.data_ptr(), stream))
@@ -225,7 +238,9 @@ class MPPI(nn.Module):
         if self._shard.world_size != 1 or self._noise_source != "philox":
             out = self.forward(state)
             return out[0].cpu(), out[1].cpu()
-        state = torch.as_tensor(state, dtype=torch.float32).detach().cpu().contiguous()
+        if not (torch.is_tensor(state) and state.dtype == torch.float32 and state.device.type == "cpu"
+                and state.is_contiguous()):
+            state = torch.as_tensor(state, dtype=torch.float32).detach().cpu().contiguous()
         assert state.shape == (self._dim_state,)
         self._sync_problem()
         u_opt = torch.empty(self._horizon, 2, dtype=torch.float32)

@@ -92,9 +92,15 @@ int bnv_mppi_set_problem(bnv_mppi* h, const float* risk_dev, int32_t grid_size, 
 int bnv_mppi_forward(bnv_mppi* h, const float* state_dev, const float* noise_dev, float* u_out_dev,
                      float* opt_states_dev, void* stream);
 
+/* forward with the state given as three HOST floats (passed by value in the launch packet: no device copy of
+ * the state is needed) and DEVICE outputs; asynchronous like bnv_mppi_forward. */
+int bnv_mppi_forward_state(bnv_mppi* h, const float state_host[3], const float* noise_dev, float* u_out_dev,
+                           float* opt_states_dev, void* stream);
+
 /* Same call with HOST buffers (the reference-facing form: `forward(state)` takes and returns tensors the
- * caller reads on the host).  Copies state host->device, runs the iteration, copies u_out/opt_states
- * device->host through pinned staging and synchronises `stream`.  world_size must be 1. */
+ * caller reads on the host).  Host->device: the state rides in the launch packet.  Device->host: the kernel
+ * stores u_out/opt_states into pinned, device-mapped staging (zero-copy over PCIe); the call synchronises
+ * `stream` and copies them to the caller's buffers.  world_size must be 1. */
 int bnv_mppi_forward_host(bnv_mppi* h, const float state_host[3], const float* noise_dev, float* u_out_host,
                           float* opt_states_host, void* stream);
 
@@ -107,6 +113,14 @@ const float* bnv_mppi_partial(const bnv_mppi* h);
 int32_t bnv_mppi_partial_len(const bnv_mppi* h);
 int bnv_mppi_finalize(bnv_mppi* h, const float* gathered_partials_dev, float* u_out_dev, float* opt_states_dev,
                       void* stream);
+
+/* Fused exchange over NVLink peer memory (replaces the host-side all-gather + bnv_mppi_finalize pair): every rank
+ * exports the CUDA IPC handle of its mailbox (64 bytes), the handles are gathered by the caller (any transport,
+ * rank-major) and attached once.  Afterwards bnv_mppi_forward on a sharded handle exchanges the shard partials
+ * inside the rollout kernel (P2P stores + release/acquire flags, double-buffered) and writes u_out/opt_states
+ * itself; all ranks must call forward the same number of times (as with any collective). */
+int bnv_mppi_mailbox_handle(bnv_mppi* h, unsigned char out[64]);
+int bnv_mppi_attach_peers(bnv_mppi* h, const unsigned char* handles /* [world_size][64] */);
 
 /* MPPI.get_top_samples (mppi.py:221-240): the n highest-weight samples of this shard in descending
  * weight order.  states_out_dev [n,T+1,3], weights_out_dev [n]. Needs BNV_FLAG_RECORD_STATES. */

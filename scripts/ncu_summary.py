@@ -1,0 +1,101 @@
+#!/usr/bin/env python
+"""Turn the raw ncu captures brought back in gpurun_out/ into the tracked summaries under profiles/.
+
+    python scripts/ncu_summary.py --tag r01 [--workload G256_K16384_T50]
+
+Reads  gpurun_out/launches.csv        (ncu --metrics gpu__time_duration.sum ... python bench.py ...)
+       gpurun_out/prof_rollout.ncu-rep (ncu --set full -k regex:rollout_kernel ...)
+Writes profiles/<tag>_launches_summary.txt, profiles/<tag>_rollout_ncu_summary.txt and updates
+       profiles/rollout_traffic.json (per-launch DRAM bytes of the rollout kernel, read by bench.py).
+"""
+import argparse
+import collections
+import csv
+import json
+import os
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "gpurun_out")
+PROF = os.path.join(ROOT, "profiles")
+
+METRICS = [
+    "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+    "launch__shared_mem_per_block_dynamic", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "smsp__inst_executed.sum", "sm__cycles_elapsed.max", "sm__cycles_active.avg", "sm__cycles_active.max",
+    "sm__inst_executed.avg.per_cycle_active", "smsp__warps_active.avg.per_cycle_active",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+]
+
+
+def to_bytes(value: str, unit: str) -> float:
+    mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+    return float(value) * mult
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--tag", default="r01")
+    ap.add_argument("--workload", default="G256_K16384_T50")
+    ap.add_argument("--cmd", default="python bench.py --steps 150 --warmup 10")
+    args = ap.parse_args()
+    os.makedirs(PROF, exist_ok=True)
+
+    path = os.path.join(OUT, "launches.csv")
+    if os.path.exists(path):
+        rows = [r for r in csv.reader(open(path)) if len(r) > 5]
+        ci = {n: i for i, n in enumerate(rows[0])}
+        d = collections.defaultdict(list)
+        for r in rows[1:]:
+            try:
+                d[r[ci["Kernel Name"]]].append(float(r[ci["Metric Value"]]))
+            except (ValueError, IndexError):
+                pass
+        tot = sum(sum(v) for v in d.values())
+        with open(os.path.join(PROF, f"{args.tag}_launches_summary.txt"), "w") as f:
+            f.write(f"# {args.tag}: ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 400 {args.cmd}\n")
+            f.write("# per-launch device time, cold-cache and serialised by ncu: compare SHARES, not absolutes\n")
+            for k, v in sorted(d.items(), key=lambda x: -sum(x[1])):
+                f.write(f"{k[:96]:96s} launches={len(v):4d} avg_us={sum(v) / len(v) / 1000:8.2f} "
+                        f"share={sum(v) / tot * 100:5.1f}%\n")
+            f.write("# at::FillFunctor = bench.py's 256 MiB L2 flush between timed steps (outside the timed event pairs)\n")
+            ours = {k: v for k, v in d.items() if "bnv::" in k}
+            tot_ours = sum(sum(v) for v in ours.values())
+            for k, v in ours.items():
+                f.write(f"# share of the step (our kernels only): {k[:60]} {sum(v) / tot_ours * 100:5.1f}%\n")
+        print(open(os.path.join(PROF, f"{args.tag}_launches_summary.txt")).read())
+
+    rep = os.path.join(OUT, "prof_rollout.ncu-rep")
+    if os.path.exists(rep):
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(raw.splitlines()))
+        hdr, units, data = rows[0], rows[1], rows[2:]
+        lines, traffic = [], []
+        for m in METRICS:
+            if m in hdr:
+                i = hdr.index(m)
+                lines.append(f"{m:70s} [{units[i]:>16s}] " + "  ".join(r[i] for r in data))
+        if "dram__bytes_read.sum" in hdr:
+            ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+            traffic = [to_bytes(r[ir], units[ir]) + to_bytes(r[iw], units[iw]) for r in data]
+        with open(os.path.join(PROF, f"{args.tag}_rollout_ncu_summary.txt"), "w") as f:
+            f.write(f"# {args.tag}: ncu --set full --clock-control none --import-source on -k regex:rollout_kernel "
+                    f"-s 20 -c {len(data)} python bench.py --steps 40 --warmup 10   (workload {args.workload})\n")
+            f.write("# one column per captured launch; ncu flushes caches between replays (cold)\n")
+            f.write("\n".join(lines) + "\n")
+            if traffic:
+                f.write(f"# DRAM traffic per launch (read+write): {[int(t) for t in traffic]} bytes; the ~17 MB of slab writes "
+                        f"stay in the 126 MB L2 (write-back) for the kernel's lifetime\n")
+        print(open(os.path.join(PROF, f"{args.tag}_rollout_ncu_summary.txt")).read())
+        if traffic:
+            tpath = os.path.join(PROF, "rollout_traffic.json")
+            tj = json.load(open(tpath)) if os.path.exists(tpath) else {}
+            tj[args.workload] = {"dram_bytes_per_launch": int(sum(traffic) / len(traffic)), "source": f"{args.tag} ncu --set full",
+                                 "launches": len(traffic)}
+            json.dump(tj, open(tpath, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
