@@ -15,8 +15,9 @@ Numbers
   value        device-timed: per-step CUDA-event pairs around forward() (state resident in HBM), L2 flushed
                between steps by writing a 256 MiB buffer, max over ranks; unit = iterations of one
                (16384-sample x 50-step) shard per second summed over ranks (= control iterations/s x N).
-  e2e          forward_host(): pinned host state -> H2D, iteration, D2H of u* and the optimal state sequence,
-               stream sync, every step, wall clock per step (L2 flushed between steps, flush not counted).
+  e2e          forward_host(): every step the 12-byte state goes host -> device in the kernel's launch packet, the
+               iteration runs, the kernel stores u* and the optimal state sequence (1012 bytes) device -> host into
+               pinned mapped memory, one stream sync; wall clock per step (L2 flushed between steps, flush not counted).
   roofline     rollout kernel alone: SURVEY 8d algorithmic bytes / its CUDA-event duration (second pass with the
                engine's kernel-event recorder on), against MEASURED_PEAKS.json hbm_gbs.
   cpu_baseline the oracle port of the reference loop (oracle/mppi_oracle.py, PyTorch CPU ops) on the host cores.
@@ -280,7 +281,8 @@ def run_native(args) -> None:
             acc += time.perf_counter() - t0
         e2e = {"value": n_e / acc, "unit": UNIT, "h2d_bytes_per_step": 12,
                "d2h_bytes_per_step": 4 * (2 * HORIZON + 3 * (HORIZON + 1)), "steps": n_e,
-               "timing": "wall clock around forward_host() per step, L2 flushed before each step"}
+               "timing": "wall clock around forward_host() per step (state H2D in the launch packet, results D2H by "
+                         "zero-copy stores to pinned host memory, one stream sync), L2 flushed before each step"}
 
     if rank != 0:
         if world > 1:
