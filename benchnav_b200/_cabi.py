@@ -17,7 +17,9 @@ from . import build as _build
 
 BNV_OK = 0
 BNV_FLAG_RECORD_STATES = 0x1
-ABI_VERSION = 1
+BNV_FLAG_STOCHASTIC_SLIP = 0x2
+BNV_RISK_CLOSED_FORM, BNV_RISK_MONTE_CARLO = 0, 1
+ABI_VERSION = 2
 
 
 class BnvError(RuntimeError):
@@ -42,10 +44,26 @@ class MppiCfg(C.Structure):
         ("world_size", C.c_int32),
         ("device", C.c_int32),
         ("flags", C.c_uint32),
+        ("num_envs", C.c_int32),
+    ]
+
+
+class Grid(C.Structure):
+    """Mirror of ``bnv_grid`` (include/bnv_mppi.h)."""
+
+    _fields_ = [
+        ("grid_size", C.c_int32),
+        ("pitch", C.c_int32),
+        ("resolution", C.c_float),
+        ("x_min", C.c_float),
+        ("x_max", C.c_float),
+        ("y_min", C.c_float),
+        ("y_max", C.c_float),
     ]
 
 
 _VP = C.c_void_p
+_FP = C.POINTER(C.c_float)
 _SIGNATURES = {
     "bnv_abi_version": (C.c_int, []),
     "bnv_last_error": (C.c_char_p, []),
@@ -53,7 +71,10 @@ _SIGNATURES = {
     "bnv_mppi_destroy": (None, [_VP]),
     "bnv_mppi_set_problem": (C.c_int, [_VP, _VP, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float,
                                        C.c_float, C.POINTER(C.c_float), C.c_float, _VP]),
+    "bnv_mppi_set_problem_ex": (C.c_int, [_VP, _VP, _VP, C.c_int32, C.c_int32, C.c_int64, C.c_float, C.c_float,
+                                          C.c_float, C.c_float, C.c_float, _FP, C.c_float, _VP]),
     "bnv_mppi_forward": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP]),
+    "bnv_mppi_forward_ex": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "bnv_mppi_forward_state": (C.c_int, [_VP, C.POINTER(C.c_float), _VP, _VP, _VP, _VP]),
     "bnv_mppi_forward_host": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP]),
     "bnv_mppi_mailbox_handle": (C.c_int, [_VP, C.POINTER(C.c_ubyte)]),
@@ -71,11 +92,24 @@ _SIGNATURES = {
     "bnv_mppi_sample_offset": (C.c_int32, [_VP]),
     "bnv_mppi_reset": (C.c_int, [_VP, _VP]),
     "bnv_mppi_draw_noise": (C.c_int, [_VP, C.c_uint64, _VP]),
+    "bnv_mppi_draw_xi": (C.c_int, [_VP, C.c_uint64, _VP, _VP, _VP]),
+    "bnv_mppi_set_keep_mean": (C.c_int, [_VP, C.c_int32]),
+    "bnv_mppi_set_terminal_goal": (C.c_int, [_VP, _FP]),
+    "bnv_mppi_set_goal_dev": (C.c_int, [_VP, _VP]),
+    "bnv_mppi_argmin": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP]),
     "bnv_mppi_launch_count": (C.c_uint64, [_VP]),
     "bnv_mppi_kernel_timing": (C.c_int, [_VP, C.c_int32]),
     "bnv_mppi_kernel_time": (C.c_int, [_VP, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "bnv_debug_timestamps": (C.c_int, [_VP, C.POINTER(C.c_longlong)]),
     "bnv_debug_sincos": (C.c_int, [_VP, _VP, _VP, C.c_int32, _VP]),
+    "bnv_trav_lookup": (C.c_int, [C.POINTER(Grid), _VP, _VP, C.c_int64, C.c_int64, _VP, C.c_int64, C.c_int32, _VP,
+                                  C.c_uint64, C.c_uint64, C.c_float, _VP, _VP, _VP]),
+    "bnv_env_step": (C.c_int, [C.POINTER(Grid), _VP, _VP, C.c_int64, C.c_int32, _VP, _VP, _VP, _VP, C.c_uint64,
+                               C.c_uint64, _FP, _FP, C.c_float, C.c_float, _VP, _VP, _VP]),
+    "bnv_risk_map": (C.c_int, [C.c_int32, C.c_float, C.c_int32, _VP, _VP, C.c_int64, _VP, C.c_int32, C.c_uint64, _VP,
+                               _VP, _VP]),
+    "bnv_dwa_actions": (C.c_int, [_VP, _FP, _FP, _FP, C.c_float, C.c_int32, C.c_int32, C.c_int32, _VP, _VP, _VP]),
+    "bnv_dwa_subgoal": (C.c_int, [_VP, C.c_int32, _VP, C.c_float, _VP, _VP]),
 }
 
 _lib = None
@@ -109,6 +143,11 @@ def load() -> C.CDLL:
         raise ImportError(f"ABI mismatch: library {lib.bnv_abi_version()} vs binding {ABI_VERSION}")
     _lib = lib
     return lib
+
+
+def make_grid(grid_size: int, pitch: int, resolution: float, x_limits, y_limits) -> Grid:
+    return Grid(int(grid_size), int(pitch), float(resolution), float(x_limits[0]), float(x_limits[1]),
+                float(y_limits[0]), float(y_limits[1]))
 
 
 def check(code: int) -> None:

@@ -19,17 +19,20 @@ INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
 LIB_DIR = os.path.join(PKG_DIR, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libbnvmppi.so")
 
-NVCC_FLAGS = [
+COMPILE_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
-    "-Xcompiler", "-fPIC", "-shared",
-    "-cudart", "static",
+    "-Xcompiler", "-fPIC",
     "-Xptxas", "-v",
 ]
+LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-cudart", "static"]
+
+
+SOURCES = ("bnv_mppi.cu", "rollout_ext.cu", "bnv_aux.cu")
 
 
 def _sources():
-    srcs = [os.path.join(CSRC, "bnv_mppi.cu")]
+    srcs = [os.path.join(CSRC, f) for f in SOURCES]
     deps = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(INCLUDE, "bnv_mppi.h")]
     return srcs, deps
 
@@ -50,15 +53,34 @@ def is_stale() -> bool:
 
 
 def build_library(verbose: bool = False) -> str:
+    """Compile every translation unit (in parallel: the rollout kernel's template space dominates) and link."""
     srcs, _ = _sources()
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [nvcc_path(), *NVCC_FLAGS, "-I", INCLUDE, "-I", CSRC, "-o", LIB_PATH, *srcs]
-    proc = subprocess.run(cmd, capture_output=True, text=True)
+    obj_dir = os.path.join(LIB_DIR, "obj")
+    os.makedirs(obj_dir, exist_ok=True)
+    nvcc = nvcc_path()
+    procs = []
+    for src in srcs:
+        obj = os.path.join(obj_dir, os.path.splitext(os.path.basename(src))[0] + ".o")
+        cmd = [nvcc, *COMPILE_FLAGS, "-I", INCLUDE, "-I", CSRC, "-c", "-o", obj, src]
+        procs.append((cmd, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    log, objs = "", []
+    for cmd, obj, proc in procs:
+        out, _ = proc.communicate()
+        log += " ".join(cmd) + "\n" + out
+        if proc.returncode != 0:
+            for _, _, other in procs:
+                if other.poll() is None:
+                    other.kill()
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + out)
+        objs.append(obj)
+    link = [nvcc, *LINK_FLAGS, "-o", LIB_PATH, *objs]
+    proc = subprocess.run(link, capture_output=True, text=True)
+    log += " ".join(link) + "\n" + proc.stdout + proc.stderr
     if proc.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
-    log = proc.stdout + proc.stderr
+        raise RuntimeError("link failed:\n" + " ".join(link) + "\n" + proc.stdout + proc.stderr)
     with open(os.path.join(LIB_DIR, "build.log"), "w") as f:
-        f.write(" ".join(cmd) + "\n" + log)
+        f.write(log)
     if verbose:
         print(log)
     return LIB_PATH

@@ -1,7 +1,7 @@
 // libbnvmppi.so -- host side of the C ABI declared in include/bnv_mppi.h.
 // Owns the solver handle (device buffers, TMA descriptor, launch geometry) and launches the sm_100a
 // kernels of mppi_kernels.cuh.  No PyTorch types anywhere: callers pass raw device pointers and a stream.
-#include "../../include/bnv_mppi.h"
+#include "bnv_internal.h"
 
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -22,22 +22,7 @@ namespace {
 
 thread_local std::string g_last_error;
 
-int fail(int code, const char* fmt, ...) {
-  char buf[512];
-  va_list ap;
-  va_start(ap, fmt);
-  vsnprintf(buf, sizeof(buf), fmt, ap);
-  va_end(ap);
-  g_last_error = buf;
-  return code;
-}
-
-#define BNV_CUDA(expr)                                                                              \
-  do {                                                                                              \
-    cudaError_t e__ = (expr);                                                                       \
-    if (e__ != cudaSuccess)                                                                         \
-      return fail(BNV_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
-  } while (0)
+#define fail bnv_fail
 
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -75,14 +60,28 @@ bool is_pow2_float(float v) {
 
 }  // namespace
 
+int bnv_fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
 struct bnv_mppi {
   bnv_mppi_cfg cfg{};
   int Kl = 0, k_offset = 0;
+  int E = 1;           // environments per forward call (batch mode when > 1)
+  bool stoch = false;  // stochastic-slip lookups
   bool problem_set = false, have_weights = false;
   uint64_t iteration = 0, launches = 0;
   bnv::EngineParams P{};
   // owned device buffers
   float* tau = nullptr;
+  size_t tau_floats = 0;
+  float* goals_dev = nullptr;  // [E][2]
   float* noise = nullptr;
   float* rec = nullptr;
   float* costs = nullptr;
@@ -110,6 +109,7 @@ struct bnv_mppi {
   size_t top_pairs_cap = 0, top_idx_cap = 0;
   float* io_host = nullptr;  // pinned mirror of io_dev
   int grid = 0, warps = 0;
+  long long resident_ctas = 0;  // how many rollout CTAs the device can hold at once (cooperative-launch bound)
   bool fast_angles = false;
   size_t rollout_smem = 0, finalize_smem = 0;
   // optional CUDA-event timing of the rollout kernel alone (bench.py's roofline)
@@ -122,6 +122,7 @@ namespace {
 
 void free_all(bnv_mppi* h) {
   cudaFree(h->tau);
+  cudaFree(h->goals_dev);
   cudaFree(h->noise);
   cudaFree(h->rec);
   cudaFree(h->costs);
@@ -144,28 +145,13 @@ void free_all(bnv_mppi* h) {
   if (h->io_host) cudaFreeHost(h->io_host);
 }
 
-// Choose warps per CTA so that noise + recorded-state slabs fit shared memory; prefer 4 (one per SM sub-partition).
-int configure_launch(bnv_mppi* h) {
-  bnv::EngineParams& P = h->P;
-  for (int w = bnv::kMaxWarps; w >= 1; w >>= 1) {
-    bnv::RolloutSmem L = bnv::rollout_smem_layout(P.T, w, P.patch_w, P.patch_h, P.use_patch, P.record);
-    if (static_cast<size_t>(L.total) <= kMaxDynSmem) {
-      h->warps = w;
-      h->rollout_smem = L.total;
-      h->grid = (h->Kl + w * 32 - 1) / (w * 32);
-      return BNV_OK;
-    }
-  }
-  return fail(BNV_ERR_UNSUPPORTED, "horizon %d does not fit the rollout kernel's shared-memory staging", P.T);
-}
-
-using RolloutFn = void (*)(bnv::EngineParams);
+using RolloutFn = BnvRolloutFn;
 using FinalizeFn = void (*)(bnv::EngineParams, const float*, int);
 
-// rollout_kernel<kPatch, kPow2, kRecord, kFastAngles, kPhilox>
+// rollout_kernel<kPatch, kPow2, kRecord, kFastAngles, kPhilox, false, false>: the single-solver instantiations
 template <bool A, bool B, bool C, bool D>
 RolloutFn pick_rollout4(bool e) {
-  return e ? bnv::rollout_kernel<A, B, C, D, true> : bnv::rollout_kernel<A, B, C, D, false>;
+  return e ? bnv::rollout_kernel<A, B, C, D, true, false, false> : bnv::rollout_kernel<A, B, C, D, false, false, false>;
 }
 template <bool A, bool B, bool C>
 RolloutFn pick_rollout3(bool d, bool e) {
@@ -181,6 +167,7 @@ RolloutFn pick_rollout1(bool b, bool c, bool d, bool e) {
 }
 RolloutFn pick_rollout(const bnv_mppi* h, bool philox) {
   const bool a = h->P.use_patch, b = h->P.geom.res_pow2, c = h->P.record, d = h->fast_angles;
+  if (h->stoch || h->E > 1) return bnv_pick_rollout_ext(a, b, philox, h->stoch, h->E > 1);  // record + fast angles
   return a ? pick_rollout1<true>(b, c, d, philox) : pick_rollout1<false>(b, c, d, philox);
 }
 template <bool A, bool B>
@@ -191,6 +178,33 @@ FinalizeFn pick_finalize(const bnv_mppi* h) {
   const bool a = h->P.use_patch, b = h->P.geom.res_pow2, c = h->fast_angles;
   if (a) return b ? pick_finalize2<true, true>(c) : pick_finalize2<true, false>(c);
   return b ? pick_finalize2<false, true>(c) : pick_finalize2<false, false>(c);
+}
+
+// Choose warps per CTA so that noise + recorded-state slabs fit shared memory; prefer 4 (one per SM sub-partition).
+// Also sets the kernels' shared-memory attribute and asks the runtime how many CTAs can be resident at once
+// (short horizons leave room for several CTAs per SM): a grid within that bound is launched cooperatively.
+int configure_launch(bnv_mppi* h) {
+  bnv::EngineParams& P = h->P;
+  const int cell = h->stoch ? 2 : 1;
+  for (int w = bnv::kMaxWarps; w >= 1; w >>= 1) {
+    bnv::RolloutSmem L = bnv::rollout_smem_layout(P.T, w, P.patch_w, P.patch_h, P.use_patch, P.record, cell);
+    if (static_cast<size_t>(L.total) <= kMaxDynSmem) {
+      h->warps = w;
+      h->rollout_smem = L.total;
+      h->grid = (h->Kl + w * 32 - 1) / (w * 32);
+      h->resident_ctas = 0;
+      for (bool philox : {false, true}) {
+        const void* fn = reinterpret_cast<const void*>(pick_rollout(h, philox));
+        BNV_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h->rollout_smem)));
+        int per_sm = 0;
+        BNV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, w * 32, h->rollout_smem));
+        const long long cap = static_cast<long long>(per_sm) * h->num_sms;
+        h->resident_ctas = philox ? std::min(h->resident_ctas, cap) : cap;
+      }
+      return BNV_OK;
+    }
+  }
+  return fail(BNV_ERR_UNSUPPORTED, "horizon %d does not fit the rollout kernel's shared-memory staging", P.T);
 }
 
 }  // namespace
@@ -212,6 +226,11 @@ int bnv_mppi_create(bnv_mppi** out, const bnv_mppi_cfg* cfg) {
     return fail(BNV_ERR_INVALID, "u_min must not exceed u_max");
   if (!(cfg->dt > 0.0f)) return fail(BNV_ERR_INVALID, "dt must be positive");
   if (cfg->num_samples < cfg->world_size) return fail(BNV_ERR_INVALID, "fewer samples than shards");
+  if (cfg->num_envs < 0 || cfg->num_envs > 65535) return fail(BNV_ERR_INVALID, "num_envs %d outside [0, 65535]", cfg->num_envs);
+  const int E = cfg->num_envs > 1 ? cfg->num_envs : 1;
+  const bool stoch = (cfg->flags & BNV_FLAG_STOCHASTIC_SLIP) != 0;
+  if ((E > 1 || stoch) && cfg->world_size != 1)
+    return fail(BNV_ERR_INVALID, "batched / stochastic-slip solvers need world_size == 1 (shard environments, not samples)");
   BNV_CUDA(cudaSetDevice(cfg->device));
   int major = 0;
   BNV_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, cfg->device));
@@ -220,28 +239,36 @@ int bnv_mppi_create(bnv_mppi** out, const bnv_mppi_cfg* cfg) {
   bnv_mppi* h = new (std::nothrow) bnv_mppi();
   if (!h) return fail(BNV_ERR_INVALID, "out of host memory");
   h->cfg = *cfg;
+  h->E = E;
+  h->stoch = stoch;
   const long long K = cfg->num_samples, W = cfg->world_size, r = cfg->rank;
   h->k_offset = static_cast<int>(r * K / W);  // shard = global samples [r K / W, (r+1) K / W)
   h->Kl = static_cast<int>((r + 1) * K / W) - h->k_offset;
   const int T = cfg->horizon, Kl = h->Kl;
-  const bool record = (cfg->flags & BNV_FLAG_RECORD_STATES) != 0;
+  const bool record = (cfg->flags & BNV_FLAG_RECORD_STATES) != 0 || E > 1 || stoch;
+  if ((E > 1 || stoch) && !(cfg->dt * std::max(std::fabs(cfg->u_min[1]), std::fabs(cfg->u_max[1])) < 3.0f)) {
+    delete h;
+    return fail(BNV_ERR_UNSUPPORTED, "batched / stochastic-slip solvers need dt * max|omega| < 3 rad per step");
+  }
   const size_t io_floats = 3 + 2 * static_cast<size_t>(T) + 3 * static_cast<size_t>(T + 1);
   cudaError_t e = cudaSuccess;
   auto alloc = [&](void** p, size_t bytes) {
     if (e == cudaSuccess) e = cudaMalloc(p, bytes);
   };
   const int max_grid = (Kl + 31) / 32;
-  alloc(reinterpret_cast<void**>(&h->noise), sizeof(float) * Kl * T * 2);
-  if (record) alloc(reinterpret_cast<void**>(&h->rec), sizeof(float) * Kl * (T + 1) * 3);
-  alloc(reinterpret_cast<void**>(&h->costs), sizeof(float) * Kl);
-  alloc(reinterpret_cast<void**>(&h->weights), sizeof(float) * Kl);
-  alloc(reinterpret_cast<void**>(&h->u_prev), sizeof(float) * T * 2);
-  alloc(reinterpret_cast<void**>(&h->part_ms), sizeof(float) * max_grid * 2);
-  alloc(reinterpret_cast<void**>(&h->part_u), sizeof(float) * max_grid * 2 * T);
+  const size_t nE = static_cast<size_t>(E);  // every per-solver buffer carries a leading E
+  alloc(reinterpret_cast<void**>(&h->noise), sizeof(float) * nE * Kl * T * 2);
+  if (record) alloc(reinterpret_cast<void**>(&h->rec), sizeof(float) * nE * Kl * (T + 1) * 3);
+  alloc(reinterpret_cast<void**>(&h->costs), sizeof(float) * nE * Kl);
+  alloc(reinterpret_cast<void**>(&h->weights), sizeof(float) * nE * Kl);
+  alloc(reinterpret_cast<void**>(&h->u_prev), sizeof(float) * nE * T * 2);
+  alloc(reinterpret_cast<void**>(&h->part_ms), sizeof(float) * nE * max_grid * 2);
+  alloc(reinterpret_cast<void**>(&h->part_u), sizeof(float) * nE * max_grid * 2 * T);
   alloc(reinterpret_cast<void**>(&h->shard_partial), sizeof(float) * (2 + 2 * T));
   alloc(reinterpret_cast<void**>(&h->io_dev), sizeof(float) * io_floats);
-  alloc(reinterpret_cast<void**>(&h->ticket), 2 * sizeof(unsigned int));
-  alloc(reinterpret_cast<void**>(&h->stats), 4 * sizeof(float));
+  alloc(reinterpret_cast<void**>(&h->ticket), 2 * nE * sizeof(unsigned int));
+  alloc(reinterpret_cast<void**>(&h->stats), 4 * nE * sizeof(float));
+  alloc(reinterpret_cast<void**>(&h->goals_dev), 2 * nE * sizeof(float));
   if (cfg->world_size > 1) {  // mailbox: 2 parities x world slots x (m, s, U[2T], flag, pad)
     h->mbox_floats = 2 * static_cast<size_t>(cfg->world_size) * (2 + 2 * static_cast<size_t>(T) + 2);
     alloc(reinterpret_cast<void**>(&h->mbox), sizeof(float) * h->mbox_floats);
@@ -249,10 +276,10 @@ int bnv_mppi_create(bnv_mppi** out, const bnv_mppi_cfg* cfg) {
     if (e == cudaSuccess) e = cudaMemset(h->mbox, 0, sizeof(float) * h->mbox_floats);
   }
   if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&h->io_host), sizeof(float) * io_floats, cudaHostAllocMapped);
-  if (e == cudaSuccess) e = cudaMemset(h->u_prev, 0, sizeof(float) * T * 2);  // mppi.py:116
-  if (e == cudaSuccess) e = cudaMemset(h->ticket, 0, 2 * sizeof(unsigned int));
-  if (e == cudaSuccess) e = cudaMemset(h->weights, 0, sizeof(float) * Kl);    // mppi.py:126-128
-  if (e == cudaSuccess && record) e = cudaMemset(h->rec, 0, sizeof(float) * Kl * (T + 1) * 3);  // mppi.py:119-125
+  if (e == cudaSuccess) e = cudaMemset(h->u_prev, 0, sizeof(float) * nE * T * 2);  // mppi.py:116
+  if (e == cudaSuccess) e = cudaMemset(h->ticket, 0, 2 * nE * sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMemset(h->weights, 0, sizeof(float) * nE * Kl);    // mppi.py:126-128
+  if (e == cudaSuccess && record) e = cudaMemset(h->rec, 0, sizeof(float) * nE * Kl * (T + 1) * 3);  // mppi.py:119-125
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
     free_all(h);
@@ -275,6 +302,11 @@ int bnv_mppi_create(bnv_mppi** out, const bnv_mppi_cfg* cfg) {
   P.k_offset = h->k_offset;
   P.rank = cfg->rank;
   P.peer_mbox = nullptr;
+  P.num_envs = E;
+  P.goals = nullptr;
+  P.keep_mean = 1;
+  P.xi_in = nullptr;
+  P.xi_opt_in = nullptr;
   P.Kl = Kl;
   P.T = T;
   P.world = cfg->world_size;
@@ -312,27 +344,44 @@ void bnv_mppi_destroy(bnv_mppi* h) {
 int bnv_mppi_set_problem(bnv_mppi* h, const float* risk_dev, int32_t grid_size, int32_t pitch, float resolution,
                          float x_min, float x_max, float y_min, float y_max, const float goal_xy[2],
                          float stuck_threshold, void* stream) {
-  if (!h || !risk_dev || !goal_xy) return fail(BNV_ERR_INVALID, "null argument");
+  if (h && h->E > 1) return fail(BNV_ERR_INVALID, "batched solver: use bnv_mppi_set_problem_ex (one goal per environment)");
+  if (h && h->stoch) return fail(BNV_ERR_INVALID, "stochastic-slip solver: use bnv_mppi_set_problem_ex (mean and std maps)");
+  return bnv_mppi_set_problem_ex(h, risk_dev, nullptr, grid_size, pitch, 0, resolution, x_min, x_max, y_min, y_max,
+                                 goal_xy, stuck_threshold, stream);
+}
+
+int bnv_mppi_set_problem_ex(bnv_mppi* h, const float* mean_dev, const float* std_dev, int32_t grid_size, int32_t pitch,
+                            int64_t env_stride, float resolution, float x_min, float x_max, float y_min, float y_max,
+                            const float* goals_xy, float stuck_threshold, void* stream) {
+  if (!h || !mean_dev || !goals_xy) return fail(BNV_ERR_INVALID, "null argument");
+  if (h->stoch != (std_dev != nullptr))
+    return fail(BNV_ERR_INVALID, h->stoch ? "stochastic-slip solver needs a std map" : "std map given to a deterministic solver");
   if (grid_size < 1 || pitch < grid_size) return fail(BNV_ERR_INVALID, "grid_size %d / pitch %d invalid", grid_size, pitch);
+  if (env_stride < 0) return fail(BNV_ERR_INVALID, "negative env_stride");
   if (!(resolution > 0.0f)) return fail(BNV_ERR_INVALID, "resolution must be positive");
   if (!(x_min < x_max) || !(y_min < y_max)) return fail(BNV_ERR_INVALID, "empty map limits");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   BNV_CUDA(cudaSetDevice(h->cfg.device));
   bnv::EngineParams& P = h->P;
-  const int G = grid_size;
+  const int G = grid_size, E = h->E;
+  const int cell = h->stoch ? 2 : 1;
   const int tpitch = (G + 3) & ~3;  // TMA needs a row stride that is a multiple of 16 bytes
-  if (!h->tau || P.G != G) {
-    if (h->tau) {
-      BNV_CUDA(cudaStreamSynchronize(s));
-      BNV_CUDA(cudaFree(h->tau));
-      h->tau = nullptr;
-    }
-    BNV_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->tau), sizeof(float) * static_cast<size_t>(G) * tpitch));
+  const size_t need = static_cast<size_t>(E) * G * tpitch * cell;
+  BNV_CUDA(cudaStreamSynchronize(s));  // earlier iterations may still read the map / goals
+  if (!h->tau || h->tau_floats != need) {
+    if (h->tau) BNV_CUDA(cudaFree(h->tau));
+    h->tau = nullptr;
+    BNV_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->tau), sizeof(float) * need));
+    h->tau_floats = need;
   }
-  dim3 grid((tpitch + 127) / 128, G);
-  bnv::trav_map_kernel<<<grid, 128, 0, s>>>(risk_dev, pitch, h->tau, tpitch, G);
+  dim3 grid((tpitch + 127) / 128, G, E);
+  if (h->stoch)
+    bnv::slip_map_kernel<<<grid, 128, 0, s>>>(mean_dev, std_dev, pitch, env_stride, reinterpret_cast<float2*>(h->tau), tpitch, G);
+  else
+    bnv::trav_map_kernel<<<grid, 128, 0, s>>>(mean_dev, pitch, env_stride, h->tau, tpitch, G);
   BNV_CUDA(cudaGetLastError());
   h->launches++;
+  BNV_CUDA(cudaMemcpy(h->goals_dev, goals_xy, sizeof(float) * 2 * E, cudaMemcpyHostToDevice));
 
   P.tau = h->tau;
   P.G = G;
@@ -344,8 +393,9 @@ int bnv_mppi_set_problem(bnv_mppi* h, const float* risk_dev, int32_t grid_size, 
   P.geom.res = resolution;
   P.geom.inv_res = 1.0f / resolution;
   P.geom.res_pow2 = is_pow2_float(resolution) ? 1 : 0;
-  P.goal_x = goal_xy[0];
-  P.goal_y = goal_xy[1];
+  P.goal_x = P.term_gx = goals_xy[0];
+  P.goal_y = P.term_gy = goals_xy[1];
+  P.goals = E > 1 ? h->goals_dev : nullptr;
   P.thr = stuck_threshold;
 
   // Reach bound: tau <= 1 and |v| <= vmax, so a rollout moves at most T * vmax * dt from the (clamped) start.
@@ -354,7 +404,7 @@ int bnv_mppi_set_problem(bnv_mppi* h, const float* risk_dev, int32_t grid_size, 
   const long long rho = static_cast<long long>(std::floor(reach_cells)) + 2;
   const long long side = 2 * rho + 1;
   const long long pw = (side + 3 + 3) & ~3LL;  // +3: the window's x origin is rounded down to a multiple of 4 cells
-  P.use_patch = (pw <= 256 && side <= 256 && pw * side * 4 <= kMaxPatchBytes) ? 1 : 0;
+  P.use_patch = (pw * cell <= 256 && side <= 256 && pw * side * 4 * cell <= kMaxPatchBytes) ? 1 : 0;
   if (debug_disable() & 1u) P.use_patch = 0;
   if (P.use_patch) {
     P.rho = static_cast<int>(rho);
@@ -362,9 +412,10 @@ int bnv_mppi_set_problem(bnv_mppi* h, const float* risk_dev, int32_t grid_size, 
     P.patch_h = static_cast<int>(side);
     EncodeTiledFn enc = get_encode_tiled();
     if (!enc) return fail(BNV_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
-    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(G), static_cast<cuuint64_t>(G)};
-    cuuint64_t gstride[1] = {static_cast<cuuint64_t>(tpitch) * sizeof(float)};
-    cuuint32_t box[2] = {static_cast<cuuint32_t>(P.patch_w), static_cast<cuuint32_t>(P.patch_h)};
+    // the E maps are stacked along y (environment e = rows [e G, (e+1) G)); a stochastic cell is two floats wide
+    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(G) * cell, static_cast<cuuint64_t>(G) * E};
+    cuuint64_t gstride[1] = {static_cast<cuuint64_t>(tpitch) * cell * sizeof(float)};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(P.patch_w * cell), static_cast<cuuint32_t>(P.patch_h)};
     cuuint32_t estride[2] = {1, 1};
     CUresult r = enc(&P.tau_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, h->tau, gdim, gstride, box, estride,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
@@ -378,17 +429,17 @@ int bnv_mppi_set_problem(bnv_mppi* h, const float* risk_dev, int32_t grid_size, 
   int rc = configure_launch(h);
   if (rc != BNV_OK) return rc;
   h->finalize_smem = 128 + (P.use_patch ? ((P.patch_w * P.patch_h + 31) / 32) * 32 * 4 : 0) + 2 * (2 * P.T + 4) * 4 + 16;
-  for (bool philox : {false, true})
-    BNV_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(pick_rollout(h, philox)),
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h->rollout_smem)));
-  BNV_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(pick_finalize(h)),
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h->finalize_smem)));
+  if (!h->stoch && E == 1)
+    BNV_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(pick_finalize(h)),
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h->finalize_smem)));
   h->problem_set = true;
   return BNV_OK;
 }
 
 static int launch_forward(bnv_mppi* h, const float* state_dev, const float* state_host, const float* noise_dev,
-                          float* u_out_dev, float* opt_states_dev, cudaStream_t s) {
+                          float* u_out_dev, float* opt_states_dev, cudaStream_t s, const float* xi_dev = nullptr,
+                          const float* xi_opt_dev = nullptr) {
+  if (state_host && h->E > 1) return fail(BNV_ERR_INVALID, "batched solver: states must be device-resident [E,3]");
   if (state_host) {  // state travels by value in the launch packet; remembered for finalize (world_size > 1)
     for (int i = 0; i < 3; ++i) h->P.state_val[i] = state_host[i];
     h->P.state_inline = 1;
@@ -399,6 +450,8 @@ static int launch_forward(bnv_mppi* h, const float* state_dev, const float* stat
   const bool philox = noise_dev == nullptr;
   P.noise_in = noise_dev;
   P.noise_out = h->noise;
+  P.xi_in = xi_dev;
+  P.xi_opt_in = xi_opt_dev;
   P.iter_lo = static_cast<uint32_t>(h->iteration);
   P.iter_hi = static_cast<uint32_t>(h->iteration >> 32);
   P.noise_bulk_ok = (!philox && (reinterpret_cast<uintptr_t>(noise_dev) & 15u) == 0) ? 1 : 0;
@@ -409,9 +462,9 @@ static int launch_forward(bnv_mppi* h, const float* state_dev, const float* stat
   h->P.state = state_dev;  // finalize (world_size > 1) re-reads the state of the iteration in flight
   P.u_out = u_out_dev;
   P.opt_rec = opt_states_dev;
-  // One CTA per SM (shared-memory bound): the grid is co-resident iff it has at most num_sms CTAs.  Then launch
-  // cooperatively (residency guaranteed by the driver) and use the deferred-store epilogue.
-  const bool coop = h->coop_ok && h->grid <= h->num_sms;
+  // The grid is co-resident iff it has at most resident_ctas CTAs (occupancy x SMs; one CTA per SM at long
+  // horizons).  Then launch cooperatively (residency guaranteed by the driver) and use the deferred-store epilogue.
+  const bool coop = h->coop_ok && static_cast<long long>(h->grid) * h->E <= h->resident_ctas;
   h->epoch = (h->epoch == 0xFFFFFFFFu) ? 1u : h->epoch + 1u;
   P.epoch = h->epoch;
   P.coop = coop ? 1 : 0;
@@ -423,7 +476,7 @@ static int launch_forward(bnv_mppi* h, const float* state_dev, const float* stat
   const bool timed = h->timing && h->ev_used + 2 <= h->ev.size();
   if (timed) BNV_CUDA(cudaEventRecord(h->ev[h->ev_used], s));
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(h->grid);
+  cfg.gridDim = dim3(h->grid, h->E);
   cfg.blockDim = dim3(h->warps * 32);
   cfg.dynamicSmemBytes = h->rollout_smem;
   cfg.stream = s;
@@ -449,8 +502,24 @@ int bnv_mppi_forward(bnv_mppi* h, const float* state_dev, const float* noise_dev
   if (!h->problem_set) return fail(BNV_ERR_STATE, "bnv_mppi_set_problem must be called before forward");
   if ((h->cfg.world_size == 1 || h->peers_attached) && (!u_out_dev || !opt_states_dev))
     return fail(BNV_ERR_INVALID, "null output buffer");
+  if (h->stoch && noise_dev) return fail(BNV_ERR_INVALID, "stochastic-slip solver: inject noise through bnv_mppi_forward_ex");
   BNV_CUDA(cudaSetDevice(h->cfg.device));
   return launch_forward(h, state_dev, nullptr, noise_dev, u_out_dev, opt_states_dev, static_cast<cudaStream_t>(stream));
+}
+
+int bnv_mppi_forward_ex(bnv_mppi* h, const float* state_dev, const float* noise_dev, const float* xi_dev,
+                        const float* xi_opt_dev, float* u_out_dev, float* opt_states_dev, void* stream) {
+  if (!h || !state_dev || !u_out_dev || !opt_states_dev) return fail(BNV_ERR_INVALID, "null argument");
+  if (!h->problem_set) return fail(BNV_ERR_STATE, "bnv_mppi_set_problem must be called before forward");
+  if (h->stoch) {
+    const bool all = noise_dev && xi_dev && xi_opt_dev, none = !noise_dev && !xi_dev && !xi_opt_dev;
+    if (!all && !none) return fail(BNV_ERR_INVALID, "noise_dev, xi_dev and xi_opt_dev must be all given or all NULL");
+  } else if (xi_dev || xi_opt_dev) {
+    return fail(BNV_ERR_INVALID, "lookup normals given to a deterministic solver");
+  }
+  BNV_CUDA(cudaSetDevice(h->cfg.device));
+  return launch_forward(h, state_dev, nullptr, noise_dev, u_out_dev, opt_states_dev, static_cast<cudaStream_t>(stream),
+                        xi_dev, xi_opt_dev);
 }
 
 int bnv_mppi_forward_state(bnv_mppi* h, const float state_host[3], const float* noise_dev, float* u_out_dev,
@@ -467,7 +536,8 @@ int bnv_mppi_forward_host(bnv_mppi* h, const float state_host[3], const float* n
                           float* opt_states_host, void* stream) {
   if (!h || !state_host || !u_out_host || !opt_states_host) return fail(BNV_ERR_INVALID, "null argument");
   if (!h->problem_set) return fail(BNV_ERR_STATE, "bnv_mppi_set_problem must be called before forward");
-  if (h->cfg.world_size != 1) return fail(BNV_ERR_INVALID, "forward_host needs world_size == 1");
+  if (h->cfg.world_size != 1 || h->E != 1) return fail(BNV_ERR_INVALID, "forward_host needs world_size == 1 and a single environment");
+  if (h->stoch && noise_dev) return fail(BNV_ERR_INVALID, "stochastic-slip solver: inject noise through bnv_mppi_forward_ex");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   BNV_CUDA(cudaSetDevice(h->cfg.device));
   const int T = h->P.T;
@@ -553,32 +623,33 @@ int bnv_mppi_top_samples(bnv_mppi* h, int32_t n, float* states_out_dev, float* w
   BNV_CUDA(cudaSetDevice(h->cfg.device));
   int n_pad = 1;
   while (n_pad < n) n_pad <<= 1;
-  if (h->top_idx_cap < static_cast<size_t>(n)) {
+  const size_t nE = static_cast<size_t>(h->E);
+  if (h->top_idx_cap < nE * n) {
     BNV_CUDA(cudaStreamSynchronize(s));
     if (h->top_idx) BNV_CUDA(cudaFree(h->top_idx));
     h->top_idx = nullptr;
-    BNV_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->top_idx), sizeof(int) * n));
-    h->top_idx_cap = n;
+    BNV_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->top_idx), sizeof(int) * nE * n));
+    h->top_idx_cap = nE * n;
   }
   unsigned long long* pairs_global = nullptr;
   size_t smem = static_cast<size_t>(n_pad) * 8;
   if (n_pad > bnv::kTopnSmemPairs) {
-    if (h->top_pairs_cap < static_cast<size_t>(n_pad)) {
+    if (h->top_pairs_cap < nE * n_pad) {
       BNV_CUDA(cudaStreamSynchronize(s));
       if (h->top_pairs) BNV_CUDA(cudaFree(h->top_pairs));
       h->top_pairs = nullptr;
-      BNV_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->top_pairs), sizeof(unsigned long long) * n_pad));
-      h->top_pairs_cap = n_pad;
+      BNV_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->top_pairs), sizeof(unsigned long long) * nE * n_pad));
+      h->top_pairs_cap = nE * n_pad;
     }
     pairs_global = h->top_pairs;
     smem = 0;
   }
   BNV_CUDA(cudaFuncSetAttribute(bnv::topn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 bnv::kTopnSmemPairs * 8));
-  bnv::topn_select_kernel<<<1, bnv::kTopnThreads, smem, s>>>(h->weights, h->Kl, n, n_pad, pairs_global,
-                                                              weights_out_dev, h->top_idx);
+  bnv::topn_select_kernel<<<h->E, bnv::kTopnThreads, smem, s>>>(h->weights, h->Kl, n, n_pad, pairs_global,
+                                                                 weights_out_dev, h->top_idx);
   BNV_CUDA(cudaGetLastError());
-  bnv::gather_rows_kernel<<<n, 128, 0, s>>>(h->rec, h->top_idx, 3 * (h->P.T + 1), states_out_dev);
+  bnv::gather_rows_kernel<<<dim3(n, h->E), 128, 0, s>>>(h->rec, h->top_idx, 3 * (h->P.T + 1), h->Kl, states_out_dev);
   BNV_CUDA(cudaGetLastError());
   h->launches += 2;
   return BNV_OK;
@@ -595,7 +666,7 @@ int32_t bnv_mppi_sample_offset(const bnv_mppi* h) { return h ? h->k_offset : 0; 
 int bnv_mppi_reset(bnv_mppi* h, void* stream) {
   if (!h) return fail(BNV_ERR_INVALID, "null argument");
   BNV_CUDA(cudaSetDevice(h->cfg.device));
-  BNV_CUDA(cudaMemsetAsync(h->u_prev, 0, sizeof(float) * h->P.T * 2, static_cast<cudaStream_t>(stream)));
+  BNV_CUDA(cudaMemsetAsync(h->u_prev, 0, sizeof(float) * h->E * h->P.T * 2, static_cast<cudaStream_t>(stream)));
   h->iteration = 0;
   h->have_weights = false;
   return BNV_OK;
@@ -607,12 +678,60 @@ int bnv_mppi_draw_noise(bnv_mppi* h, uint64_t iteration, void* stream) {
   const int T = h->P.T;
   const long long work = static_cast<long long>(h->Kl) * ((T + 1) / 2);
   const int blocks = static_cast<int>((work + 255) / 256);
-  bnv::noise_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  bnv::noise_kernel<<<dim3(blocks, h->E), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       h->noise, h->Kl, T, h->k_offset, static_cast<uint32_t>(h->cfg.seed), static_cast<uint32_t>(h->cfg.seed >> 32),
       static_cast<uint32_t>(iteration), static_cast<uint32_t>(iteration >> 32), h->cfg.sigma[0], h->cfg.sigma[1]);
   BNV_CUDA(cudaGetLastError());
   h->launches++;
   return BNV_OK;
+}
+
+int bnv_mppi_draw_xi(bnv_mppi* h, uint64_t iteration, float* xi_out_dev, float* xi_opt_out_dev, void* stream) {
+  if (!h || !xi_out_dev || !xi_opt_out_dev) return fail(BNV_ERR_INVALID, "null argument");
+  if (!h->stoch) return fail(BNV_ERR_STATE, "not a stochastic-slip solver");
+  BNV_CUDA(cudaSetDevice(h->cfg.device));
+  const int T = h->P.T;
+  const long long work = static_cast<long long>(h->Kl + 1) * ((T + 1) / 2);
+  const int blocks = static_cast<int>((work + 255) / 256);
+  bnv::xi_kernel<<<dim3(blocks, h->E), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      xi_out_dev, xi_opt_out_dev, h->Kl, T, h->k_offset, static_cast<uint32_t>(h->cfg.seed),
+      static_cast<uint32_t>(h->cfg.seed >> 32), static_cast<uint32_t>(iteration), static_cast<uint32_t>(iteration >> 32));
+  BNV_CUDA(cudaGetLastError());
+  h->launches++;
+  return BNV_OK;
+}
+
+int bnv_mppi_set_keep_mean(bnv_mppi* h, int32_t keep) {
+  if (!h) return fail(BNV_ERR_INVALID, "null argument");
+  h->P.keep_mean = keep ? 1 : 0;
+  return BNV_OK;
+}
+
+int bnv_mppi_set_terminal_goal(bnv_mppi* h, const float goal_xy[2]) {
+  if (!h || !goal_xy) return fail(BNV_ERR_INVALID, "null argument");
+  if (h->E > 1) return fail(BNV_ERR_INVALID, "not available on a batched solver");
+  h->P.term_gx = goal_xy[0];
+  h->P.term_gy = goal_xy[1];
+  return BNV_OK;
+}
+
+int bnv_mppi_set_goal_dev(bnv_mppi* h, const float* goal_dev) {
+  if (!h) return fail(BNV_ERR_INVALID, "null argument");
+  if (h->E > 1) return fail(BNV_ERR_INVALID, "not available on a batched solver");
+  h->P.goals = goal_dev;
+  return BNV_OK;
+}
+
+int bnv_mppi_argmin(bnv_mppi* h, const float* actions_dev, float* action_out_dev, float* states_out_dev,
+                    int32_t* index_out_dev, void* stream) {
+  if (!h || !actions_dev || !action_out_dev || !states_out_dev) return fail(BNV_ERR_INVALID, "null argument");
+  if (!h->P.record) return fail(BNV_ERR_STATE, "argmin needs BNV_FLAG_RECORD_STATES");
+  if (!h->have_weights || h->E > 1) return fail(BNV_ERR_STATE, "argmin needs a completed forward of a single solver");
+  BNV_CUDA(cudaSetDevice(h->cfg.device));
+  int rc = bnv_launch_argmin(h->costs, h->Kl, actions_dev, h->rec, 3 * (h->P.T + 1), action_out_dev, states_out_dev,
+                             index_out_dev, static_cast<cudaStream_t>(stream));
+  if (rc == BNV_OK) h->launches++;
+  return rc;
 }
 
 uint64_t bnv_mppi_launch_count(const bnv_mppi* h) { return h ? h->launches : 0; }

@@ -14,6 +14,12 @@
 // traversability window staged by one 2-D TMA load.  At K = 16384 there is at most one warp per scheduler: the
 // kernel is bound by the per-step dependency chain, not by bandwidth, so the loop body is branch-free, keeps
 // every invariant in registers, and fills the chain's stall slots with the next step pair's Philox draw.
+//
+// Two optional modes (template flags, separate instantiations so the single-solver path pays nothing):
+//   kBatch  blockIdx.y = environment: E independent MPPI problems (own map, state, goal, mean sequence) in ONE
+//           launch (BASELINE config 3); every per-environment buffer is the single-solver layout with a leading E.
+//   kStoch  stochastic slip (BASELINE config 4): the window holds the cell's slip (mean, std); every lookup draws
+//           tau = 1 - clamp(mean + std * xi, 0, 1) with a fresh xi ~ N(0,1) (traversability_model.py:65-69).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -30,11 +36,16 @@ constexpr int kFinalizeThreads = 128;
 
 struct alignas(64) EngineParams {
   CUtensorMap tau_map;  // 2-D tiled descriptor over the padded tau map, box = patch_w x patch_h
-  const float* tau;     // [G][pitch]
-  int G, pitch;
+  const float* tau;     // [E][G][pitch] traversability, or [E][G][pitch][2] slip (mean, std) in stochastic mode
+  int G, pitch;         // pitch in cells
   GridGeom geom;
   Bounds bounds;
   float goal_x, goal_y, thr;
+  float term_gx, term_gy;  // goal of the terminal cost: the goal itself, except under DWA's sub-goal (dwa.py:225-233)
+  const float* goals;      // kBatch: [E][2] goal per environment (device); else optional [2] device override of goal_x/y
+  int num_envs;            // E (1 unless kBatch)
+  const float* xi_in;      // kStoch, injected: [E][Kl][2T+1] lookup normals (transit t, stage t interleaved; terminal last)
+  const float* xi_opt_in;  // kStoch, injected: [E][T] lookup normals of the optimal rollout
   float lambda, inv_lambda, icov0, icov1;  // temperature, 1/sigma^2 (diag of mppi.py:95 inverse covariance)
   int lambda_pow2;                        // lambda is a power of two: -c * (1/lambda) == -c / lambda exactly
   float sigma0, sigma1;
@@ -61,6 +72,7 @@ struct alignas(64) EngineParams {
   unsigned int* ticket;  // [0] arrival counter of the last-CTA election, [1] "merge done" epoch flag (coop)
   float* stats;          // [2] (M, S) of the last merge, published to the waiting CTAs (coop)
   unsigned int epoch;    // unique per launch
+  int keep_mean;         // write u* back as the next call's mean sequence (mppi.py:217); 0 for DWA's constant actions
   int coop;              // grid is co-resident (cooperative launch): deferred slab stores, in-register weights
   float* const* peer_mbox;  // [world] device pointers to every rank's mailbox (peer memory over NVLink), or null
   unsigned int xchg_seq;    // exchange sequence number (same on every rank), selects the mailbox parity
@@ -81,18 +93,18 @@ struct alignas(64) EngineParams {
 
 // Shared-memory carve-up of the rollout kernel (identical on host and device).
 struct RolloutSmem {
-  int off_patch, off_noise, off_v, off_rec, off_uprev, off_coef, off_e, off_warpu, off_red, total;
+  int off_patch, off_noise, off_rec, off_uprev, off_coef, off_e, off_warpu, off_red, off_merge, total;
 };
+constexpr int kMergeACap = 1024;    // fast grid merge: per-CTA rescale factors kept in shared memory
+constexpr int kMergeGrpCap = 1024;  // ... and ngrp x 2T partial column sums
 __host__ __device__ inline RolloutSmem rollout_smem_layout(int T, int warps, int patch_w, int patch_h, int use_patch,
-                                                           int record) {
+                                                           int record, int cell_floats = 1) {
   RolloutSmem s;
   int spb = warps * 32;
   int off = 128;  // [0,128): mbarriers (1 patch + kMaxWarps noise) and the last-CTA flag
   s.off_patch = off;
-  off += use_patch ? ((patch_w * patch_h * 4 + 127) / 128) * 128 : 0;
+  off += use_patch ? ((patch_w * patch_h * cell_floats * 4 + 127) / 128) * 128 : 0;
   s.off_noise = off;
-  off += ((spb * 2 * T * 4 + 127) / 128) * 128;
-  s.off_v = off;
   off += ((spb * 2 * T * 4 + 127) / 128) * 128;
   s.off_rec = off;
   off += record ? ((spb * 3 * (T + 1) * 4 + 127) / 128) * 128 : 0;
@@ -106,29 +118,46 @@ __host__ __device__ inline RolloutSmem rollout_smem_layout(int T, int warps, int
   off += ((kMaxWarps * 2 * T * 4 + 15) / 16) * 16;
   s.off_red = off;
   off += 64 * 4;
+  s.off_merge = off;  // last CTA only: a_g [kMergeACap], group column sums [max(kMergeGrpCap, 2T)]
+  off += (kMergeACap + (2 * T > kMergeGrpCap ? 2 * T : kMergeGrpCap)) * 4;
   s.total = off;
   return s;
 }
 
+#ifndef BNV_ROLLOUT_ONLY
 // --------------------------------------------------------------------------------------------- tau map
-__global__ void trav_map_kernel(const float* __restrict__ risk, int risk_pitch, float* __restrict__ tau, int pitch,
-                                int G) {
+// blockIdx.z = environment: `env_stride` elements between consecutive environments' risk maps (0 = shared map).
+__global__ void trav_map_kernel(const float* __restrict__ risk, int risk_pitch, long long env_stride,
+                                float* __restrict__ tau, int pitch, int G) {
   int x = blockIdx.x * blockDim.x + threadIdx.x;
   int y = blockIdx.y;
   if (x >= pitch) return;
+  const float* src = risk + static_cast<size_t>(blockIdx.z) * env_stride;
   float v = 0.0f;
   if (x < G) {
-    float r = risk[static_cast<size_t>(y) * risk_pitch + x];
+    float r = src[static_cast<size_t>(y) * risk_pitch + x];
     // torch.clamp propagates NaN; fminf/fmaxf would not
     float c = (r != r) ? r : fminf(fmaxf(r, 0.0f), 1.0f);
     v = __fsub_rn(1.0f, c);
   }
-  tau[static_cast<size_t>(y) * pitch + x] = v;
+  tau[(static_cast<size_t>(blockIdx.z) * G + y) * pitch + x] = v;
+}
+
+// Stochastic mode: interleave the slip distribution's (mean, std) per cell, [E][G][pitch][2].
+__global__ void slip_map_kernel(const float* __restrict__ mean, const float* __restrict__ stdv, int src_pitch,
+                                long long env_stride, float2* __restrict__ out, int pitch, int G) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x;
+  int y = blockIdx.y;
+  if (x >= pitch) return;
+  const size_t off = static_cast<size_t>(blockIdx.z) * env_stride + static_cast<size_t>(y) * src_pitch + x;
+  float2 v = make_float2(0.0f, 0.0f);
+  if (x < G) v = make_float2(mean[off], stdv[off]);
+  out[(static_cast<size_t>(blockIdx.z) * G + y) * pitch + x] = v;
 }
 
 // --------------------------------------------------------------------------------------------- noise
 // Stand-alone draw of the engine's noise stream: one thread = one (sample, step pair) = noise[k][2p..2p+1][0..1].
-// Bit-identical to what rollout_kernel<kPhilox> produces in its loop (same noise_pair()).
+// Bit-identical to what rollout_kernel<kPhilox> produces in its loop (same noise_pair()).  blockIdx.y = environment.
 __global__ void __launch_bounds__(256) noise_kernel(float* __restrict__ noise, int Kl, int T, int k_offset,
                                                     uint32_t seed_lo, uint32_t seed_hi, uint32_t iter_lo,
                                                     uint32_t iter_hi, float sigma0, float sigma1) {
@@ -137,12 +166,48 @@ __global__ void __launch_bounds__(256) noise_kernel(float* __restrict__ noise, i
   if (gid >= static_cast<long long>(Kl) * pairs) return;
   int k = static_cast<int>(gid / pairs);
   int p = static_cast<int>(gid - static_cast<long long>(k) * pairs);
-  const float4 n = noise_pair(static_cast<uint32_t>(k + k_offset), static_cast<uint32_t>(p), iter_lo, iter_hi,
-                              make_uint2(seed_lo, seed_hi), sigma0, sigma1);
-  float* dst = noise + (static_cast<size_t>(k) * T + 2 * p) * 2;
+  const uint32_t env = blockIdx.y;
+  const float4 n = noise_pair(static_cast<uint32_t>(k + k_offset), static_cast<uint32_t>(p), iter_lo,
+                              iter_hi + (env << 16), make_uint2(seed_lo, seed_hi), sigma0, sigma1);
+  float* dst = noise + ((static_cast<size_t>(env) * Kl + k) * T + 2 * p) * 2;
   *reinterpret_cast<float2*>(dst) = make_float2(n.x, n.y);
   if (2 * p + 1 < T) *reinterpret_cast<float2*>(dst + 2) = make_float2(n.z, n.w);
 }
+
+// Stand-alone draw of the stochastic mode's lookup normals (same xi_quad() calls as the rollout kernel):
+// xi [E][Kl][2T+1] = (transit 0, stage 0, transit 1, stage 1, ..., terminal), xi_opt [E][T] for the optimal rollout.
+// One thread = one (sample, step pair); sample index Kl stands for the optimal rollout.
+__global__ void __launch_bounds__(256) xi_kernel(float* __restrict__ xi, float* __restrict__ xi_opt, int Kl, int T,
+                                                 int k_offset, uint32_t seed_lo, uint32_t seed_hi, uint32_t iter_lo,
+                                                 uint32_t iter_hi) {
+  const int pairs = (T + 1) >> 1;
+  long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= static_cast<long long>(Kl + 1) * pairs) return;
+  const int k = static_cast<int>(gid / pairs);
+  const int p = static_cast<int>(gid - static_cast<long long>(k) * pairs);
+  const uint32_t env = blockIdx.y;
+  const uint32_t ih = iter_hi + (env << 16);
+  const uint2 key = make_uint2(seed_lo, seed_hi);
+  if (k == Kl) {
+    const float4 q = xi_quad(kOptimalSample, static_cast<uint32_t>(p), iter_lo, ih, key);
+    float* dst = xi_opt + static_cast<size_t>(env) * T;
+    dst[2 * p] = q.x;
+    if (2 * p + 1 < T) dst[2 * p + 1] = q.z;
+    return;
+  }
+  const uint32_t kg = static_cast<uint32_t>(k + k_offset);
+  const float4 q = xi_quad(kg, static_cast<uint32_t>(p), iter_lo, ih, key);
+  float* row = xi + (static_cast<size_t>(env) * Kl + k) * (2 * T + 1);
+  row[4 * p] = q.x;
+  row[4 * p + 1] = q.y;
+  if (2 * p + 1 < T) {
+    row[4 * p + 2] = q.z;
+    row[4 * p + 3] = q.w;
+  }
+  if (p == 0) row[2 * T] = xi_quad(kg, kXiTerminalPair, iter_lo, ih, key).x;
+}
+
+#endif  // BNV_ROLLOUT_ONLY
 
 // --------------------------------------------------------------------------------------------- helpers
 __device__ __forceinline__ float warp_max(float v) {
@@ -181,23 +246,26 @@ __device__ __forceinline__ WindowGeom window_for_state(const EngineParams& P, fl
   return w;
 }
 
-__device__ __forceinline__ StepConsts make_step_consts(const EngineParams& P, const WindowGeom& wg, const float* patch_s) {
+// kCell = floats per window cell: 1 (traversability) or 2 (slip mean, std).  `tau_env` = this environment's map.
+__device__ __forceinline__ StepConsts make_step_consts(const EngineParams& P, const WindowGeom& wg, const float* patch_s,
+                                                       const float* tau_env, float gx, float gy, int cell_floats) {
   StepConsts c;
   c.x_min = P.geom.x_min; c.y_min = P.geom.y_min; c.x_max = P.geom.x_max; c.y_max = P.geom.y_max;
   c.res = P.geom.res; c.inv_res = P.geom.inv_res; c.dt = P.bounds.dt;
-  c.gx = P.goal_x; c.gy = P.goal_y; c.thr = P.thr;
+  c.gx = gx; c.gy = gy; c.thr = P.thr;
   c.u_min0 = P.bounds.u_min0; c.u_min1 = P.bounds.u_min1; c.u_max0 = P.bounds.u_max0; c.u_max1 = P.bounds.u_max1;
   c.lo_x = wg.lo_x; c.hi_x = wg.hi_x; c.lo_y = wg.lo_y; c.hi_y = wg.hi_y;
+  const uint32_t esz = 4u * static_cast<uint32_t>(cell_floats);
   if (P.use_patch) {
     c.pitch = P.patch_w;
-    c.win_addr = smem_u32(patch_s) - 4u * static_cast<uint32_t>(wg.oy * P.patch_w + wg.ox);
+    c.win_addr = smem_u32(patch_s) - esz * static_cast<uint32_t>(wg.oy * P.patch_w + wg.ox);
     c.map = nullptr;
   } else {
     c.pitch = P.pitch;
     c.win_addr = 0u;
-    c.map = P.tau;
+    c.map = tau_env;
   }
-  c.finish();
+  c.finish(esz);
   return c;
 }
 
@@ -206,23 +274,47 @@ __device__ __forceinline__ float score_of(float cost, const EngineParams& P) {
   return P.lambda_pow2 ? __fmul_rn(-cost, P.inv_lambda) : __fdiv_rn(-cost, P.lambda);
 }
 
+// Where the lookup normals of the stochastic mode come from: injected (tests) or the engine's Philox stream.
+struct XiSource {
+  const float* row;  // injected: this sample's [2T+1] normals (or the optimal rollout's [T]); null = Philox
+  uint32_t sample, iter_lo, iter_hi;
+  uint2 key;
+};
+
 // Batch-1 optimal rollout (mppi.py:202-214) by one thread: first step with the general math, the rest fast.
 // `uc_s` holds u* already clamped to the action bounds: transit re-clamps the action (robot_model.py:82-83) and
-// u*, a rounded weighted sum, may leave the bounds by an ulp.
-template <bool kPatch, bool kPow2, bool kFastAngles>
-__device__ void optimal_rollout(const EngineParams& P, const StepConsts& c, const float* uc_s, float sx, float sy,
-                                float sth) {
-  const int T = P.T;
+// u*, a rounded weighted sum, may leave the bounds by an ulp.  `out` = [T+1][3] recorded states.
+// kStoch: every transit draws its own lookup normal (injected xi.row[t], or Philox sample id kOptimalSample).
+template <bool kPatch, bool kPow2, bool kFastAngles, bool kStoch>
+__device__ void optimal_rollout(int T, const StepConsts& c, const float* uc_s, float sx, float sy, float sth,
+                                float* out, const XiSource& xi) {
   float x = sx, y = sy, th = sth, xr, yr, thr;
-  float tau = lookup_tau<kPatch, kPow2, false>(c, x, y);
+  float tau = 0.0f;
+  float2 ms = make_float2(0.0f, 0.0f);
+  float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto xi_at = [&](int t) -> float {
+    if (xi.row != nullptr) return __ldg(xi.row + t);
+    if ((t & 1) == 0) q = xi_quad(xi.sample, static_cast<uint32_t>(t >> 1), xi.iter_lo, xi.iter_hi, xi.key);
+    return (t & 1) ? q.z : q.x;
+  };
+  if (kStoch) {
+    ms = lookup_slip<kPatch, kPow2, false>(c, x, y);
+    tau = slip_to_trav(ms, xi_at(0));
+  } else {
+    tau = lookup_tau<kPatch, kPow2, false>(c, x, y);
+  }
   const float2* u2 = reinterpret_cast<const float2*>(uc_s);
   float2 u = u2[0];
   unicycle_step<false>(c, tau, u.x, u.y, x, y, th, xr, yr, thr);
-  float* out = P.opt_rec;
   out[0] = xr; out[1] = yr; out[2] = thr;
 #pragma unroll 2
   for (int t = 1; t < T; ++t) {
-    tau = lookup_tau<kPatch, kPow2, true>(c, x, y);
+    if (kStoch) {
+      ms = lookup_slip<kPatch, kPow2, true>(c, x, y);
+      tau = slip_to_trav(ms, xi_at(t));
+    } else {
+      tau = lookup_tau<kPatch, kPow2, true>(c, x, y);
+    }
     u = u2[t];
     unicycle_step<kFastAngles>(c, tau, u.x, u.y, x, y, th, xr, yr, thr);
     out[3 * t + 0] = xr; out[3 * t + 1] = yr; out[3 * t + 2] = thr;
@@ -234,18 +326,18 @@ __device__ void optimal_rollout(const EngineParams& P, const StepConsts& c, cons
 // other SMs, so every load is an L2 round trip).  scale_of(g) gives the factor of CTA g's samples.
 template <typename ScaleFn>
 __device__ __forceinline__ void rescale_weights(float* weights, int Kl, int spb_shift, int wt, int wn, ScaleFn scale_of) {
-  const int n4 = Kl >> 2;
+  const int n4 = ((reinterpret_cast<uintptr_t>(weights) & 15u) == 0u) ? (Kl >> 2) : 0;  // float4 path needs alignment
   float4* w4 = reinterpret_cast<float4*>(weights);
-  constexpr int kBatch = 8;
-  for (int base = 0; base < n4; base += wn * kBatch) {
-    float4 ev[kBatch];
+  constexpr int kBatchLoads = 8;
+  for (int base = 0; base < n4; base += wn * kBatchLoads) {
+    float4 ev[kBatchLoads];
 #pragma unroll
-    for (int j = 0; j < kBatch; ++j) {
+    for (int j = 0; j < kBatchLoads; ++j) {
       const int q = base + j * wn + wt;
       if (q < n4) ev[j] = __ldcg(w4 + q);
     }
 #pragma unroll
-    for (int j = 0; j < kBatch; ++j) {
+    for (int j = 0; j < kBatchLoads; ++j) {
       const int q = base + j * wn + wt;
       if (q < n4) {
         const float a = scale_of((q << 2) >> spb_shift);  // spb is a multiple of 4: a float4 never straddles CTAs
@@ -274,7 +366,10 @@ __device__ void finish_iteration(const EngineParams& P, const StepConsts& c, flo
     P.u_prev[i] = u;
   }
   __syncthreads();
-  if (tid == 0) optimal_rollout<kPatch, kPow2, kFastAngles>(P, c, uc_s, sx, sy, sth);
+  if (tid == 0) {
+    XiSource none{};
+    optimal_rollout<kPatch, kPow2, kFastAngles, false>(T, c, uc_s, sx, sy, sth, P.opt_rec, none);
+  }
   // With more than one warp the serial optimal rollout keeps warp 0 busy and the other warps rescale underneath it.
   const bool split = nthr > 32;
   if (split && tid < 32) return;
@@ -285,18 +380,21 @@ __device__ void finish_iteration(const EngineParams& P, const StepConsts& c, flo
 
 // --------------------------------------------------------------------------------------------- rollout
 // Slabs -> HBM: recorded states (and the drawn noise), one bulk store per warp slab; asynchronous, the caller
-// waits for the shared-memory reads (bulk_wait_read_all) before the CTA exits.
+// waits for the shared-memory reads (bulk_wait_read_all) before the CTA exits.  rec_env / noise_env = this
+// environment's [Kl][T+1][3] / [Kl][T][2] arrays.
 template <bool kRecord, bool kPhilox>
-__device__ __forceinline__ void store_slabs(const EngineParams& P, float* rec_s, float* nz_w, int warp, int lane,
-                                            int warp_first, int warp_rows, uint32_t nz_bytes) {
+__device__ __forceinline__ void store_slabs(const EngineParams& P, float* rec_env, float* noise_env, float* rec_s,
+                                            float* nz_w, int warp, int lane, int warp_first, int warp_rows,
+                                            uint32_t nz_bytes) {
   if (warp_rows <= 0 || !(kRecord || kPhilox)) return;
   const int T = P.T;
-  float* rec_g = P.rec + static_cast<size_t>(warp_first) * 3 * (T + 1);
+  float* rec_g = rec_env + static_cast<size_t>(warp_first) * 3 * (T + 1);
   const uint32_t rec_bytes = static_cast<uint32_t>(warp_rows) * 3u * (T + 1) * 4u;
   float* rec_w = rec_s + warp * 32 * 3 * (T + 1);
-  float* nz_g = P.noise_out + static_cast<size_t>(warp_first) * 2 * T;
-  const bool rec_bulk = kRecord && P.rec_bulk_ok && (rec_bytes & 15u) == 0u;
-  const bool out_bulk = kPhilox && (nz_bytes & 15u) == 0u;  // the engine's buffer is 256 B aligned
+  float* nz_g = noise_env + static_cast<size_t>(warp_first) * 2 * T;
+  const bool rec_bulk = kRecord && P.rec_bulk_ok && (rec_bytes & 15u) == 0u &&
+                        (reinterpret_cast<uintptr_t>(rec_g) & 15u) == 0u;
+  const bool out_bulk = kPhilox && (nz_bytes & 15u) == 0u && (reinterpret_cast<uintptr_t>(nz_g) & 15u) == 0u;
   fence_proxy_async_smem();
   __syncwarp();
   if (elect_one()) {
@@ -336,26 +434,38 @@ __device__ __forceinline__ void st_release_gpu(unsigned int* p, unsigned int v) 
 // state, shared lookup for the stage cost and the next step, cost accumulation.
 struct SampleState {
   float x, y, th, tau, stage_sum, act0, act1;
+  float2 ms;  // kStoch: (mean, std) of the slip distribution in the current cell
 };
 
 // ucf_s[t] = (u_prev[t][0], u_prev[t][1], u_prev[t][0] / sigma0^2, u_prev[t][1] / sigma1^2): one 16-byte load per step.
-template <bool kPatch, bool kPow2, bool kRecord, bool kFastStep>
-__device__ __forceinline__ void sample_step(SampleState& s, const StepConsts& C, int t, float nx, float ny,
-                                            const float4* ucf_s, float* vrow, float* rrow) {
+// The clamped control v is not kept: the weighted-sum pass recomputes it from the noise slab with the same two ops.
+// kStoch: xi_tr / xi_st = lookup normals of this step's transit and of the stage cost of its recorded state; the two
+// lookups hit the same cell (the index clamp makes cell(raw successor) == cell(clamped successor)), so the (mean, std)
+// fetch is shared and only the draw differs.
+template <bool kPatch, bool kPow2, bool kRecord, bool kFastStep, bool kStoch>
+__device__ __forceinline__ void sample_step(SampleState& s, const StepConsts& C, int t, float nx, float ny, float xi_tr,
+                                            float xi_st, const float4* ucf_s, float* rrow) {
   const float4 uc = ucf_s[t];
   const float v0 = clampf(__fadd_rn(uc.x, nx), C.u_min0, C.u_max0);  // mppi.py:152-157
   const float v1 = clampf(__fadd_rn(uc.y, ny), C.u_min1, C.u_max1);
-  *reinterpret_cast<float2*>(vrow + 2 * t) = make_float2(v0, v1);    // kept for the weighted control sum
   float xr, yr, thr;
-  unicycle_step<kFastStep>(C, s.tau, v0, v1, s.x, s.y, s.th, xr, yr, thr);
+  const float tau_dyn = kStoch ? slip_to_trav(s.ms, xi_tr) : s.tau;
+  unicycle_step<kFastStep>(C, tau_dyn, v0, v1, s.x, s.y, s.th, xr, yr, thr);
   if (kRecord) {
     rrow[3 * t + 0] = xr;
     rrow[3 * t + 1] = yr;
     rrow[3 * t + 2] = thr;
   }
   // one lookup serves the stage cost of the recorded (raw) position and the next dynamics step
-  s.tau = lookup_tau<kPatch, kPow2, true>(C, s.x, s.y);
-  s.stage_sum = __fadd_rn(s.stage_sum, goal_and_stuck_cost(C, xr, yr, s.tau));
+  float tau_cost;
+  if (kStoch) {
+    s.ms = lookup_slip<kPatch, kPow2, true>(C, s.x, s.y);
+    tau_cost = slip_to_trav(s.ms, xi_st);
+  } else {
+    s.tau = lookup_tau<kPatch, kPow2, true>(C, s.x, s.y);
+    tau_cost = s.tau;
+  }
+  s.stage_sum = __fadd_rn(s.stage_sum, goal_and_stuck_cost(C, xr, yr, tau_cost));
   s.act0 = fmaf(uc.z, v0, s.act0);  // u_prev[t]^T Sigma^-1 v (mppi.py:178-182), one running sum per control dim
   s.act1 = fmaf(uc.w, v1, s.act1);
 }
@@ -363,8 +473,9 @@ __device__ __forceinline__ void sample_step(SampleState& s, const StepConsts& C,
 // kPatch: traversability window staged in shared memory by TMA (else looked up in the global map);
 // kPow2: resolution is a power of two (multiply instead of divide in the cell index);
 // kRecord: keep every sample's recorded states; kFastAngles: dt * max|omega| < pi (branch-free steps 1..T-1);
-// kPhilox: draw the noise in the loop (else it is injected and bulk-loaded from HBM).
-template <bool kPatch, bool kPow2, bool kRecord, bool kFastAngles, bool kPhilox>
+// kPhilox: draw the noise in the loop (else it is injected and bulk-loaded from HBM);
+// kStoch: stochastic-slip lookups; kBatch: blockIdx.y = environment.
+template <bool kPatch, bool kPow2, bool kRecord, bool kFastAngles, bool kPhilox, bool kStoch, bool kBatch>
 __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid_constant__ EngineParams P) {
   extern __shared__ __align__(128) unsigned char smem[];
   const long long t_start = clock64();
@@ -372,19 +483,34 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
   const int T = P.T;
   const int nwarps = blockDim.x >> 5;
   const int spb = nwarps * 32;
-  const RolloutSmem L = rollout_smem_layout(T, nwarps, P.patch_w, P.patch_h, kPatch, kRecord);
+  constexpr int kCell = kStoch ? 2 : 1;
+  const RolloutSmem L = rollout_smem_layout(T, nwarps, P.patch_w, P.patch_h, kPatch, kRecord, kCell);
   uint64_t* bar_patch = reinterpret_cast<uint64_t*>(smem);
   uint64_t* bar_noise = reinterpret_cast<uint64_t*>(smem) + 1;  // [kMaxWarps]
   int* last_flag = reinterpret_cast<int*>(smem + 64);
   float* patch_s = reinterpret_cast<float*>(smem + L.off_patch);
   float* noise_s = reinterpret_cast<float*>(smem + L.off_noise);
-  float* v_s = reinterpret_cast<float*>(smem + L.off_v);
   float* rec_s = reinterpret_cast<float*>(smem + L.off_rec);
   float* uprev_s = reinterpret_cast<float*>(smem + L.off_uprev);
   float* coef_s = reinterpret_cast<float*>(smem + L.off_coef);
   float* e_s = reinterpret_cast<float*>(smem + L.off_e);
   float* warpu_s = reinterpret_cast<float*>(smem + L.off_warpu);
   float* red_s = reinterpret_cast<float*>(smem + L.off_red);
+
+  // ---- this CTA's environment: every per-solver array carries a leading E in batch mode
+  const int env = kBatch ? static_cast<int>(blockIdx.y) : 0;
+  const size_t eK = static_cast<size_t>(env) * P.Kl;                 // first sample row of the environment
+  const size_t eB = static_cast<size_t>(env) * gridDim.x;            // first per-CTA partial of the environment
+  float* const u_prev_e = P.u_prev + static_cast<size_t>(env) * 2 * T;
+  float* const costs_e = P.costs + eK;
+  float* const weights_e = P.weights + eK;
+  float* const rec_e = kRecord ? P.rec + eK * 3 * (T + 1) : nullptr;
+  float* const noise_out_e = P.noise_out + eK * 2 * T;
+  float* const part_ms_e = P.part_ms + eB * 2;
+  float* const part_u_e = P.part_u + eB * 2 * T;
+  unsigned int* const ticket_e = P.ticket + 2 * env;  // [0] arrival counter, [1] "merge done" epoch flag
+  float* const stats_e = P.stats + 2 * env;
+  const uint32_t iter_hi_e = P.iter_hi + (static_cast<uint32_t>(env) << 16);  // Philox counter word 3 carries the env
 
   const int cta_first = blockIdx.x * spb;
   const int warp_first = cta_first + warp * 32;
@@ -402,11 +528,12 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
 
   // ---- injected noise: stage this warp's slab, rows [warp_first, warp_first+warp_rows) x 2T floats, contiguous in HBM
   float* nz_w = noise_s + warp * 32 * 2 * T;
-  float* v_w = v_s + warp * 32 * 2 * T;
   const uint32_t nz_bytes = static_cast<uint32_t>(warp_rows) * 2u * T * 4u;
-  const bool nz_bulk = P.noise_bulk_ok && ((nz_bytes & 15u) == 0u) && warp_rows > 0;
+  bool nz_bulk = false;
   if (!kPhilox) {
-    const float* nz_g = P.noise_in + static_cast<size_t>(warp_first) * 2 * T;
+    const float* nz_g = P.noise_in + (eK + warp_first) * 2 * T;
+    nz_bulk = P.noise_bulk_ok && ((nz_bytes & 15u) == 0u) && warp_rows > 0 &&
+              (reinterpret_cast<uintptr_t>(nz_g) & 15u) == 0u;
     if (nz_bulk) {
       if (elect_one()) {
         mbar_arrive_expect_tx(bar_noise + warp, nz_bytes);
@@ -416,34 +543,43 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
       for (int i = lane; i < warp_rows * 2 * T; i += 32) nz_w[i] = nz_g[i];
     }
   }
-  // v rows of a ragged warp that carry no sample: keep them finite (the weighted-sum pass multiplies them by 0)
-  for (int i = warp_rows * 2 * T + lane; i < 32 * 2 * T; i += 32) v_w[i] = 0.0f;
+  // noise rows of a ragged warp that carry no sample: keep them finite (the weighted-sum pass multiplies the
+  // controls rebuilt from them by 0)
+  for (int i = warp_rows * 2 * T + lane; i < 32 * 2 * T; i += 32) nz_w[i] = 0.0f;
 
   // ---- state, window geometry, traversability window via TMA
-  const float sx = P.state_inline ? P.state_val[0] : __ldg(P.state);
-  const float sy = P.state_inline ? P.state_val[1] : __ldg(P.state + 1);
-  const float sth = P.state_inline ? P.state_val[2] : __ldg(P.state + 2);
+  const float* state_e = P.state + 3 * env;
+  const float sx = P.state_inline ? P.state_val[0] : __ldg(state_e);
+  const float sy = P.state_inline ? P.state_val[1] : __ldg(state_e + 1);
+  const float sth = P.state_inline ? P.state_val[2] : __ldg(state_e + 2);
   const WindowGeom wg = window_for_state(P, sx, sy);
   if (kPatch) {
     if (warp == 0) {
       if (elect_one()) {
-        mbar_arrive_expect_tx(bar_patch, static_cast<uint32_t>(P.patch_w * P.patch_h * 4));
-        tma_load_2d(patch_s, &P.tau_map, wg.ox, wg.oy, bar_patch);
+        mbar_arrive_expect_tx(bar_patch, static_cast<uint32_t>(P.patch_w * P.patch_h * 4 * kCell));
+        tma_load_2d(patch_s, &P.tau_map, wg.ox * kCell, wg.oy + env * P.G, bar_patch);
       }
     }
   }
-  StepConsts C = make_step_consts(P, wg, patch_s);
+  const float* tau_e = P.tau + static_cast<size_t>(env) * P.G * P.pitch * kCell;
+  // goal: per environment (batch), a device-resident override (DWA's sub-goal, selected on the device), or by value
+  const float gx = kBatch ? __ldg(P.goals + 2 * env) : (P.goals != nullptr ? __ldg(P.goals) : P.goal_x);
+  const float gy = kBatch ? __ldg(P.goals + 2 * env + 1) : (P.goals != nullptr ? __ldg(P.goals + 1) : P.goal_y);
+  const float term_gx = kBatch ? gx : P.term_gx, term_gy = kBatch ? gy : P.term_gy;
+  StepConsts C = make_step_consts(P, wg, patch_s, tau_e, gx, gy, kCell);
 
   // first step pair of the Philox stream: drawn while the TMA window and the mean sequence are in flight
   const uint32_t kg = static_cast<uint32_t>(k + P.k_offset);
   const uint2 key = make_uint2(P.seed_lo, P.seed_hi);
   float sig0 = P.sigma0, sig1 = P.sigma1;
   float4 nz_cur = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (kPhilox) nz_cur = noise_pair(kg, 0u, P.iter_lo, P.iter_hi, key, sig0, sig1);
+  float4 xi_cur = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (kPhilox) nz_cur = noise_pair(kg, 0u, P.iter_lo, iter_hi_e, key, sig0, sig1);
+  if (kPhilox && kStoch) xi_cur = xi_quad(kg, 0u, P.iter_lo, iter_hi_e, key);
 
   // mean sequence and the per-step action-cost coefficients u_prev[t] Sigma^-1 (mppi.py:178-181)
   for (int i = tid; i < 2 * T; i += blockDim.x) {
-    const float u = P.u_prev[i];
+    const float u = u_prev_e[i];
     uprev_s[i] = u;
     float* uc = coef_s + 4 * (i >> 1) + (i & 1);
     uc[0] = u;
@@ -464,12 +600,15 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
   // ---- T-step rollout, one sample per thread
   float cost = FLT_MAX;
   float* nrow = nz_w + lane * 2 * T;
-  float* vrow = v_w + lane * 2 * T;
   float* rrow = rec_s + (warp * 32 + lane) * 3 * (T + 1);
   if (valid) {
     SampleState s;
     s.x = sx; s.y = sy; s.th = sth; s.stage_sum = 0.0f; s.act0 = 0.0f; s.act1 = 0.0f;
-    s.tau = lookup_tau<kPatch, kPow2, false>(C, s.x, s.y);
+    s.tau = 0.0f;
+    s.ms = make_float2(0.0f, 0.0f);
+    if (kStoch) s.ms = lookup_slip<kPatch, kPow2, false>(C, s.x, s.y);
+    else s.tau = lookup_tau<kPatch, kPow2, false>(C, s.x, s.y);
+    const float* xrow = (kStoch && !kPhilox) ? P.xi_in + (eK + k) * (2 * T + 1) : nullptr;
     // Steps are processed in pairs (one Philox call yields both steps' noise).  The pair after the current one is
     // drawn in the same straight-line block as the current pair's steps -- unconditionally, so that there is no
     // branch and ptxas can interleave its ~100 independent instructions into the stall slots of the dependency
@@ -480,7 +619,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
       float4 nz;
       if (kPhilox) {
         nz = nz_cur;
-        nz_cur = noise_pair(kg, static_cast<uint32_t>(p + 1), P.iter_lo, P.iter_hi, key, sig0, sig1);
+        nz_cur = noise_pair(kg, static_cast<uint32_t>(p + 1), P.iter_lo, iter_hi_e, key, sig0, sig1);
       } else {
         const float2 a = *reinterpret_cast<const float2*>(nrow + 4 * p);
         const float2 b = *reinterpret_cast<const float2*>(nrow + 4 * p + 2);
@@ -488,39 +627,66 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
       }
       return nz;
     };
+    auto fetch_xi = [&](int p) -> float4 {  // lookup normals (transit 2p, stage 2p, transit 2p+1, stage 2p+1)
+      float4 xq = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (kStoch) {
+        if (kPhilox) {
+          xq = xi_cur;
+          xi_cur = xi_quad(kg, static_cast<uint32_t>(p + 1), P.iter_lo, iter_hi_e, key);
+        } else {
+          xq = make_float4(__ldg(xrow + 4 * p), __ldg(xrow + 4 * p + 1), __ldg(xrow + 4 * p + 2), __ldg(xrow + 4 * p + 3));
+        }
+      }
+      return xq;
+    };
     if (nfull >= 1) {
       const float4 nz = fetch_pair(0);
+      const float4 xq = fetch_xi(0);
       if (kPhilox) {
         *reinterpret_cast<float2*>(nrow) = make_float2(nz.x, nz.y);
         *reinterpret_cast<float2*>(nrow + 2) = make_float2(nz.z, nz.w);
       }
-      sample_step<kPatch, kPow2, kRecord, false>(s, C, 0, nz.x, nz.y, ucf_s, vrow, rrow);
-      sample_step<kPatch, kPow2, kRecord, kFastAngles>(s, C, 1, nz.z, nz.w, ucf_s, vrow, rrow);
+      sample_step<kPatch, kPow2, kRecord, false, kStoch>(s, C, 0, nz.x, nz.y, xq.x, xq.y, ucf_s, rrow);
+      sample_step<kPatch, kPow2, kRecord, kFastAngles, kStoch>(s, C, 1, nz.z, nz.w, xq.z, xq.w, ucf_s, rrow);
       for (int p = 1; p < nfull; ++p) {
         const float4 nq = fetch_pair(p);
+        const float4 xp = fetch_xi(p);
         if (kPhilox) {
           *reinterpret_cast<float2*>(nrow + 4 * p) = make_float2(nq.x, nq.y);
           *reinterpret_cast<float2*>(nrow + 4 * p + 2) = make_float2(nq.z, nq.w);
         }
-        sample_step<kPatch, kPow2, kRecord, kFastAngles>(s, C, 2 * p, nq.x, nq.y, ucf_s, vrow, rrow);
-        sample_step<kPatch, kPow2, kRecord, kFastAngles>(s, C, 2 * p + 1, nq.z, nq.w, ucf_s, vrow, rrow);
+        sample_step<kPatch, kPow2, kRecord, kFastAngles, kStoch>(s, C, 2 * p, nq.x, nq.y, xp.x, xp.y, ucf_s, rrow);
+        sample_step<kPatch, kPow2, kRecord, kFastAngles, kStoch>(s, C, 2 * p + 1, nq.z, nq.w, xp.z, xp.w, ucf_s, rrow);
       }
     }
     if (T & 1) {  // last (or only) step of an odd horizon: first half of pair nfull
       float2 nl;
+      float xl_tr = 0.0f, xl_st = 0.0f;
       if (kPhilox) {
         nl = make_float2(nz_cur.x, nz_cur.y);
         *reinterpret_cast<float2*>(nrow + 4 * nfull) = nl;
+        xl_tr = xi_cur.x;
+        xl_st = xi_cur.y;
       } else {
         nl = *reinterpret_cast<const float2*>(nrow + 4 * nfull);
+        if (kStoch) {
+          xl_tr = __ldg(xrow + 4 * nfull);
+          xl_st = __ldg(xrow + 4 * nfull + 1);
+        }
       }
-      if (nfull == 0) sample_step<kPatch, kPow2, kRecord, false>(s, C, 0, nl.x, nl.y, ucf_s, vrow, rrow);
-      else sample_step<kPatch, kPow2, kRecord, kFastAngles>(s, C, T - 1, nl.x, nl.y, ucf_s, vrow, rrow);
+      if (nfull == 0) sample_step<kPatch, kPow2, kRecord, false, kStoch>(s, C, 0, nl.x, nl.y, xl_tr, xl_st, ucf_s, rrow);
+      else sample_step<kPatch, kPow2, kRecord, kFastAngles, kStoch>(s, C, T - 1, nl.x, nl.y, xl_tr, xl_st, ucf_s, rrow);
     }
     if (kRecord) { rrow[3 * T + 0] = s.x; rrow[3 * T + 1] = s.y; rrow[3 * T + 2] = s.th; }
-    const float terminal = goal_and_stuck_cost(C, s.x, s.y, s.tau);                            // mppi.py:184
+    // terminal cost (mppi.py:184; objectives.py:65): same cell as the last stage cost, its own draw when stochastic
+    float tau_term = s.tau;
+    if (kStoch) {
+      const float xt = kPhilox ? xi_quad(kg, kXiTerminalPair, P.iter_lo, iter_hi_e, key).x : __ldg(xrow + 2 * T);
+      tau_term = slip_to_trav(s.ms, xt);
+    }
+    const float terminal = goal_and_stuck_cost_at(C, term_gx, term_gy, s.x, s.y, tau_term);
     cost = __fadd_rn(__fadd_rn(s.stage_sum, terminal), __fmul_rn(P.lambda, s.act0 + s.act1));   // mppi.py:186-190
-    P.costs[k] = cost;
+    costs_e[k] = cost;
   }
   const long long t_loop1 = clock64();
 
@@ -536,19 +702,22 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
   float ws = warp_sum(e);
   if (lane == 0) red_s[8 + warp] = ws;
   __syncwarp();
-  // each warp: columns over lanes, its own 32 samples; v_w holds the clamped controls, e_s the un-normalised weights
+  // each warp: columns over lanes, its own 32 samples; the clamped controls v = clamp(u_prev + noise) are rebuilt from
+  // the noise slab (the same two ops as in sample_step), e_s holds the un-normalised weights
   {
     const float4* e4 = reinterpret_cast<const float4*>(e_s + warp * 32);
     for (int c = lane; c < 2 * T; c += 32) {
-      const float* col = v_w + c;
+      const float* col = nz_w + c;
+      const float um = uprev_s[c];
+      const float lo = (c & 1) ? C.u_min1 : C.u_min0, hi = (c & 1) ? C.u_max1 : C.u_max0;
       float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f, acc3 = 0.0f;
 #pragma unroll
-      for (int r4 = 0; r4 < 8; ++r4) {  // rows past warp_rows carry e = 0 and zeros
+      for (int r4 = 0; r4 < 8; ++r4) {  // rows past warp_rows carry e = 0 and zero noise
         const float4 ev = e4[r4];
-        acc0 = fmaf(ev.x, col[(4 * r4 + 0) * 2 * T], acc0);
-        acc1 = fmaf(ev.y, col[(4 * r4 + 1) * 2 * T], acc1);
-        acc2 = fmaf(ev.z, col[(4 * r4 + 2) * 2 * T], acc2);
-        acc3 = fmaf(ev.w, col[(4 * r4 + 3) * 2 * T], acc3);
+        acc0 = fmaf(ev.x, clampf(__fadd_rn(um, col[(4 * r4 + 0) * 2 * T]), lo, hi), acc0);
+        acc1 = fmaf(ev.y, clampf(__fadd_rn(um, col[(4 * r4 + 1) * 2 * T]), lo, hi), acc1);
+        acc2 = fmaf(ev.z, clampf(__fadd_rn(um, col[(4 * r4 + 2) * 2 * T]), lo, hi), acc2);
+        acc3 = fmaf(ev.w, clampf(__fadd_rn(um, col[(4 * r4 + 3) * 2 * T]), lo, hi), acc3);
       }
       warpu_s[warp * 2 * T + c] = (acc0 + acc1) + (acc2 + acc3);
     }
@@ -559,11 +728,11 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
   for (int c = tid; c < 2 * T; c += blockDim.x) {
     float acc = 0.0f;
     for (int w = 0; w < nwarps; ++w) acc += warpu_s[w * 2 * T + c];
-    P.part_u[static_cast<size_t>(blockIdx.x) * 2 * T + c] = acc;
+    part_u_e[static_cast<size_t>(blockIdx.x) * 2 * T + c] = acc;
   }
   if (tid == 0) {
-    P.part_ms[2 * blockIdx.x + 0] = m_cta;
-    P.part_ms[2 * blockIdx.x + 1] = s_cta;
+    part_ms_e[2 * blockIdx.x + 0] = m_cta;
+    part_ms_e[2 * blockIdx.x + 1] = s_cta;
   }
   // Two epilogue schedules.  coop (the whole grid is co-resident; cooperative launch): the slab stores (17 MB over
   // the grid) are held back until the last CTA has merged the partials -- issued earlier, their burst through
@@ -572,53 +741,53 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
   // the last CTA rescales all weights.
   const bool coop = P.coop != 0;
   if (!coop) {
-    if (valid) P.weights[k] = e;  // exp(score - m_cta); rescaled by the last CTA
-    store_slabs<kRecord, kPhilox>(P, rec_s, nz_w, warp, lane, warp_first, warp_rows, nz_bytes);
+    if (valid) weights_e[k] = e;  // exp(score - m_cta); rescaled by the last CTA
+    store_slabs<kRecord, kPhilox>(P, rec_e, noise_out_e, rec_s, nz_w, warp, lane, warp_first, warp_rows, nz_bytes);
   }
   const long long t_part = clock64();
 
-  // ---- grid-wide merge by the last CTA to finish (atomic ticket).  The CTA barrier orders every thread's writes
-  // before thread 0's acq_rel atomic (cumulativity): the release half publishes this CTA's partial, the acquire
-  // half (in the CTA that draws the last ticket) makes every other CTA's partial visible to the loads below.
+  // ---- grid-wide merge (per environment) by the last CTA to finish (atomic ticket).  The CTA barrier orders every
+  // thread's writes before thread 0's acq_rel atomic (cumulativity): the release half publishes this CTA's partial,
+  // the acquire half (in the CTA that draws the last ticket) makes every other CTA's partial visible to the loads below.
   __syncthreads();
   if (tid == 0) {
-    unsigned int prev = atom_add_acq_rel_gpu(P.ticket, 1u);
+    unsigned int prev = atom_add_acq_rel_gpu(ticket_e, 1u);
     *last_flag = (prev == gridDim.x - 1) ? 1 : 0;
   }
   __syncthreads();
   const bool is_last = *last_flag != 0;
   float M = 0.0f, S = 1.0f;
   if (is_last) {
-    if (P.dbg_ts != nullptr && tid == 0) {
+    const bool stamp = P.dbg_ts != nullptr && env == 0;
+    if (stamp && tid == 0) {
       P.dbg_ts[0] = t_start; P.dbg_ts[1] = t_loop0; P.dbg_ts[2] = t_loop1; P.dbg_ts[3] = t_part;
     }
-    BNV_STAMP(4);
+    if (stamp) BNV_STAMP(4);
     const int nblk = gridDim.x;
     const int ncol = 2 * T;
-    float* a_s = v_s;  // per-CTA rescale factors exp(m_g - M); the v slab is dead by now
-    const int a_cap = (spb * 2 * T) / 2;
-    float* grp_s = v_s + a_cap;  // [ngrp][ncol] partial column sums
+    float* a_s = reinterpret_cast<float*>(smem + L.off_merge);  // per-CTA rescale factors exp(m_g - M)
+    float* grp_s = a_s + kMergeACap;                             // [ngrp][ncol] partial column sums
     // Fast path (2T a multiple of 4, one float4 column unit per thread, every a_g in shared memory): everything the
     // merge needs from other SMs -- (m_g, s_g) and this thread's share of the U_g rows -- is requested up front and
     // consumed from registers, so the merge costs one L2 round trip.  Fixed assignment and fixed-order sums keep
     // the result bit-reproducible.
     constexpr int kMsCache = 8, kMergeBatch = 32;
     const int nunit = ncol >> 2;
-    const bool fast_merge = (ncol & 3) == 0 && nunit <= static_cast<int>(blockDim.x) && nblk <= a_cap &&
-                            nblk <= kMsCache * static_cast<int>(blockDim.x);
+    const bool fast_merge = (ncol & 3) == 0 && nunit <= static_cast<int>(blockDim.x) && nblk <= kMergeACap &&
+                            ncol <= kMergeGrpCap && nblk <= kMsCache * static_cast<int>(blockDim.x);
     int ngrp = 1;
     if (fast_merge) {
-      ngrp = min(min(static_cast<int>(blockDim.x) / nunit, a_cap / ncol), nblk);
+      ngrp = min(min(static_cast<int>(blockDim.x) / nunit, kMergeGrpCap / ncol), nblk);
       float2 ms[kMsCache];
 #pragma unroll
       for (int j = 0; j < kMsCache; ++j) {
         const int g = tid + j * static_cast<int>(blockDim.x);
         ms[j] = make_float2(-FLT_MAX, 0.0f);
-        if (g < nblk) ms[j] = __ldcg(reinterpret_cast<const float2*>(P.part_ms) + g);
+        if (g < nblk) ms[j] = __ldcg(reinterpret_cast<const float2*>(part_ms_e) + g);
       }
       const int unit = tid % nunit, grp = tid / nunit;
       const int cnt = (grp < ngrp) ? (nblk - grp + ngrp - 1) / ngrp : 0;  // CTAs grp, grp + ngrp, ... owned by this thread
-      const float4* src = reinterpret_cast<const float4*>(P.part_u + static_cast<size_t>(grp) * ncol) + unit;
+      const float4* src = reinterpret_cast<const float4*>(part_u_e + static_cast<size_t>(grp) * ncol) + unit;
       const size_t stride4 = static_cast<size_t>(ngrp) * nunit;
       float4 pv[kMergeBatch];
 #pragma unroll
@@ -629,11 +798,11 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
       float lm = -FLT_MAX;
 #pragma unroll
       for (int j = 0; j < kMsCache; ++j) lm = fmaxf(lm, ms[j].x);
-      BNV_STAMP(12);
+      if (stamp) BNV_STAMP(12);
       lm = warp_max(lm);
       if (lane == 0) red_s[16 + warp] = lm;
       __syncthreads();
-      BNV_STAMP(13);
+      if (stamp) BNV_STAMP(13);
       M = red_s[16];
       for (int w = 1; w < nwarps; ++w) M = fmaxf(M, red_s[16 + w]);
       float lsum = 0.0f;
@@ -649,7 +818,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
       lsum = warp_sum(lsum);
       if (lane == 0) red_s[24 + warp] = lsum;
       __syncthreads();
-      BNV_STAMP(14);
+      if (stamp) BNV_STAMP(14);
       if (cnt > 0) {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         const float* ap = a_s + grp;
@@ -676,7 +845,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
     } else {
       // general path (odd horizons, very long horizons, very many CTAs): plain loops, a_g recomputed on the fly
       float lm = -FLT_MAX;
-      for (int g = tid; g < nblk; g += blockDim.x) lm = fmaxf(lm, __ldcg(P.part_ms + 2 * g));
+      for (int g = tid; g < nblk; g += blockDim.x) lm = fmaxf(lm, __ldcg(part_ms_e + 2 * g));
       lm = warp_max(lm);
       if (lane == 0) red_s[16 + warp] = lm;
       __syncthreads();
@@ -684,17 +853,17 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
       for (int w = 1; w < nwarps; ++w) M = fmaxf(M, red_s[16 + w]);
       float lsum = 0.0f;
       for (int g = tid; g < nblk; g += blockDim.x)
-        lsum = fmaf(__expf(__ldcg(P.part_ms + 2 * g) - M), __ldcg(P.part_ms + 2 * g + 1), lsum);
+        lsum = fmaf(__expf(__ldcg(part_ms_e + 2 * g) - M), __ldcg(part_ms_e + 2 * g + 1), lsum);
       lsum = warp_sum(lsum);
       if (lane == 0) red_s[24 + warp] = lsum;
       for (int c = tid; c < ncol; c += blockDim.x) {
         float acc = 0.0f;
         for (int g = 0; g < nblk; ++g)
-          acc = fmaf(__expf(__ldcg(P.part_ms + 2 * g) - M), __ldcg(P.part_u + static_cast<size_t>(g) * ncol + c), acc);
+          acc = fmaf(__expf(__ldcg(part_ms_e + 2 * g) - M), __ldcg(part_u_e + static_cast<size_t>(g) * ncol + c), acc);
         grp_s[c] = acc;
       }
     }
-    BNV_STAMP(15);
+    if (stamp) BNV_STAMP(15);
     __syncthreads();
     S = 0.0f;
     for (int w = 0; w < nwarps; ++w) S += red_s[24 + w];
@@ -709,7 +878,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
     // its own mailbox and merges the W partials in rank order -- identical arithmetic on every rank, so every rank
     // holds the same u*.  Mailboxes are double-buffered by the parity of the exchange sequence number: a rank can
     // be at most one iteration ahead of the slowest peer.
-    const bool fused = P.world > 1 && P.peer_mbox != nullptr;
+    const bool fused = !kBatch && P.world > 1 && P.peer_mbox != nullptr;
     float m_shard = M;  // reference of the per-sample exponentials already computed on this shard
     if (fused) {
       const int W = P.world, plen = 2 + ncol, slot = plen + 2;
@@ -746,17 +915,18 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
     }
     const bool complete = P.world == 1 || fused;  // (M, S, U) now cover every sample of the solver
     if (coop && tid == 0) {  // publish (M, S) and release the waiting CTAs as early as possible
-      P.stats[0] = M;
-      P.stats[1] = S;
-      st_release_gpu(P.ticket + 1, P.epoch);
+      stats_e[0] = M;
+      stats_e[1] = S;
+      st_release_gpu(ticket_e + 1, P.epoch);
     }
     if (complete) {
+      float* u_out_e = P.u_out + static_cast<size_t>(env) * ncol;
       for (int c = tid; c < ncol; c += blockDim.x) {
         const float u = __fdiv_rn(uprev_s[c], S);  // u* = U / S (mppi.py:196-199)
         uprev_s[c] = u;
         warpu_s[c] = clampf(u, (c & 1) ? C.u_min1 : C.u_min0, (c & 1) ? C.u_max1 : C.u_max0);  // for the optimal rollout
-        P.u_out[c] = u;
-        P.u_prev[c] = u;  // next call's mean sequence, unshifted (mppi.py:217)
+        u_out_e[c] = u;
+        if (P.keep_mean) u_prev_e[c] = u;  // next call's mean sequence, unshifted (mppi.py:217)
       }
     } else {  // unfused sharding: hand the shard partial to the host-side exchange + finalize_kernel
       if (tid == 0) {
@@ -766,20 +936,25 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
       for (int c = tid; c < ncol; c += blockDim.x) P.shard_partial[2 + c] = uprev_s[c];
     }
     __syncthreads();
-    BNV_STAMP(5);
-    if (tid == 0) *P.ticket = 0u;  // re-arm for the next launch
-    BNV_STAMP(6);
+    if (stamp) BNV_STAMP(5);
+    if (tid == 0) *ticket_e = 0u;  // re-arm for the next launch
+    if (stamp) BNV_STAMP(6);
     if (!coop) {
       // the other warps rescale every sample's weight underneath warp 0's serial optimal rollout:
       // weights[k] = exp(score_k - m_cta) * exp(m_cta - M) / S (softmax, mppi.py:193; 1/S deferred when unfused-sharded)
       const float inv_s = complete ? __fdiv_rn(__expf(m_shard - M), S) : 1.0f;
       const bool own_thread = complete && blockDim.x > 32;
-      auto scale_of = [&](int g) { return fast_merge ? a_s[g] : __expf(__ldcg(P.part_ms + 2 * g) - m_shard); };
-      if (complete && tid == 0) optimal_rollout<kPatch, kPow2, kFastAngles>(P, C, warpu_s, sx, sy, sth);
-      BNV_STAMP(7);
+      auto scale_of = [&](int g) { return fast_merge ? a_s[g] : __expf(__ldcg(part_ms_e + 2 * g) - m_shard); };
+      if (complete && tid == 0) {
+        const XiSource xs{(kStoch && !kPhilox) ? P.xi_opt_in + static_cast<size_t>(env) * T : nullptr, kOptimalSample,
+                          P.iter_lo, iter_hi_e, key};
+        optimal_rollout<kPatch, kPow2, kFastAngles, kStoch>(T, C, warpu_s, sx, sy, sth,
+                                                            P.opt_rec + static_cast<size_t>(env) * 3 * (T + 1), xs);
+      }
+      if (stamp) BNV_STAMP(7);
       if (!(own_thread && tid < 32)) {
         if (!own_thread) __syncwarp();
-        rescale_weights(P.weights, P.Kl, 31 - __clz(spb), own_thread ? tid - 32 : tid,
+        rescale_weights(weights_e, P.Kl, 31 - __clz(spb), own_thread ? tid - 32 : tid,
                         own_thread ? static_cast<int>(blockDim.x) - 32 : static_cast<int>(blockDim.x),
                         [&](int g) { return scale_of(g) * inv_s; });
       }
@@ -787,25 +962,31 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
   } else if (coop) {
     // wait for the last CTA's merge (all CTAs are co-resident: cooperative launch), then pick up (M, S)
     if (tid == 0) {
-      while (ld_acquire_gpu(P.ticket + 1) != P.epoch) __nanosleep(32);
+      while (ld_acquire_gpu(ticket_e + 1) != P.epoch) __nanosleep(32);
     }
     __syncthreads();
-    M = __ldcg(P.stats);
-    S = __ldcg(P.stats + 1);
+    M = __ldcg(stats_e);
+    S = __ldcg(stats_e + 1);
   }
   if (coop) {
     // softmax weight of this thread's sample straight from registers (mppi.py:193; 1/S deferred when unfused-sharded)
-    const bool complete = P.world == 1 || P.peer_mbox != nullptr;
-    if (valid) P.weights[k] = e * __expf(m_cta - M) * (complete ? __fdiv_rn(1.0f, S) : 1.0f);
-    store_slabs<kRecord, kPhilox>(P, rec_s, nz_w, warp, lane, warp_first, warp_rows, nz_bytes);
-    if (is_last && complete && tid == 0) optimal_rollout<kPatch, kPow2, kFastAngles>(P, C, warpu_s, sx, sy, sth);
-    if (is_last) BNV_STAMP(7);
+    const bool complete = P.world == 1 || (!kBatch && P.peer_mbox != nullptr);
+    if (valid) weights_e[k] = e * __expf(m_cta - M) * (complete ? __fdiv_rn(1.0f, S) : 1.0f);
+    store_slabs<kRecord, kPhilox>(P, rec_e, noise_out_e, rec_s, nz_w, warp, lane, warp_first, warp_rows, nz_bytes);
+    if (is_last && complete && tid == 0) {
+      const XiSource xs{(kStoch && !kPhilox) ? P.xi_opt_in + static_cast<size_t>(env) * T : nullptr, kOptimalSample,
+                        P.iter_lo, iter_hi_e, key};
+      optimal_rollout<kPatch, kPow2, kFastAngles, kStoch>(T, C, warpu_s, sx, sy, sth,
+                                                          P.opt_rec + static_cast<size_t>(env) * 3 * (T + 1), xs);
+    }
+    if (is_last && P.dbg_ts != nullptr && env == 0) BNV_STAMP(7);
   }
   // shared memory must stay allocated until the bulk stores have read it
   if (kRecord || kPhilox) bulk_wait_read_all();
-  if (is_last) BNV_STAMP_ANY(10, 32);
+  if (is_last && P.dbg_ts != nullptr && env == 0) BNV_STAMP_ANY(10, 32);
 }
 
+#ifndef BNV_ROLLOUT_ONLY
 // --------------------------------------------------------------------------------------------- finalize (multi-GPU)
 // gathered: [world][2+2T] shard partials, identical on every rank -> every rank computes the same u*.
 // One CTA: merges, rescales this shard's weights (they hold exp(score - M_shard)), writes the outputs and runs
@@ -836,7 +1017,7 @@ __global__ void __launch_bounds__(kFinalizeThreads) finalize_kernel(const __grid
       }
     }
   }
-  StepConsts C = make_step_consts(P, wg, patch_s);
+  StepConsts C = make_step_consts(P, wg, patch_s, P.tau, P.goal_x, P.goal_y, 1);
   float M = -FLT_MAX;
   for (int g = 0; g < P.world; ++g) M = fmaxf(M, gathered[g * plen]);
   float S = 0.0f;
@@ -865,6 +1046,11 @@ __global__ void __launch_bounds__(kTopnThreads) topn_select_kernel(const float* 
                                                                    int n_pad, unsigned long long* pairs_global,
                                                                    float* __restrict__ out_w, int* __restrict__ out_idx) {
   extern __shared__ __align__(128) unsigned char smem[];
+  // blockIdx.x = environment (batch mode): each CTA selects within its own [K] weights
+  weights += static_cast<size_t>(blockIdx.x) * K;
+  out_w += static_cast<size_t>(blockIdx.x) * n;
+  out_idx += static_cast<size_t>(blockIdx.x) * n;
+  if (pairs_global) pairs_global += static_cast<size_t>(blockIdx.x) * n_pad;
   __shared__ unsigned int hist[256];
   __shared__ unsigned int sel_prefix, sel_remaining, n_gt, n_eq;
   unsigned long long* pairs = pairs_global ? pairs_global : reinterpret_cast<unsigned long long*>(smem);
@@ -935,11 +1121,12 @@ __global__ void __launch_bounds__(kTopnThreads) topn_select_kernel(const float* 
   }
 }
 
-// out[i][:] = rec[idx[i]][:], row = 3 (T+1) floats.
-__global__ void gather_rows_kernel(const float* __restrict__ rec, const int* __restrict__ idx, int row_len,
+// out[e][i][:] = rec[e][idx[e][i]][:], row = 3 (T+1) floats; blockIdx.y = environment e with K rows each.
+__global__ void gather_rows_kernel(const float* __restrict__ rec, const int* __restrict__ idx, int row_len, int K,
                                    float* __restrict__ out) {
-  const float* src = rec + static_cast<size_t>(idx[blockIdx.x]) * row_len;
-  float* dst = out + static_cast<size_t>(blockIdx.x) * row_len;
+  const size_t e = blockIdx.y, n = gridDim.x;
+  const float* src = rec + (e * K + idx[e * n + blockIdx.x]) * row_len;
+  float* dst = out + (e * n + blockIdx.x) * row_len;
   for (int i = threadIdx.x; i < row_len; i += blockDim.x) dst[i] = src[i];
 }
 
@@ -948,5 +1135,7 @@ __global__ void sincos_debug_kernel(const float* __restrict__ th, float* __restr
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) sincos_heading<false>(th[i], &s[i], &c[i]);
 }
+
+#endif  // BNV_ROLLOUT_ONLY
 
 }  // namespace bnv

@@ -48,10 +48,11 @@ struct StepConsts {
   // "magic floor" variants (see lookup_tau): indices carry the bias kMagicBits, folded into bounds and base
   int mlo_x, mhi_x, mlo_y, mhi_y;
   uint32_t mwin_addr;
-  __device__ __forceinline__ void finish() {
+  // elem_bytes: 4 (one traversability value per cell) or 8 (interleaved slip mean/std per cell, stochastic mode)
+  __device__ __forceinline__ void finish(uint32_t elem_bytes = 4u) {
     mlo_x = lo_x + kMagicBits; mhi_x = hi_x + kMagicBits; mlo_y = lo_y + kMagicBits; mhi_y = hi_y + kMagicBits;
-    mwin_addr = win_addr - 4u * (static_cast<uint32_t>(kMagicBits) * static_cast<uint32_t>(pitch) +
-                                 static_cast<uint32_t>(kMagicBits));
+    mwin_addr = win_addr - elem_bytes * (static_cast<uint32_t>(kMagicBits) * static_cast<uint32_t>(pitch) +
+                                         static_cast<uint32_t>(kMagicBits));
   }
   __device__ __forceinline__ void pin_all() {
     pin(x_min); pin(y_min); pin(x_max); pin(y_max); pin(res); pin(inv_res); pin(dt);
@@ -108,6 +109,46 @@ __device__ __forceinline__ float lookup_tau(const StepConsts& c, float x, float 
     }
   }
   return __ldg(c.map + idx);
+}
+
+// Stochastic-slip mode (BASELINE config 4; observation-mode lookup, traversability_model.py:65-69 +
+// grid_map.py:169-178): the table holds (mean, std) of the cell's slip distribution interleaved, 8 bytes per cell.
+// Same cell index as lookup_tau; returns (mean, std).
+template <bool kPatch, bool kPow2, bool kMagic>
+__device__ __forceinline__ float2 lookup_slip(const StepConsts& c, float x, float y) {
+  int idx;
+  if (kMagic) {
+    float dx = __fsub_rn(x, c.x_min), dy = __fsub_rn(y, c.y_min);
+    float qx = kPow2 ? __fmul_rn(dx, c.inv_res) : __fdiv_rn(dx, c.res);
+    float qy = kPow2 ? __fmul_rn(dy, c.inv_res) : __fdiv_rn(dy, c.res);
+    int ix = min(max(__float_as_int(__fadd_rd(qx, kMagicFloat)), c.mlo_x), c.mhi_x);
+    int iy = min(max(__float_as_int(__fadd_rd(qy, kMagicFloat)), c.mlo_y), c.mhi_y);
+    if (kPatch) {
+      float2 t;
+      uint32_t a = c.mwin_addr + 8u * (static_cast<uint32_t>(iy) * static_cast<uint32_t>(c.pitch) + static_cast<uint32_t>(ix));
+      asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(t.x), "=f"(t.y) : "r"(a));
+      return t;
+    }
+    idx = (iy - kMagicBits) * c.pitch + (ix - kMagicBits);
+  } else {
+    int ix = min(max(cell_coord<kPow2>(x, c.x_min, c.res, c.inv_res), c.lo_x), c.hi_x);
+    int iy = min(max(cell_coord<kPow2>(y, c.y_min, c.res, c.inv_res), c.lo_y), c.hi_y);
+    idx = iy * c.pitch + ix;
+    if (kPatch) {
+      float2 t;
+      asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(t.x), "=f"(t.y) : "r"(c.win_addr + 8u * static_cast<uint32_t>(idx)));
+      return t;
+    }
+  }
+  return __ldg(reinterpret_cast<const float2*>(c.map) + idx);
+}
+
+// 1 - clamp(sample, 0, 1) with sample = xi * std + mean: Normal(mean, std).sample() is ATen's
+// normal_(0,1).mul_(std).add_(mean) (two roundings, no FMA); torch.clamp propagates NaN.
+__device__ __forceinline__ float slip_to_trav(float2 ms, float xi) {
+  float smp = __fadd_rn(__fmul_rn(xi, ms.y), ms.x);
+  float c = (smp != smp) ? smp : fminf(fmaxf(smp, 0.0f), 1.0f);
+  return __fsub_rn(1.0f, c);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -188,12 +229,16 @@ __device__ __forceinline__ void unicycle_step(const StepConsts& c, float tau, fl
 
 // Stage/terminal cost term (objectives.py:46-53): ||p - goal|| + 1e4 * [tau <= thr].  sqrt.approx has a
 // maximum relative error of 2^-23 (PTX ISA), far inside the cost tolerance, and no slow-path branch.
-__device__ __forceinline__ float goal_and_stuck_cost(const StepConsts& c, float px, float py, float tau) {
-  float dx = __fsub_rn(px, c.gx), dy = __fsub_rn(py, c.gy);
+__device__ __forceinline__ float goal_and_stuck_cost_at(const StepConsts& c, float gx, float gy, float px, float py,
+                                                        float tau) {
+  float dx = __fsub_rn(px, gx), dy = __fsub_rn(py, gy);
   float d2 = fmaf(dx, dx, dy * dy);
   float d;
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(d2));  // ftz: squared distances below 1e-38 m^2 read as 0
   return __fadd_rn(d, (tau <= c.thr) ? kStuckPenalty : 0.0f);
+}
+__device__ __forceinline__ float goal_and_stuck_cost(const StepConsts& c, float px, float py, float tau) {
+  return goal_and_stuck_cost_at(c, c.gx, c.gy, px, py, tau);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -236,6 +281,19 @@ __device__ __forceinline__ float4 noise_pair(uint32_t sample, uint32_t pair, uin
   const float2 a = box_muller(r.x, r.y);
   const float2 b = box_muller(r.z, r.w);
   return make_float4(sigma0 * a.x, sigma1 * a.y, sigma0 * b.x, sigma1 * b.y);
+}
+
+// Standard normals for the stochastic-slip lookups of one sample: stream `pair | 0x80000000` of the same
+// generator (the control noise uses pair < 2^31).  For step pair p: (transit 2p, stage 2p, transit 2p+1, stage 2p+1);
+// pair 0x7FFFFFFF: .x = terminal lookup.
+constexpr uint32_t kXiStream = 0x80000000u;
+constexpr uint32_t kXiTerminalPair = 0x7FFFFFFFu;
+constexpr uint32_t kOptimalSample = 0xFFFFFFFFu;  // "sample" id of the batch-1 optimal rollout's lookups
+__device__ __forceinline__ float4 xi_quad(uint32_t sample, uint32_t pair, uint32_t iter_lo, uint32_t iter_hi, uint2 key) {
+  const uint4 r = philox4x32_10(make_uint4(sample, pair | kXiStream, iter_lo, iter_hi), key);
+  const float2 a = box_muller(r.x, r.y);
+  const float2 b = box_muller(r.z, r.w);
+  return make_float4(a.x, a.y, b.x, b.y);
 }
 
 }  // namespace bnv

@@ -40,6 +40,20 @@ class _DevView:
         self._owner = owner  # keep the handle alive while the view exists
 
 
+def _slip_distribution(grid_map, key: str = "predictions"):
+    """(mean, std) tensors of ``GridMap.distributions[key]`` (grid_map.py:24-33): what the observation-mode lookup
+    samples from (traversability_model.py:65-69)."""
+    try:
+        dist = grid_map.distributions[key]
+        mean, std = dist.mean, dist.stddev
+    except (AttributeError, KeyError, TypeError) as exc:
+        raise TypeError(f"grid map has no Normal distribution under distributions['{key}']") from exc
+    g = int(grid_map.grid_size)
+    if tuple(mean.shape) != (g, g) or tuple(std.shape) != (g, g):
+        raise ValueError("slip distribution mean/stddev must be [grid_size, grid_size]")
+    return mean, std
+
+
 def _introspect_problem(dynamics, objectives):
     """Pull what ``forward`` reads through ``dynamics``/``objectives`` out of the objects."""
     try:
@@ -74,7 +88,7 @@ class MPPI(nn.Module):
     def __init__(self, horizon: int, num_samples: int, dim_state: int, dim_control: int, dynamics, objectives,
                  sigmas: torch.Tensor, lambda_: float, device=torch.device("cuda"), dtype=torch.float32,
                  seed: int = 42, *, noise_source: str = "philox", record_states: bool = True,
-                 process_group=None, exchange: str = "p2p") -> None:
+                 process_group=None, exchange: str = "p2p", stochastic_slip: bool = False) -> None:
         super().__init__()
         torch.manual_seed(seed)  # mppi.py:55
         # same shape checks (and exception type) as mppi.py:58-66
@@ -105,18 +119,26 @@ class MPPI(nn.Module):
         self._sigmas = sigmas.clone().detach().to(dev, dtype)
         self._shard = ShardInfo.from_group(process_group)
         self._lib = _cabi.load()
+        # BASELINE config 4: every lookup of the rollouts samples the slip prediction of the cell
+        self._stochastic = bool(stochastic_slip)
+        if self._stochastic and self._shard.world_size != 1:
+            raise ValueError("stochastic_slip needs a single-GPU solver")
+        if self._stochastic and noise_source != "philox":
+            raise ValueError("stochastic_slip draws its noise in the engine (noise_source='philox')")
 
         risks, g, res, x_lim, y_lim, goal, thr, dt = _introspect_problem(dynamics, objectives)
         cfg = _cabi.MppiCfg(num_samples=self._num_samples, horizon=self._horizon, lambda_=self._lambda, dt=dt,
                             seed=int(seed) & 0xFFFFFFFFFFFFFFFF, rank=self._shard.rank,
                             world_size=self._shard.world_size, device=dev.index,
-                            flags=_cabi.BNV_FLAG_RECORD_STATES if record_states else 0)
+                            flags=(_cabi.BNV_FLAG_RECORD_STATES if record_states else 0)
+                            | (_cabi.BNV_FLAG_STOCHASTIC_SLIP if self._stochastic else 0))
         sig, lo, hi = (t.detach().cpu().to(torch.float32).tolist() for t in (sigmas, dynamics.min_action, dynamics.max_action))
         for i in range(2):
             cfg.sigma[i], cfg.u_min[i], cfg.u_max[i] = sig[i], lo[i], hi[i]
         self._handle = C.c_void_p()
         _cabi.check(self._lib.bnv_mppi_create(C.byref(self._handle), C.byref(cfg)))
-        self._record_states = bool(record_states)
+        record_states = bool(record_states) or self._stochastic
+        self._record_states = record_states
         self._local_samples = int(self._lib.bnv_mppi_local_samples(self._handle))
         self._sample_offset = int(self._lib.bnv_mppi_sample_offset(self._handle))
         self._sample_shape = torch.Size([self._local_samples, self._horizon])
@@ -161,18 +183,28 @@ class MPPI(nn.Module):
         """(Re)upload the risk map / goal / threshold when the reference objects changed (cheap identity check)."""
         dyn, obj = self._dynamics, self._objectives
         risks, goal = dyn._traversability_model._risks, obj._goal_pos
+        if self._stochastic:
+            risks = _slip_distribution(dyn._grid_map)[0]
         quick = (id(risks), risks._version if torch.is_tensor(risks) else None, id(goal),
                  goal._version if torch.is_tensor(goal) else None, obj._stuck_threshold, id(dyn._grid_map))
         if not force and quick == self._risk_key:
             return
         risks, g, res, x_lim, y_lim, goal, thr, _ = _introspect_problem(dyn, obj)
         goal_xy = torch.as_tensor(goal).detach().to("cpu", torch.float32).reshape(-1)[:2].tolist()
-        self._risk_dev = risks.detach().to(self._device, torch.float32).contiguous()
         self._goal_host[0], self._goal_host[1] = goal_xy
         with torch.cuda.device(self._device):
-            _cabi.check(self._lib.bnv_mppi_set_problem(
-                self._handle, self._risk_dev.data_ptr(), g, self._risk_dev.stride(0), res, x_lim[0], x_lim[1],
-                y_lim[0], y_lim[1], self._goal_host, thr, self._stream()))
+            if self._stochastic:
+                mean, std = _slip_distribution(dyn._grid_map)
+                self._risk_dev = mean.detach().to(self._device, torch.float32).contiguous()
+                self._std_dev = std.detach().to(self._device, torch.float32).contiguous()
+                _cabi.check(self._lib.bnv_mppi_set_problem_ex(
+                    self._handle, self._risk_dev.data_ptr(), self._std_dev.data_ptr(), g, self._risk_dev.stride(0), 0,
+                    res, x_lim[0], x_lim[1], y_lim[0], y_lim[1], self._goal_host, thr, self._stream()))
+            else:
+                self._risk_dev = risks.detach().to(self._device, torch.float32).contiguous()
+                _cabi.check(self._lib.bnv_mppi_set_problem(
+                    self._handle, self._risk_dev.data_ptr(), g, self._risk_dev.stride(0), res, x_lim[0], x_lim[1],
+                    y_lim[0], y_lim[1], self._goal_host, thr, self._stream()))
         self._risk_key = quick
 
     def __del__(self):
@@ -184,12 +216,14 @@ class MPPI(nn.Module):
             pass
 
     # ------------------------------------------------------------------ reference API
-    def forward(self, state: torch.Tensor, noise: Optional[torch.Tensor] = None
-                ) -> Tuple[torch.Tensor, torch.Tensor]:
+    def forward(self, state: torch.Tensor, noise: Optional[torch.Tensor] = None, xi: Optional[torch.Tensor] = None,
+                xi_opt: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
         """One control iteration (mppi.py:130-219).
 
         Returns ``(optimal_action_seq [T,2], optimal_state_seq [1,T+1,3])`` on the solver's device.
         ``noise`` (optional, [K_local,T,2]) injects the sigma-scaled control noise of this shard.
+        ``xi`` [K,2T+1] / ``xi_opt`` [T] (stochastic_slip only, together with ``noise``) inject the standard normals
+        behind the lookups' ``Normal.sample()`` calls (layout: include/bnv_mppi.h, bnv_mppi_forward_ex).
         """
         if not torch.is_tensor(state):
             state = torch.tensor(state, dtype=self._dtype)
@@ -218,7 +252,23 @@ class MPPI(nn.Module):
             opt_states = torch.empty(1, self._horizon + 1, 3, device=self._device, dtype=torch.float32)
             stream = self._stream()
             noise_ptr = noise.data_ptr() if noise is not None else None
-            if state_host is None:
+            if self._stochastic:
+                if (noise is None) != (xi is None) or (noise is None) != (xi_opt is None):
+                    raise ValueError("stochastic_slip: give noise, xi and xi_opt together or none of them")
+                if state_ptr is None:
+                    self._state_dev.copy_(state.detach().to(torch.float32), non_blocking=True)
+                    state_ptr = self._state_dev.data_ptr()
+                xi_ptr = xo_ptr = None
+                if xi is not None:
+                    if tuple(xi.shape) != (self._local_samples, 2 * self._horizon + 1) or tuple(xi_opt.shape) != (self._horizon,):
+                        raise ValueError("xi must be [K, 2T+1] and xi_opt [T]")
+                    xi = xi.detach().to(self._device, torch.float32).contiguous()
+                    xi_opt = xi_opt.detach().to(self._device, torch.float32).contiguous()
+                    self._xi_keepalive = (xi, xi_opt)
+                    xi_ptr, xo_ptr = xi.data_ptr(), xi_opt.data_ptr()
+                _cabi.check(self._lib.bnv_mppi_forward_ex(self._handle, state_ptr, noise_ptr, xi_ptr, xo_ptr,
+                                                          u_opt.data_ptr(), opt_states.data_ptr(), stream))
+            elif state_host is None:
                 _cabi.check(self._lib.bnv_mppi_forward(self._handle, state_ptr, noise_ptr, u_opt.data_ptr(),
                                                        opt_states.data_ptr(), stream))
             else:
@@ -264,6 +314,16 @@ class MPPI(nn.Module):
         return states, weights
 
     # ------------------------------------------------------------------ extras
+    def draw_lookup_normals(self, iteration: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(xi [K,2T+1], xi_opt [T]) the engine draws for its stochastic lookups in the given iteration (0-based since
+        construction / reset): lets a test replay an in-engine-noise iteration through the oracle."""
+        xi = torch.empty(self._local_samples, 2 * self._horizon + 1, device=self._device, dtype=torch.float32)
+        xi_opt = torch.empty(self._horizon, device=self._device, dtype=torch.float32)
+        with torch.cuda.device(self._device):
+            _cabi.check(self._lib.bnv_mppi_draw_xi(self._handle, int(iteration), xi.data_ptr(), xi_opt.data_ptr(),
+                                                   self._stream()))
+        return xi, xi_opt
+
     def reset(self) -> None:
         """Zero the mean sequence and restart the engine's noise stream (a freshly built solver)."""
         _cabi.check(self._lib.bnv_mppi_reset(self._handle, self._stream()))

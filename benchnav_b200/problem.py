@@ -25,13 +25,23 @@ class ModelConfig:
 class GridSpec:
     """Geometry of a square 2.5D grid map; limits follow grid_map.py:42-50."""
 
-    def __init__(self, grid_size: int, resolution: float, device: str = "cpu") -> None:
+    def __init__(self, grid_size: int, resolution: float, device: str = "cpu", distributions=None) -> None:
+        # distributions: {"predictions": d, "latent_models": d} with d.mean / d.stddev [G,G] (grid_map.py:24-33)
+        self.distributions = distributions if distributions is not None else {}
         self.grid_size = int(grid_size)
         self.resolution = resolution
         self.center_x = self.center_y = grid_size * resolution / 2
         self.x_limits = (self.center_x - grid_size / 2 * resolution, self.center_x + grid_size / 2 * resolution)
         self.y_limits = (self.center_y - grid_size / 2 * resolution, self.center_y + grid_size / 2 * resolution)
         self.device = device
+
+
+@dataclass
+class SlipDistribution:
+    """Per-cell Normal slip model: the two tensors a ``torch.distributions.Normal`` exposes as mean / stddev."""
+
+    mean: torch.Tensor
+    stddev: torch.Tensor
 
 
 class _RiskHolder:

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define BNV_ABI_VERSION 1
+#define BNV_ABI_VERSION 2
 
 typedef enum bnv_status {
   BNV_OK = 0,
@@ -40,6 +40,12 @@ typedef enum bnv_status {
 /* bnv_mppi_cfg.flags */
 #define BNV_FLAG_RECORD_STATES 0x1u /* keep every sample's recorded state sequence (reference `_state_seq_batch`,
                                        mppi.py:119-125); required by bnv_mppi_top_samples */
+#define BNV_FLAG_STOCHASTIC_SLIP 0x2u /* BASELINE config 4: every traversability lookup of the rollouts draws
+                                         1 - clamp(Normal(mean, std).sample(), 0, 1) from the cell's slip distribution
+                                         (the observation-mode lookup, traversability_model.py:65-69, applied to
+                                         GridMap.distributions["predictions"]) instead of reading the risk map;
+                                         needs bnv_mppi_set_problem_ex with a std map; implies RECORD_STATES;
+                                         world_size must be 1 */
 
 /* Constructor arguments of the reference `MPPI.__init__` (src/planners/local_planners/mppi.py:23-36) plus
  * the action bounds it copies from `dynamics.min_action/max_action` (mppi.py:83-88, robot_model.py:54-57),
@@ -57,6 +63,11 @@ typedef struct bnv_mppi_cfg {
   int32_t world_size;     /* number of sample shards (GPUs); 1 = single GPU */
   int32_t device;         /* CUDA device ordinal */
   uint32_t flags;         /* BNV_FLAG_* */
+  int32_t num_envs;       /* E: independent environments solved per forward call (BASELINE config 3: one planner per
+                             planetary_env instance, all in one launch); 0 or 1 = a single solver.  With E > 1 every
+                             per-solver buffer below gains a leading dimension E, num_samples is per environment,
+                             world_size must be 1 (environments, not samples, are what shards across GPUs) and
+                             RECORD_STATES is implied. */
 } bnv_mppi_cfg;
 
 typedef struct bnv_mppi bnv_mppi; /* opaque solver handle */
@@ -80,6 +91,15 @@ int bnv_mppi_set_problem(bnv_mppi* h, const float* risk_dev, int32_t grid_size, 
                          float x_min, float x_max, float y_min, float y_max, const float goal_xy[2],
                          float stuck_threshold, void* stream);
 
+/* General form of bnv_mppi_set_problem.
+ *   mean_dev   [E][G][pitch] risk maps (deterministic mode) or slip means (BNV_FLAG_STOCHASTIC_SLIP);
+ *              `env_stride` elements between consecutive environments' maps (0 = all environments share one map)
+ *   std_dev    slip standard deviations, same layout (stochastic mode only; NULL otherwise)
+ *   goals_xy   HOST array [E][2], one goal per environment (objectives.py:25) */
+int bnv_mppi_set_problem_ex(bnv_mppi* h, const float* mean_dev, const float* std_dev, int32_t grid_size, int32_t pitch,
+                            int64_t env_stride, float resolution, float x_min, float x_max, float y_min, float y_max,
+                            const float* goals_xy, float stuck_threshold, void* stream);
+
 /* MPPI.forward (mppi.py:130-219), device buffers.
  *   state_dev      [3]        current state (x, y, theta)
  *   noise_dev      [Kl,T,2]   sigma-scaled control noise exactly as `_action_noises` (mppi.py:149-151) for
@@ -91,6 +111,17 @@ int bnv_mppi_set_problem(bnv_mppi* h, const float* risk_dev, int32_t grid_size, 
  * u_out/opt_states untouched; exchange bnv_mppi_partial() across ranks and call bnv_mppi_finalize(). */
 int bnv_mppi_forward(bnv_mppi* h, const float* state_dev, const float* noise_dev, float* u_out_dev,
                      float* opt_states_dev, void* stream);
+
+/* forward with injected lookup normals (BNV_FLAG_STOCHASTIC_SLIP; parity tests):
+ *   xi_dev      [E][Kl][2T+1]  per sample: (transit lookup of step 0, stage-cost lookup of recorded state 0, transit 1,
+ *                              stage 1, ..., terminal-cost lookup) -- the standard normals behind each
+ *                              Normal(mean, std).sample() of robot_model.py:76 / objectives.py:50
+ *   xi_opt_dev  [E][T]         transit lookups of the batch-1 optimal rollout (mppi.py:209-214)
+ * noise_dev, xi_dev and xi_opt_dev must be all given or all NULL (NULL: drawn in-kernel from the Philox stream).
+ * In batch mode (num_envs = E > 1) state_dev is [E][3], noise_dev [E][K][T][2], u_out_dev [E][T][2] and
+ * opt_states_dev [E][T+1][3] -- for bnv_mppi_forward as well. */
+int bnv_mppi_forward_ex(bnv_mppi* h, const float* state_dev, const float* noise_dev, const float* xi_dev,
+                        const float* xi_opt_dev, float* u_out_dev, float* opt_states_dev, void* stream);
 
 /* forward with the state given as three HOST floats (passed by value in the launch packet: no device copy of
  * the state is needed) and DEVICE outputs; asynchronous like bnv_mppi_forward. */
@@ -125,6 +156,7 @@ int bnv_mppi_attach_peers(bnv_mppi* h, const unsigned char* handles /* [world_si
 /* MPPI.get_top_samples (mppi.py:221-240): the n highest-weight samples of this shard in descending
  * weight order.  states_out_dev [n,T+1,3], weights_out_dev [n]. Needs BNV_FLAG_RECORD_STATES. */
 int bnv_mppi_top_samples(bnv_mppi* h, int32_t n, float* states_out_dev, float* weights_out_dev, void* stream);
+/* (batch mode: the n best samples of every environment, states_out_dev [E,n,T+1,3], weights_out_dev [E,n]) */
 
 /* Module state the reference exposes as attributes (device pointers owned by the handle, shard-local):
  *   weights  [Kl]        `_weights`            (mppi.py:193)
@@ -149,6 +181,28 @@ int bnv_mppi_reset(bnv_mppi* h, void* stream);
  * stream can be inspected or pre-drawn. */
 int bnv_mppi_draw_noise(bnv_mppi* h, uint64_t iteration, void* stream);
 
+/* The stochastic mode's lookup normals for the given iteration index, by the stand-alone kernel (the same Philox
+ * calls the rollout kernel makes): xi_out_dev [E][Kl][2T+1], xi_opt_out_dev [E][T] (layouts of bnv_mppi_forward_ex),
+ * caller-owned.  Lets a test replay an in-engine-noise iteration through the oracle. */
+int bnv_mppi_draw_xi(bnv_mppi* h, uint64_t iteration, float* xi_out_dev, float* xi_opt_out_dev, void* stream);
+
+/* ---- hooks used by the DWA planner built on the same rollout kernel (src/planners/local_planners/dwa.py) ----
+ * DWA.forward (dwa.py:116-149) = the MPPI rollout/cost machinery with K = num_lin_vel * num_ang_vel constant
+ * action sequences injected as "noise" around a zero mean (bnv_mppi_forward with noise_dev = the held actions),
+ * lambda_ = 1 (weights = softmax(-cost), dwa.py:147), argmin instead of the weighted mean.
+ *   bnv_mppi_set_keep_mean(h, 0)      u* is not written back as the next mean sequence (the mean stays zero)
+ *   bnv_mppi_set_terminal_goal        goal of the terminal cost (always the final goal, dwa.py:233) when the stage
+ *                                     cost follows a sub-goal (dwa.py:225-231); reset by bnv_mppi_set_problem*
+ *   bnv_mppi_set_goal_dev             device-resident [2] override of the stage-cost goal (the sub-goal selected by
+ *                                     bnv_dwa_subgoal), NULL = back to the goal of bnv_mppi_set_problem
+ *   bnv_mppi_argmin                   first index of the minimum cost of the last forward, that sample's action
+ *                                     (from actions_dev [K,2]) and recorded states [T+1,3] (dwa.py:141-144) */
+int bnv_mppi_set_keep_mean(bnv_mppi* h, int32_t keep);
+int bnv_mppi_set_terminal_goal(bnv_mppi* h, const float goal_xy[2]);
+int bnv_mppi_set_goal_dev(bnv_mppi* h, const float* goal_dev);
+int bnv_mppi_argmin(bnv_mppi* h, const float* actions_dev, float* action_out_dev, float* states_out_dev,
+                    int32_t* index_out_dev, void* stream);
+
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 uint64_t bnv_mppi_launch_count(const bnv_mppi* h);
 
@@ -165,6 +219,66 @@ int bnv_debug_timestamps(bnv_mppi* h, long long out[16]);
 /* Test hook: evaluates the engine's in-range sin/cos (used by the state update in place of
  * torch.cos/torch.sin, robot_model.py:86-87) on n device floats. */
 int bnv_debug_sincos(const float* theta_dev, float* sin_dev, float* cos_dev, int32_t n, void* stream);
+
+/* ================================================================================================
+ * Rows either side of the MPPI iteration: stateless entry points, device pointers on
+ * the CURRENT CUDA device, asynchronous on `stream`.
+ * ================================================================================================ */
+
+/* GridMap geometry (grid_map.py:40-50) of a [grid_size, grid_size] map stored with `pitch` elements per row. */
+typedef struct bnv_grid {
+  int32_t grid_size;
+  int32_t pitch;
+  float resolution;
+  float x_min, x_max, y_min, y_max;
+} bnv_grid;
+
+/* TraversabilityModel.get_traversability (traversability_model.py:53-72) at n positions (rows of `pos_stride`
+ * floats starting with x, y -- e.g. states [B,P,3] flattened, pos_stride 3) and PlanetaryEnv.collision_check
+ * (planetary_env.py:221-232).
+ *   std_dev == NULL  inference mode: trav = 1 - clamp(mean[cell], 0, 1) with mean = the risk map
+ *   std_dev != NULL  observation mode: trav = 1 - clamp(mean[cell] + std[cell] * xi, 0, 1); xi_dev [n] standard
+ *                    normals, or NULL to draw them from Philox(seed, counter)
+ *   rows_per_env > 0 positions are [E][rows_per_env] and environment e reads the map at mean_dev + e * env_stride
+ *   trav_out_dev [n] and/or stuck_out_dev [n] (uint8, trav <= stuck_threshold); either may be NULL. */
+int bnv_trav_lookup(const bnv_grid* grid, const float* mean_dev, const float* std_dev, int64_t env_stride,
+                    int64_t rows_per_env, const float* pos_dev, int64_t n, int32_t pos_stride, const float* xi_dev,
+                    uint64_t seed, uint64_t counter, float stuck_threshold, float* trav_out_dev,
+                    uint8_t* stuck_out_dev, void* stream);
+
+/* PlanetaryEnv.step (planetary_env.py:189-219) for E independent environments in one launch:
+ * observation-mode transit of states_dev [E,3] (updated in place) under actions_dev [E,2], reward_out_dev [E] = the
+ * traversability drawn for the step, terminated_out_dev [E] (uint8) = ||p - goal|| < goal_threshold.  Maps as in
+ * bnv_trav_lookup (env_stride 0 = shared).  xi_dev [E] or NULL (Philox(seed, counter)).  The elapsed-time /
+ * truncation bookkeeping (two scalars) stays with the caller. */
+int bnv_env_step(const bnv_grid* grid, const float* mean_dev, const float* std_dev, int64_t env_stride,
+                 int32_t num_envs, float* states_dev, const float* actions_dev, const float* goals_dev,
+                 const float* xi_dev, uint64_t seed, uint64_t counter, const float u_min[2], const float u_max[2],
+                 float delta_t, float goal_threshold, float* reward_out_dev, uint8_t* terminated_out_dev, void* stream);
+
+/* TraversabilityModel._infer_risk_map (traversability_model.py:28-51) over n_cells cells.
+ *   metric      0 expected value, 1 VaR, 2 CVaR (utils.py:18); confidence = ModelConfig.confidence_value
+ *   method      BNV_RISK_CLOSED_FORM: mean + coef * std (exact for the Normal slip model);
+ *               BNV_RISK_MONTE_CARLO: the reference's estimator -- num_samples draws per cell, torch.quantile
+ *               (linear) and the mean of the tail above it -- on injected samples_dev [num_samples, n_cells]
+ *               (exactly `distributions.sample((num_samples,))`) or, with samples_dev NULL, on Philox(seed) draws;
+ *               samples_out_dev (optional, same shape) receives those draws. */
+#define BNV_RISK_CLOSED_FORM 0
+#define BNV_RISK_MONTE_CARLO 1
+int bnv_risk_map(int32_t metric, float confidence, int32_t method, const float* mean_dev, const float* std_dev,
+                 int64_t n_cells, const float* samples_dev, int32_t num_samples, uint64_t seed, float* risk_out_dev,
+                 float* samples_out_dev, void* stream);
+
+/* DWA._generate_actions (dwa.py:151-184): actions_out_dev [nv*nw, 2] = cartesian product of the linspaces over the
+ * dynamic window around prev_action_dev [2]; controls_out_dev [nv*nw, T, 2] = each action held over the horizon
+ * (the form bnv_mppi_forward takes as injected noise). */
+int bnv_dwa_actions(const float* prev_action_dev, const float u_min[2], const float u_max[2], const float a_lim[2],
+                    float delta_t, int32_t num_lin_vel, int32_t num_ang_vel, int32_t horizon, float* actions_out_dev,
+                    float* controls_out_dev, void* stream);
+
+/* DWA._select_sub_goal (dwa.py:260-285): path_dev [n,2], state_dev [3] -> goal_out_dev [2]. */
+int bnv_dwa_subgoal(const float* path_dev, int32_t n, const float* state_dev, float lookahead_distance,
+                    float* goal_out_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -50,7 +50,7 @@ Vocabulary (matches DESIGN.md)
 from __future__ import annotations
 
 import math
-from dataclasses import dataclass
+from dataclasses import dataclass, replace
 from typing import Dict, Optional, Sequence, Tuple
 
 import torch
@@ -73,6 +73,9 @@ class Problem:
     u_min: Tuple[float, float] = (0.0, -1.0)  # robot_model.py:54-57
     u_max: Tuple[float, float] = (1.0, 1.0)
     dt: float = 0.1  # robot_model.py:60 (MPPI never overrides it)
+    # stochastic-slip mode (BASELINE config 4): `risk` holds the slip MEAN and `slip_std` its standard deviation;
+    # lookups then sample the cell's Normal (observation-mode lookup, traversability_model.py:65-69)
+    slip_std: Optional[torch.Tensor] = None
 
     @property
     def grid_size(self) -> int:
@@ -103,21 +106,33 @@ def cell_indices(p: Problem, xy: torch.Tensor) -> Tuple[torch.Tensor, torch.Tens
     return idx[..., 0].long(), idx[..., 1].long()
 
 
-def traversability(p: Problem, xy: torch.Tensor) -> torch.Tensor:
-    """traversability_model.py:70-72 + grid_map.py:167: 1 - clamp(risk[iy, ix], 0, 1)."""
+def traversability(p: Problem, xy: torch.Tensor, xi: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """traversability_model.py:70-72 + grid_map.py:167: 1 - clamp(risk[iy, ix], 0, 1).
+
+    With ``xi`` (standard normals, one per position) the observation-mode lookup instead
+    (traversability_model.py:65-69, grid_map.py:169-178): ``Normal(mean[cell], std[cell]).sample()`` is ATen's
+    ``normal_(0, 1).mul_(std).add_(mean)``, i.e. ``xi * std + mean`` with two roundings.
+    """
     ix, iy = cell_indices(p, xy)
-    return 1 - torch.clamp(p.risk.to(xy.dtype)[iy, ix], 0, 1)
+    if xi is None:
+        return 1 - torch.clamp(p.risk.to(xy.dtype)[iy, ix], 0, 1)
+    assert p.slip_std is not None, "stochastic lookup needs Problem.slip_std"
+    sample = xi.to(xy.dtype).mul(p.slip_std.to(xy.dtype)[iy, ix]).add(p.risk.to(xy.dtype)[iy, ix])
+    return 1 - torch.clamp(sample, 0, 1)
 
 
 # --------------------------------------------------------------------------- dynamics
-def unicycle_step(p: Problem, s: torch.Tensor, u: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+def unicycle_step(p: Problem, s: torch.Tensor, u: torch.Tensor, xi: Optional[torch.Tensor] = None,
+                  dt: Optional[float] = None, return_trav: bool = False):
     """One ``transit`` (robot_model.py:75-95) written without aliasing.
 
     Returns ``(raw, nxt)``: ``raw`` is the un-clamped / un-wrapped successor (what
     the reference's in-place ``+=`` leaves in the *input* slot) and ``nxt`` the
-    clamped/wrapped state it returns.
+    clamped/wrapped state it returns.  ``xi``: lookup normals (stochastic / observation mode).
     """
-    tau = traversability(p, s[:, :2])
+    tau = traversability(p, s[:, :2], xi)
+    if dt is not None:
+        p = replace(p, dt=dt)
     v = torch.clamp(u[:, 0], p.u_min[0], p.u_max[0])
     w = torch.clamp(u[:, 1], p.u_min[1], p.u_max[1])
     th = s[:, 2]
@@ -127,66 +142,84 @@ def unicycle_step(p: Problem, s: torch.Tensor, u: torch.Tensor) -> Tuple[torch.T
     th_wrapped = (th_raw + torch.pi) % (2 * torch.pi) - torch.pi
     raw = torch.stack([x, y, th_raw], dim=1)
     nxt = torch.stack([torch.clamp(x, p.x_min, p.x_max), torch.clamp(y, p.y_min, p.y_max), th_wrapped], dim=1)
+    if return_trav:
+        return raw, nxt, tau
     return raw, nxt
 
 
-def rollout(p: Problem, state: torch.Tensor, controls: torch.Tensor) -> torch.Tensor:
+def rollout(p: Problem, state: torch.Tensor, controls: torch.Tensor, xi: Optional[torch.Tensor] = None
+            ) -> torch.Tensor:
     """mppi.py:160-165 (and :209-214 for the batch-1 optimal rollout).
 
     ``controls`` [B,T,2] -> ``rec`` [B,T+1,3] with the aliasing quirk reproduced.
+    ``xi`` [B,T]: lookup normals of the T transits (stochastic mode).
     """
     b, t_h = controls.shape[0], controls.shape[1]
     rec = torch.zeros(b, t_h + 1, 3, dtype=controls.dtype)
     cur = state.to(controls.dtype).repeat(b, 1)
     for t in range(t_h):
-        raw, cur = unicycle_step(p, cur, controls[:, t, :])
+        raw, cur = unicycle_step(p, cur, controls[:, t, :], None if xi is None else xi[:, t])
         rec[:, t, :] = raw
     rec[:, t_h, :] = cur
     return rec
 
 
 # --------------------------------------------------------------------------- costs
-def stage_cost(p: Problem, s: torch.Tensor) -> torch.Tensor:
-    """objectives.py:46-53 on one [B,3] slice of ``rec``."""
-    goal = torch.tensor(p.goal, dtype=torch.float32).to(s.dtype)
+def stage_cost(p: Problem, s: torch.Tensor, xi: Optional[torch.Tensor] = None,
+               goal: Optional[Sequence[float]] = None) -> torch.Tensor:
+    """objectives.py:46-53 on one [B,3] slice of ``rec`` (``goal`` overrides the problem's: DWA's sub-goal)."""
+    goal = torch.tensor(p.goal if goal is None else goal, dtype=torch.float32).to(s.dtype)
     dist = torch.norm(s[:, :2] - goal, dim=1)
-    stuck = traversability(p, s[:, :2]) <= p.stuck_threshold
+    stuck = traversability(p, s[:, :2], xi) <= p.stuck_threshold
     return dist + STUCK_PENALTY * stuck
 
 
 def sample_costs(p: Problem, rec: torch.Tensor, controls: torch.Tensor, u_prev: torch.Tensor,
-                 sigmas: torch.Tensor, lam: float) -> torch.Tensor:
-    """mppi.py:168-190: sum_t stage + terminal + sum_t lambda * u_prev[t]^T Sigma^-1 v[k,t]."""
+                 sigmas: torch.Tensor, lam: float, xi_stage: Optional[torch.Tensor] = None,
+                 xi_term: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """mppi.py:168-190: sum_t stage + terminal + sum_t lambda * u_prev[t]^T Sigma^-1 v[k,t].
+    ``xi_stage`` [K,T] / ``xi_term`` [K]: lookup normals of the cost evaluations (stochastic mode)."""
     k, t_h = controls.shape[0], controls.shape[1]
     dt = controls.dtype
     inv_cov = torch.inverse(torch.diag(sigmas.to(torch.float32) ** 2)).to(dt)  # mppi.py:94-97
     stage = torch.zeros(k, t_h, dtype=dt)
     act = torch.zeros(k, t_h, dtype=dt)
     for t in range(t_h):
-        stage[:, t] = stage_cost(p, rec[:, t, :])
+        stage[:, t] = stage_cost(p, rec[:, t, :], None if xi_stage is None else xi_stage[:, t])
         act[:, t] = u_prev[t] @ inv_cov @ controls[:, t].T
-    terminal = stage_cost(p, rec[:, -1, :])
+    terminal = stage_cost(p, rec[:, -1, :], xi_term)
     return torch.sum(stage, dim=1) + terminal + torch.sum(lam * act, dim=1)
 
 
 # --------------------------------------------------------------------------- one iteration
 def mppi_iteration(p: Problem, state: torch.Tensor, u_prev: torch.Tensor, noise: torch.Tensor,
-                   sigmas: torch.Tensor, lam: float, dtype: torch.dtype = torch.float32) -> Dict[str, torch.Tensor]:
+                   sigmas: torch.Tensor, lam: float, dtype: torch.dtype = torch.float32,
+                   xi: Optional[torch.Tensor] = None, xi_opt: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
     """One ``MPPI.forward`` (mppi.py:146-217) with the noise injected.
 
     Returns u_opt [T,2], opt_rec [1,T+1,3], rec [K,T+1,3], weights [K], costs [K], controls [K,T,2].
+
+    Stochastic-slip mode (BASELINE config 4; no native reference -- SURVEY 8c): the same function with every
+    ``get_traversability`` call sampling the cell's slip prediction.  ``xi`` [K,2T+1] holds, per sample, the normals of
+    (transit 0, stage 0, transit 1, stage 1, ..., terminal), ``xi_opt`` [T] those of the optimal rollout's transits.
     """
+    xi_tr = xi_st = xi_term = None
+    if xi is not None:
+        t_h = noise.shape[1]
+        xi = xi.to(dtype)
+        xi_tr, xi_st, xi_term = xi[:, 0:2 * t_h:2], xi[:, 1:2 * t_h:2], xi[:, 2 * t_h]
     state = state.to(dtype)
     u_prev = u_prev.to(dtype)
     noise = noise.to(dtype)
     lo = torch.tensor(p.u_min, dtype=torch.float32).to(dtype)
     hi = torch.tensor(p.u_max, dtype=torch.float32).to(dtype)
     controls = torch.clamp(u_prev + noise, lo, hi)  # mppi.py:152-157
-    rec = rollout(p, state, controls)
-    costs = sample_costs(p, rec, controls, u_prev, sigmas, lam)
+    rec = rollout(p, state, controls, xi_tr)
+    costs = sample_costs(p, rec, controls, u_prev, sigmas, lam, xi_st, xi_term)
     weights = torch.softmax(-costs / lam, dim=0)  # mppi.py:193
     u_opt = torch.sum(weights.view(-1, 1, 1) * controls, dim=0)  # mppi.py:196-199
-    opt_rec = rollout(p, state, u_opt.repeat(1, 1, 1))  # mppi.py:202-214
+    opt_rec = rollout(p, state, u_opt.repeat(1, 1, 1),
+                      None if xi_opt is None else xi_opt.to(dtype).view(1, -1))  # mppi.py:202-214
     return {"u_opt": u_opt, "opt_rec": opt_rec, "rec": rec, "weights": weights, "costs": costs,
             "controls": controls}
 

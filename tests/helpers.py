@@ -26,3 +26,15 @@ def oracle_call(case: dict, i: int, dtype=torch.float32, u_prev=None):
 
 def t2n(x: torch.Tensor) -> np.ndarray:
     return x.detach().cpu().numpy()
+
+
+def ext_problem(case: dict, stochastic: bool) -> orc.Problem:
+    """Problem of an extended golden case (env / dwa / stoch): `mean`+`std` maps, or a `risk` map."""
+    grid = torch.from_numpy(case["mean"] if "mean" in case else case["risk"])
+    goal = case["goal"].tolist() if "goal" in case else [0.0, 0.0]
+    thr = float(case["thr"]) if "thr" in case else 0.0
+    p = orc.make_problem(grid, float(case["resolution"]), goal, thr)
+    assert (p.x_min, p.x_max, p.y_min, p.y_max) == tuple(case["limits"].tolist())
+    if stochastic:
+        p.slip_std = torch.from_numpy(case["std"])
+    return p

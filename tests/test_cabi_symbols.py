@@ -31,9 +31,10 @@ def test_every_declared_symbol_is_exported_and_bound():
 
 
 def test_cfg_struct_layout_matches_header():
-    # int32 K, int32 T, float[2], float, float[2], float[2], float, (pad) uint64, int32 x3, uint32
-    assert C.sizeof(_cabi.MppiCfg) == 64
-    assert _cabi.MppiCfg.seed.offset == 40 and _cabi.MppiCfg.flags.offset == 60
+    # int32 K, int32 T, float[2], float, float[2], float[2], float, (pad) uint64, int32 x3, uint32, int32, (pad)
+    assert C.sizeof(_cabi.MppiCfg) == 72
+    assert _cabi.MppiCfg.seed.offset == 40 and _cabi.MppiCfg.flags.offset == 60 and _cabi.MppiCfg.num_envs.offset == 64
+    assert C.sizeof(_cabi.Grid) == 28
 
 
 def test_sm100a_only_sass_with_tma_and_bulk_copies():
@@ -42,7 +43,9 @@ def test_sm100a_only_sass_with_tma_and_bulk_copies():
     assert "sm_100a" in sass
     funcs = sass.split("Function : ")[1:]
     rollouts = [f for f in funcs if "rollout_kernel" in f.splitlines()[0]]
-    assert len(rollouts) == 32  # kPatch x kPow2 x kRecord x kFastAngles x kPhilox
+    # single solver: kPatch x kPow2 x kRecord x kFastAngles x kPhilox = 32; stochastic and/or batched modes
+    # (record + fast angles only): 3 x kPatch x kPow2 x kPhilox = 24
+    assert len(rollouts) == 56
     for f in rollouts:
         name = f.splitlines()[0]
         patch = "rollout_kernelILb1E" in name

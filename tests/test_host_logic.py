@@ -30,7 +30,10 @@ def test_shard_range_rejects_bad_geometry():
 
 def test_grid_limits_follow_the_reference_formula(golden_cases):
     for case in golden_cases.values():
-        g = GridSpec(case["risk"].shape[0], float(case["resolution"]))
+        if "limits" not in case:
+            continue
+        grid = case["risk"] if "risk" in case else case["mean"]
+        g = GridSpec(grid.shape[0], float(case["resolution"]))
         assert (g.x_limits[0], g.x_limits[1], g.y_limits[0], g.y_limits[1]) == tuple(case["limits"].tolist())
 
 
