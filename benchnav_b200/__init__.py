@@ -2,6 +2,10 @@
 
 Public surface:
     MPPI                 drop-in for the reference ``src.planners.local_planners.mppi.MPPI``
+    BatchedMPPI          E planners (one per environment) in one launch (BASELINE config 3)
+    DWA                  drop-in for ``src.planners.local_planners.dwa.DWA`` on the same rollout kernel
+    BatchedPlanetaryEnv  ``PlanetaryEnv.step / collision_check`` for E environments on the device
+    infer_risk_map       ``TraversabilityModel._infer_risk_map`` on the device
     build_library()      (re)compile libbnvmppi.so in-tree with nvcc
     synthetic            synthetic terrain / problem generators used by bench.py and the tests
 """
@@ -15,4 +19,20 @@ def __getattr__(name):
         from .mppi import MPPI
 
         return MPPI
+    if name == "BatchedMPPI":
+        from .batch import BatchedMPPI
+
+        return BatchedMPPI
+    if name == "DWA":
+        from .dwa import DWA
+
+        return DWA
+    if name == "BatchedPlanetaryEnv":
+        from .env import BatchedPlanetaryEnv
+
+        return BatchedPlanetaryEnv
+    if name == "infer_risk_map":
+        from .risk import infer_risk_map
+
+        return infer_risk_map
     raise AttributeError(name)

@@ -97,6 +97,7 @@ _SIGNATURES = {
     "bnv_mppi_set_terminal_goal": (C.c_int, [_VP, _FP]),
     "bnv_mppi_set_goal_dev": (C.c_int, [_VP, _VP]),
     "bnv_mppi_argmin": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP]),
+    "bnv_mppi_dwa_subgoal": (C.c_int, [_VP, _VP, C.c_int32, _VP, _VP, C.c_float, _VP, _VP]),
     "bnv_mppi_launch_count": (C.c_uint64, [_VP]),
     "bnv_mppi_kernel_timing": (C.c_int, [_VP, C.c_int32]),
     "bnv_mppi_kernel_time": (C.c_int, [_VP, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
@@ -109,7 +110,6 @@ _SIGNATURES = {
     "bnv_risk_map": (C.c_int, [C.c_int32, C.c_float, C.c_int32, _VP, _VP, C.c_int64, _VP, C.c_int32, C.c_uint64, _VP,
                                _VP, _VP]),
     "bnv_dwa_actions": (C.c_int, [_VP, _FP, _FP, _FP, C.c_float, C.c_int32, C.c_int32, C.c_int32, _VP, _VP, _VP]),
-    "bnv_dwa_subgoal": (C.c_int, [_VP, C.c_int32, _VP, C.c_float, _VP, _VP]),
 }
 
 _lib = None

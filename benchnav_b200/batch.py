@@ -1,0 +1,133 @@
+"""``BatchedMPPI``: E independent MPPI planners -- one per ``PlanetaryEnv`` instance -- solved in ONE kernel launch
+(BASELINE config 3: "batched 64 planetary_env instances x K=4096, T=30").
+
+The reference has no batched planner: config 3's meaning is "E separate reference ``MPPI`` objects stepped in a Python
+loop" (SURVEY 8c), which is also how the parity tests check this class.  Here every per-solver buffer of the engine
+simply carries a leading E and the rollout kernel's grid gains a y dimension (environment); each environment has its
+own risk map, state, goal and mean sequence.  Environments, not samples, are what shards across GPUs: give every rank
+its own slice of the environment list (``benchnav_b200.dist.shard_range(E, rank, world)``) -- there is nothing to
+exchange, so no collective is involved.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _cabi
+from .mppi import _DevView, _introspect_problem
+
+
+class BatchedMPPI(nn.Module):
+    """E reference-shaped (dynamics, objectives) pairs with a common grid geometry -> one batched solver."""
+
+    def __init__(self, horizon: int, num_samples: int, dynamics_list: Sequence, objectives_list: Sequence,
+                 sigmas: torch.Tensor, lambda_: float, device=torch.device("cuda"), seed: int = 42) -> None:
+        super().__init__()
+        if len(dynamics_list) != len(objectives_list) or len(dynamics_list) < 1:
+            raise ValueError("need one objectives object per dynamics object")
+        assert sigmas.shape == (2,), "sigmas must be a tensor of shape (dim_control,)"
+        dev = torch.device(device)
+        if dev.type != "cuda" or not torch.cuda.is_available():
+            raise RuntimeError("benchnav_b200.BatchedMPPI runs on CUDA (sm_100a) only; there is no CPU fallback")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        self._device = dev
+        self._num_envs = E = len(dynamics_list)
+        self._horizon, self._num_samples = int(horizon), int(num_samples)
+        self._dynamics, self._objectives = list(dynamics_list), list(objectives_list)
+        self._lib = _cabi.load()
+        infos = [_introspect_problem(d, o) for d, o in zip(dynamics_list, objectives_list)]
+        _, g, res, x_lim, y_lim, _, thr, dt = infos[0]
+        for info in infos[1:]:
+            if (info[1], info[2], info[3], info[4], info[6], info[7]) != (g, res, x_lim, y_lim, thr, dt):
+                raise ValueError("all environments of a batch must share grid geometry, threshold and time step")
+        d0 = dynamics_list[0]
+        for d in dynamics_list[1:]:
+            if not (torch.equal(d.min_action.cpu(), d0.min_action.cpu()) and torch.equal(d.max_action.cpu(), d0.max_action.cpu())):
+                raise ValueError("all environments of a batch must share the action bounds")
+        cfg = _cabi.MppiCfg(num_samples=self._num_samples, horizon=self._horizon, lambda_=float(lambda_), dt=dt,
+                            seed=int(seed) & 0xFFFFFFFFFFFFFFFF, rank=0, world_size=1, device=dev.index,
+                            flags=_cabi.BNV_FLAG_RECORD_STATES, num_envs=E)
+        sig, lo, hi = (t.detach().cpu().to(torch.float32).tolist() for t in (sigmas, d0.min_action, d0.max_action))
+        for i in range(2):
+            cfg.sigma[i], cfg.u_min[i], cfg.u_max[i] = sig[i], lo[i], hi[i]
+        self._handle = C.c_void_p()
+        _cabi.check(self._lib.bnv_mppi_create(C.byref(self._handle), C.byref(cfg)))
+        self._geom = (g, res, x_lim, y_lim, thr)
+        self.sync_problems()
+        k, t = self._num_samples, self._horizon
+        view = lambda ptr, shape: torch.as_tensor(_DevView(ptr, shape, self), device=dev)  # noqa: E731
+        self._weights = view(self._lib.bnv_mppi_weights(self._handle), (E, k))
+        self._costs = view(self._lib.bnv_mppi_costs(self._handle), (E, k))
+        self._previous_action_seq = view(self._lib.bnv_mppi_u_prev(self._handle), (E, t, 2))
+        self._action_noises = view(self._lib.bnv_mppi_noise(self._handle), (E, k, t, 2))
+        self._state_seq_batch = view(self._lib.bnv_mppi_states(self._handle), (E, k, t + 1, 3))
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self._device).cuda_stream
+
+    def sync_problems(self) -> None:
+        """(Re)upload every environment's risk map and goal (call again after changing them)."""
+        g, res, x_lim, y_lim, thr = self._geom
+        risks = torch.stack([d._traversability_model._risks.detach().to(torch.float32).cpu() for d in self._dynamics])
+        self._risk_dev = risks.to(self._device).contiguous()
+        goals = (C.c_float * (2 * self._num_envs))()
+        for e, o in enumerate(self._objectives):
+            gx, gy = torch.as_tensor(o._goal_pos).detach().to("cpu", torch.float32).reshape(-1)[:2].tolist()
+            goals[2 * e], goals[2 * e + 1] = gx, gy
+        with torch.cuda.device(self._device):
+            _cabi.check(self._lib.bnv_mppi_set_problem_ex(
+                self._handle, self._risk_dev.data_ptr(), None, g, self._risk_dev.stride(1), self._risk_dev.stride(0),
+                res, x_lim[0], x_lim[1], y_lim[0], y_lim[1], goals, thr, self._stream()))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None) is not None and self._handle.value:
+                self._lib.bnv_mppi_destroy(self._handle)
+                self._handle = C.c_void_p()
+        except Exception:  # interpreter shutdown
+            pass
+
+    def forward(self, states: torch.Tensor, noise: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """One control iteration of every environment (mppi.py:130-219 x E).
+
+        ``states`` [E,3] -> ``(optimal_action_seq [E,T,2], optimal_state_seq [E,1,T+1,3])``;
+        ``noise`` (optional, [E,K,T,2]) injects the sigma-scaled control noise."""
+        E, t, k = self._num_envs, self._horizon, self._num_samples
+        assert tuple(states.shape) == (E, 3)
+        states = states.detach().to(self._device, torch.float32).contiguous()
+        noise_ptr = None
+        if noise is not None:
+            if tuple(noise.shape) != (E, k, t, 2):
+                raise ValueError(f"noise must have shape {(E, k, t, 2)}")
+            noise = noise.detach().to(self._device, torch.float32).contiguous()
+            noise_ptr = noise.data_ptr()
+        u_opt = torch.empty(E, t, 2, device=self._device, dtype=torch.float32)
+        opt_states = torch.empty(E, 1, t + 1, 3, device=self._device, dtype=torch.float32)
+        with torch.cuda.device(self._device):
+            _cabi.check(self._lib.bnv_mppi_forward(self._handle, states.data_ptr(), noise_ptr, u_opt.data_ptr(),
+                                                   opt_states.data_ptr(), self._stream()))
+        self._keepalive = (states, noise)
+        return u_opt, opt_states
+
+    def get_top_samples(self, num_samples: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Top ``num_samples`` rollouts of every environment by weight (mppi.py:221-240 x E): [E,n,T+1,3], [E,n]."""
+        assert num_samples <= self._num_samples
+        n, E = int(num_samples), self._num_envs
+        states = torch.empty(E, n, self._horizon + 1, 3, device=self._device, dtype=torch.float32)
+        weights = torch.empty(E, n, device=self._device, dtype=torch.float32)
+        with torch.cuda.device(self._device):
+            _cabi.check(self._lib.bnv_mppi_top_samples(self._handle, n, states.data_ptr(), weights.data_ptr(),
+                                                       self._stream()))
+        return states, weights
+
+    def reset(self) -> None:
+        _cabi.check(self._lib.bnv_mppi_reset(self._handle, self._stream()))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.bnv_mppi_launch_count(self._handle))

@@ -249,17 +249,33 @@ __global__ void __launch_bounds__(128) dwa_actions_kernel(const float* __restric
   for (int t = 0; t < T; ++t) row[t] = make_float2(v, w);
 }
 
-// dwa.py:260-285: among path points ahead of the robot (|atan2(d) - theta| < pi/2) and farther than the lookahead
-// distance, the nearest one (first index whose distance equals that minimum); the last point if there is none.
+// dwa.py:225-228 + :260-285.  The reference selects the sub-goal from state_seq_batch[0, 0, :] AFTER the simulation:
+// the raw (unclamped, unwrapped) successor that transit's in-place update left in slot 0 of the FIRST action's
+// rollout, not the robot state.  Thread 0 recomputes that one step (traversability lookup in the engine's tau map,
+// robot_model.py:75-88), then: among path points ahead of it (|atan2(d) - theta| < pi/2) and farther than the
+// lookahead distance, the nearest one (first index whose distance equals that minimum); the last point if none.
 // One CTA.
-__global__ void __launch_bounds__(256) dwa_subgoal_kernel(const float* __restrict__ path, int N,
+__global__ void __launch_bounds__(256) dwa_subgoal_kernel(GridGeom geom, int G, const float* __restrict__ tau,
+                                                          int pitch, Bounds b, const float* __restrict__ actions,
+                                                          const float* __restrict__ path, int N,
                                                           const float* __restrict__ state, float lookahead,
                                                           float* __restrict__ goal_out) {
   __shared__ float s_min[8];
   __shared__ int s_idx[8];
   __shared__ float s_best;
+  __shared__ float s_ref[3];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float sx = state[0], sy = state[1], sth = state[2];
+  if (tid == 0) {
+    float x = state[0], y = state[1], th = state[2], xr, yr, thr;
+    const float t0 = tau[cell_of(geom, G, pitch, x, y)];
+    const float v0 = clampf(actions[0], b.u_min0, b.u_max0), v1 = clampf(actions[1], b.u_min1, b.u_max1);
+    StepConsts c{};
+    c.x_min = geom.x_min; c.y_min = geom.y_min; c.x_max = geom.x_max; c.y_max = geom.y_max; c.dt = b.dt;
+    unicycle_step<false>(c, t0, v0, v1, x, y, th, xr, yr, thr);
+    s_ref[0] = xr; s_ref[1] = yr; s_ref[2] = thr;
+  }
+  __syncthreads();
+  const float sx = s_ref[0], sy = s_ref[1], sth = s_ref[2];
   float best = INFINITY;
   for (int i = tid; i < N; i += blockDim.x) {
     const float dx = __fsub_rn(path[2 * i], sx), dy = __fsub_rn(path[2 * i + 1], sy);

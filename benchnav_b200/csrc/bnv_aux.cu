@@ -64,6 +64,14 @@ int bnv_launch_argmin(const float* costs, int K, const float* actions, const flo
   return BNV_OK;
 }
 
+int bnv_launch_dwa_subgoal(const bnv::GridGeom& geom, int G, const float* tau, int pitch, const bnv::Bounds& b,
+                           const float* actions, const float* path, int n, const float* state, float lookahead,
+                           float* goal_out, cudaStream_t s) {
+  bnv::dwa_subgoal_kernel<<<1, 256, 0, s>>>(geom, G, tau, pitch, b, actions, path, n, state, lookahead, goal_out);
+  BNV_CUDA(cudaGetLastError());
+  return BNV_OK;
+}
+
 extern "C" {
 
 int bnv_trav_lookup(const bnv_grid* grid, const float* mean_dev, const float* std_dev, int64_t env_stride,
@@ -160,15 +168,6 @@ int bnv_dwa_actions(const float* prev_action_dev, const float u_min[2], const fl
   const int n = num_lin_vel * num_ang_vel;
   bnv::dwa_actions_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
       prev_action_dev, b, a_lim[0], a_lim[1], delta_t, num_lin_vel, num_ang_vel, horizon, actions_out_dev, controls_out_dev);
-  BNV_CUDA(cudaGetLastError());
-  return BNV_OK;
-}
-
-int bnv_dwa_subgoal(const float* path_dev, int32_t n, const float* state_dev, float lookahead_distance,
-                    float* goal_out_dev, void* stream) {
-  if (!path_dev || !state_dev || !goal_out_dev) return bnv_fail(BNV_ERR_INVALID, "null argument");
-  if (n < 1) return bnv_fail(BNV_ERR_INVALID, "empty reference path");
-  bnv::dwa_subgoal_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(path_dev, n, state_dev, lookahead_distance, goal_out_dev);
   BNV_CUDA(cudaGetLastError());
   return BNV_OK;
 }

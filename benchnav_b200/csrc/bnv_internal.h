@@ -6,6 +6,8 @@
 
 namespace bnv {
 struct EngineParams;
+struct GridGeom;
+struct Bounds;
 }
 
 // Records a thread-local message for bnv_last_error() and returns `code` (defined in bnv_mppi.cu).
@@ -27,3 +29,8 @@ BnvRolloutFn bnv_pick_rollout_ext(bool patch, bool pow2, bool philox, bool stoch
 // argmin_gather_kernel (aux_kernels.cuh) launcher, defined in bnv_aux.cu.
 int bnv_launch_argmin(const float* costs, int K, const float* actions, const float* rec, int row_len, float* action_out,
                       float* states_out, int* idx_out, cudaStream_t s);
+
+// dwa_subgoal_kernel (aux_kernels.cuh) launcher, defined in bnv_aux.cu.
+int bnv_launch_dwa_subgoal(const bnv::GridGeom& geom, int G, const float* tau, int pitch, const bnv::Bounds& b,
+                           const float* actions, const float* path, int n, const float* state, float lookahead,
+                           float* goal_out, cudaStream_t s);

@@ -734,6 +734,19 @@ int bnv_mppi_argmin(bnv_mppi* h, const float* actions_dev, float* action_out_dev
   return rc;
 }
 
+int bnv_mppi_dwa_subgoal(bnv_mppi* h, const float* path_dev, int32_t n, const float* state_dev, const float* actions_dev,
+                         float lookahead_distance, float* goal_out_dev, void* stream) {
+  if (!h || !path_dev || !state_dev || !actions_dev || !goal_out_dev) return fail(BNV_ERR_INVALID, "null argument");
+  if (n < 1) return fail(BNV_ERR_INVALID, "empty reference path");
+  if (!h->problem_set) return fail(BNV_ERR_STATE, "bnv_mppi_set_problem must be called first");
+  if (h->stoch || h->E > 1) return fail(BNV_ERR_INVALID, "needs a deterministic single solver");
+  BNV_CUDA(cudaSetDevice(h->cfg.device));
+  int rc = bnv_launch_dwa_subgoal(h->P.geom, h->P.G, h->tau, h->P.pitch, h->P.bounds, actions_dev, path_dev, n, state_dev,
+                                  lookahead_distance, goal_out_dev, static_cast<cudaStream_t>(stream));
+  if (rc == BNV_OK) h->launches++;
+  return rc;
+}
+
 uint64_t bnv_mppi_launch_count(const bnv_mppi* h) { return h ? h->launches : 0; }
 
 int bnv_mppi_kernel_timing(bnv_mppi* h, int32_t max_launches) {

@@ -194,7 +194,7 @@ int bnv_mppi_draw_xi(bnv_mppi* h, uint64_t iteration, float* xi_out_dev, float* 
  *   bnv_mppi_set_terminal_goal        goal of the terminal cost (always the final goal, dwa.py:233) when the stage
  *                                     cost follows a sub-goal (dwa.py:225-231); reset by bnv_mppi_set_problem*
  *   bnv_mppi_set_goal_dev             device-resident [2] override of the stage-cost goal (the sub-goal selected by
- *                                     bnv_dwa_subgoal), NULL = back to the goal of bnv_mppi_set_problem
+ *                                     bnv_mppi_dwa_subgoal), NULL = back to the goal of bnv_mppi_set_problem
  *   bnv_mppi_argmin                   first index of the minimum cost of the last forward, that sample's action
  *                                     (from actions_dev [K,2]) and recorded states [T+1,3] (dwa.py:141-144) */
 int bnv_mppi_set_keep_mean(bnv_mppi* h, int32_t keep);
@@ -202,6 +202,12 @@ int bnv_mppi_set_terminal_goal(bnv_mppi* h, const float goal_xy[2]);
 int bnv_mppi_set_goal_dev(bnv_mppi* h, const float* goal_dev);
 int bnv_mppi_argmin(bnv_mppi* h, const float* actions_dev, float* action_out_dev, float* states_out_dev,
                     int32_t* index_out_dev, void* stream);
+/* DWA._select_sub_goal (dwa.py:260-285) as DWA._compute_costs calls it (dwa.py:225-228): on
+ * state_seq_batch[0, 0, :] AFTER the simulation, i.e. on the raw successor that transit's in-place update left in
+ * slot 0 of the first action's rollout -- recomputed here from state_dev [3], actions_dev[0] and the handle's
+ * traversability map.  path_dev [n,2] -> goal_out_dev [2] (feed it to bnv_mppi_set_goal_dev). */
+int bnv_mppi_dwa_subgoal(bnv_mppi* h, const float* path_dev, int32_t n, const float* state_dev, const float* actions_dev,
+                         float lookahead_distance, float* goal_out_dev, void* stream);
 
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 uint64_t bnv_mppi_launch_count(const bnv_mppi* h);
@@ -275,10 +281,6 @@ int bnv_risk_map(int32_t metric, float confidence, int32_t method, const float* 
 int bnv_dwa_actions(const float* prev_action_dev, const float u_min[2], const float u_max[2], const float a_lim[2],
                     float delta_t, int32_t num_lin_vel, int32_t num_ang_vel, int32_t horizon, float* actions_out_dev,
                     float* controls_out_dev, void* stream);
-
-/* DWA._select_sub_goal (dwa.py:260-285): path_dev [n,2], state_dev [3] -> goal_out_dev [2]. */
-int bnv_dwa_subgoal(const float* path_dev, int32_t n, const float* state_dev, float lookahead_distance,
-                    float* goal_out_dev, void* stream);
 
 #ifdef __cplusplus
 }
