@@ -306,6 +306,7 @@ def run_native(args) -> None:
                                    (", fused P2P mailbox exchange in-kernel" if solver._fused_exchange else
                                     ", NCCL all-gather + finalize kernel")),
                    "l2": "flushed between timed steps (256 MiB write); per-step CUDA-event pairs",
+                   "launch": solver.launch_geometry,
                    "control_iters_per_sec": control_rate, "back_to_back_ms_per_step": hot_ms,
                    "rollout_steps_per_sec": control_rate * k_total * HORIZON},
         "roofline": {"bound": "hbm", "kernel": "bnv::rollout_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",

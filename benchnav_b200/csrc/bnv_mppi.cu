@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -108,6 +109,7 @@ struct bnv_mppi {
   unsigned long long* top_pairs = nullptr;
   size_t top_pairs_cap = 0, top_idx_cap = 0;
   float* io_host = nullptr;  // pinned mirror of io_dev
+  float* io_host_dev = nullptr;  // its device-side address (zero-copy)
   int grid = 0, warps = 0;
   long long resident_ctas = 0;  // how many rollout CTAs the device can hold at once (cooperative-launch bound)
   bool fast_angles = false;
@@ -250,7 +252,8 @@ int bnv_mppi_create(bnv_mppi** out, const bnv_mppi_cfg* cfg) {
     delete h;
     return fail(BNV_ERR_UNSUPPORTED, "batched / stochastic-slip solvers need dt * max|omega| < 3 rad per step");
   }
-  const size_t io_floats = 3 + 2 * static_cast<size_t>(T) + 3 * static_cast<size_t>(T + 1);
+  // [3] state + [2T] u_out + [3(T+1)] opt states + completion word (padded to 4 floats)
+  const size_t io_floats = 3 + 2 * static_cast<size_t>(T) + 3 * static_cast<size_t>(T + 1) + 4;
   cudaError_t e = cudaSuccess;
   auto alloc = [&](void** p, size_t bytes) {
     if (e == cudaSuccess) e = cudaMalloc(p, bytes);
@@ -276,6 +279,7 @@ int bnv_mppi_create(bnv_mppi** out, const bnv_mppi_cfg* cfg) {
     if (e == cudaSuccess) e = cudaMemset(h->mbox, 0, sizeof(float) * h->mbox_floats);
   }
   if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&h->io_host), sizeof(float) * io_floats, cudaHostAllocMapped);
+  if (e == cudaSuccess) std::memset(h->io_host, 0, sizeof(float) * io_floats);
   if (e == cudaSuccess) e = cudaMemset(h->u_prev, 0, sizeof(float) * nE * T * 2);  // mppi.py:116
   if (e == cudaSuccess) e = cudaMemset(h->ticket, 0, 2 * nE * sizeof(unsigned int));
   if (e == cudaSuccess) e = cudaMemset(h->weights, 0, sizeof(float) * nE * Kl);    // mppi.py:126-128
@@ -305,6 +309,7 @@ int bnv_mppi_create(bnv_mppi** out, const bnv_mppi_cfg* cfg) {
   P.num_envs = E;
   P.goals = nullptr;
   P.keep_mean = 1;
+  P.done_flag = nullptr;
   P.xi_in = nullptr;
   P.xi_opt_in = nullptr;
   P.Kl = Kl;
@@ -544,11 +549,30 @@ int bnv_mppi_forward_host(bnv_mppi* h, const float state_host[3], const float* n
   // Host -> device: the 12-byte state rides in the kernel's launch packet.  Device -> host: the kernel stores u* and
   // the optimal state sequence straight into the handle's pinned, device-mapped staging buffer (zero-copy over
   // PCIe); one stream synchronisation makes them visible, then they are copied out to the caller's buffers.
-  float* out_dev = nullptr;
-  BNV_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&out_dev), h->io_host, 0));
+  if (!h->io_host_dev) BNV_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->io_host_dev), h->io_host, 0));
+  float* out_dev = h->io_host_dev;
+  // Completion: the kernel raises a word in the same pinned buffer as soon as both results are written (before its
+  // tail: slab stores draining, CTAs exiting); the host polls it instead of paying a stream synchronisation.
+  const size_t flag_off = 3 + 2 * static_cast<size_t>(T) + 3 * static_cast<size_t>(T + 1);
+  volatile unsigned int* flag = reinterpret_cast<volatile unsigned int*>(h->io_host + flag_off);
+  h->P.done_flag = reinterpret_cast<unsigned int*>(out_dev + flag_off);
   int rc = launch_forward(h, nullptr, state_host, noise_dev, out_dev + 3, out_dev + 3 + 2 * T, s);
+  h->P.done_flag = nullptr;
   if (rc != BNV_OK) return rc;
-  BNV_CUDA(cudaStreamSynchronize(s));
+  const unsigned int want = h->epoch;
+  bool seen = false;
+  for (long spins = 0; spins < 50000000L; ++spins) {  // a fault or a stuck device ends in the synchronise below
+    if (*flag == want) {
+      seen = true;
+      break;
+    }
+    if ((spins & 1023) == 1023 && cudaStreamQuery(s) != cudaErrorNotReady) break;
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#endif
+  }
+  if (!seen) BNV_CUDA(cudaStreamSynchronize(s));
+  std::atomic_thread_fence(std::memory_order_acquire);
   std::memcpy(u_out_host, h->io_host + 3, 2 * static_cast<size_t>(T) * sizeof(float));
   std::memcpy(opt_states_host, h->io_host + 3 + 2 * T, 3 * static_cast<size_t>(T + 1) * sizeof(float));
   return BNV_OK;
@@ -748,6 +772,17 @@ int bnv_mppi_dwa_subgoal(bnv_mppi* h, const float* path_dev, int32_t n, const fl
 }
 
 uint64_t bnv_mppi_launch_count(const bnv_mppi* h) { return h ? h->launches : 0; }
+
+int bnv_mppi_launch_geometry(const bnv_mppi* h, int32_t out[4]) {
+  if (!h || !out) return fail(BNV_ERR_INVALID, "null argument");
+  if (!h->problem_set) return fail(BNV_ERR_STATE, "bnv_mppi_set_problem must be called first");
+  const bool coop = h->coop_ok && static_cast<long long>(h->grid) * h->E <= h->resident_ctas;
+  out[0] = h->grid;
+  out[1] = h->warps;
+  out[2] = 1;  // thread-block clusters: measured slower than the L2 merge for this epilogue, not used
+  out[3] = coop ? 1 : 0;
+  return BNV_OK;
+}
 
 int bnv_mppi_kernel_timing(bnv_mppi* h, int32_t max_launches) {
   if (!h || max_launches < 0) return fail(BNV_ERR_INVALID, "bad argument");

@@ -72,6 +72,8 @@ struct alignas(64) EngineParams {
   unsigned int* ticket;  // [0] arrival counter of the last-CTA election, [1] "merge done" epoch flag (coop)
   float* stats;          // [2] (M, S) of the last merge, published to the waiting CTAs (coop)
   unsigned int epoch;    // unique per launch
+  unsigned int* done_flag;  // optional, mapped HOST memory: set to `epoch` once u_out / opt_rec are complete, so that a
+                            // host thread polling it sees the results without waiting for the kernel's tail
   int keep_mean;         // write u* back as the next call's mean sequence (mppi.py:217); 0 for DWA's constant actions
   int coop;              // grid is co-resident (cooperative launch): deferred slab stores, in-register weights
   float* const* peer_mbox;  // [world] device pointers to every rank's mailbox (peer memory over NVLink), or null
@@ -428,6 +430,15 @@ __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) 
 }
 __device__ __forceinline__ void st_release_gpu(unsigned int* p, unsigned int v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Results complete (u_out and opt_rec written by this CTA, ordered before this thread by the CTA barrier): publish
+// them system-wide and raise the host-visible completion word.
+__device__ __forceinline__ void signal_done(const EngineParams& P) {
+  if (P.done_flag != nullptr) {
+    __threadfence_system();
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(P.done_flag), "r"(P.epoch) : "memory");
+  }
 }
 
 // One rollout step of one sample (mppi.py:152-165, :174-182): control from mean + noise, unicycle step, recorded
@@ -950,6 +961,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
                           P.iter_lo, iter_hi_e, key};
         optimal_rollout<kPatch, kPow2, kFastAngles, kStoch>(T, C, warpu_s, sx, sy, sth,
                                                             P.opt_rec + static_cast<size_t>(env) * 3 * (T + 1), xs);
+        signal_done(P);
       }
       if (stamp) BNV_STAMP(7);
       if (!(own_thread && tid < 32)) {
@@ -978,6 +990,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
                         P.iter_lo, iter_hi_e, key};
       optimal_rollout<kPatch, kPow2, kFastAngles, kStoch>(T, C, warpu_s, sx, sy, sth,
                                                           P.opt_rec + static_cast<size_t>(env) * 3 * (T + 1), xs);
+      signal_done(P);
     }
     if (is_last && P.dbg_ts != nullptr && env == 0) BNV_STAMP(7);
   }

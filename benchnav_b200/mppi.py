@@ -177,7 +177,10 @@ class MPPI(nn.Module):
         return (eps * self._sigmas).contiguous()
 
     def _stream(self) -> int:
-        return torch.cuda.current_stream(self._device).cuda_stream
+        try:  # raw handle of torch's current stream without building a Stream object (~1 us saved per call)
+            return torch._C._cuda_getCurrentRawStream(self._device.index)
+        except AttributeError:
+            return torch.cuda.current_stream(self._device).cuda_stream
 
     def _sync_problem(self, force: bool = False) -> None:
         """(Re)upload the risk map / goal / threshold when the reference objects changed (cheap identity check)."""
@@ -331,6 +334,13 @@ class MPPI(nn.Module):
     @property
     def launch_count(self) -> int:
         return int(self._lib.bnv_mppi_launch_count(self._handle))
+
+    @property
+    def launch_geometry(self) -> dict:
+        """Rollout-kernel launch shape: CTAs, warps per CTA, thread-block cluster size, cooperative or not."""
+        out = (C.c_int32 * 4)()
+        _cabi.check(self._lib.bnv_mppi_launch_geometry(self._handle, out))
+        return {"ctas": out[0], "warps_per_cta": out[1], "cluster": out[2], "cooperative": bool(out[3])}
 
     def kernel_timing(self, max_launches: int) -> None:
         """Record CUDA-event pairs around the rollout kernel of the next ``max_launches`` iterations."""
