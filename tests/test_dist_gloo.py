@@ -72,3 +72,50 @@ def test_two_rank_partial_exchange_and_merge():
     np.testing.assert_allclose(res[0][1], case["u_opt_0"], atol=2e-5)  # == reference single-process u*
     np.testing.assert_allclose(res[0][3], case["top_weights_0"][:8], atol=1e-5)
     np.testing.assert_array_equal(res[0][3], res[1][3])
+
+
+def _env_worker(rank: int, world: int, port: int, q) -> None:
+    """Batched solvers shard ENVIRONMENTS: every rank plans for its slice of the environment list and nothing is
+    exchanged (the process group exists only so that the ranks agree on the partition)."""
+    import sys
+
+    sys.path.insert(0, ROOT)
+    from benchnav_b200.dist import ShardInfo, shard_range
+    from oracle import mppi_oracle as orc
+    from tests.helpers import problem_from_golden
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        case = dict(np.load(os.path.join(ROOT, "tests", "golden", "tiny_g8_k33_t1.npz")))
+        p = problem_from_golden(case)
+        shard = ShardInfo.from_group(dist.group.WORLD)
+        E = 5
+        a, b = shard_range(E, shard.rank, shard.world_size)
+        out = {}
+        for e in range(a, b):  # environment e = the golden problem with its own goal and start state
+            pe = orc.make_problem(p.risk, p.resolution, (p.goal[0] - 0.3 * e, p.goal[1] + 0.2 * e), p.stuck_threshold)
+            st = torch.from_numpy(case["state_0"]) + torch.tensor([0.1 * e, 0.0, 0.05 * e])
+            r = orc.mppi_iteration(pe, st, torch.from_numpy(case["u_prev_0"]), torch.from_numpy(case["noise_0"]),
+                                   torch.from_numpy(case["sigmas"]), float(case["lam"]))
+            out[e] = r["u_opt"].numpy()
+        q.put((rank, (a, b), out))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_environment_sharding_needs_no_exchange():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_env_worker, args=(r, world, port, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda x: x[0])
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    assert res[0][1] == (0, 2) and res[1][1] == (2, 5)  # contiguous, disjoint, covering slices of the 5 environments
+    merged = {**res[0][2], **res[1][2]}
+    assert sorted(merged) == list(range(5))
+    assert not np.array_equal(merged[0], merged[4])  # the environments really are different problems
