@@ -327,3 +327,57 @@ def test_dwa_golden_calls(golden_cases):
         ts, tw = solver.get_top_samples()
         np.testing.assert_allclose(tw.cpu().numpy(), c[f"top_weights_{i}"], rtol=0, atol=2e-4)
         assert ts.shape == (100, T + 1, 3) and bool((tw[:-1] >= tw[1:]).all())
+
+
+# ------------------------------------------------------------------------------------------------ closed loop
+def test_closed_loop_planner_and_environment_follow_the_oracle():
+    """Tutorial 3.3's loop (solver.forward -> env.step -> collision_check -> get_top_samples) on the device for three
+    environments at once, against the same loop run with the CPU oracles on identical injected draws."""
+    from benchnav_b200 import BatchedMPPI, BatchedPlanetaryEnv
+
+    E, K, T, g, sig, lam, steps = 3, 512, 20, 64, [0.5, 0.5], 0.5, 12
+    dyns, objs, risks, goals, states0, thr = _batch_problems(E, g)
+    stds = [torch.full((g, g), 0.03) for _ in range(E)]
+
+    class GM:
+        def __init__(self, mean, std):
+            from benchnav_b200.problem import SlipDistribution
+
+            self.grid_size, self.resolution = g, 0.5
+            self.x_limits = self.y_limits = (0.0, g * 0.5)
+            self.distributions = {"latent_models": SlipDistribution(mean, std)}
+
+    planner = BatchedMPPI(T, K, dyns, objs, torch.tensor(sig), lam, seed=9)
+    env = BatchedPlanetaryEnv([GM(risks[e], stds[e]) for e in range(E)], states0[:, :2], torch.stack(goals),
+                              stuck_threshold=0.1)
+    env._robot_state.copy_(states0)  # same start heading as the oracle loop
+    gen = torch.Generator().manual_seed(21)
+    ref_state = states0.clone()
+    ref_uprev = torch.zeros(E, T, 2)
+    for step in range(steps):
+        noise = torch.randn(E, K, T, 2, generator=gen) * torch.tensor(sig)
+        xi = torch.randn(E, generator=gen)
+        xi_c = torch.randn(E, T + 1, generator=gen)
+        u, seq = planner.forward(env._robot_state, noise=noise)
+        coll = env.collision_check(seq[:, 0], xi=xi_c)
+        top_s, top_w = planner.get_top_samples(16)
+        st, rew, term, trunc = env.step(u[:, 0, :], xi=xi)
+        torch.cuda.synchronize()
+        for e in range(E):
+            p = orc.make_problem(risks[e], 0.5, goals[e].tolist(), thr)
+            ref = orc.mppi_iteration(p, ref_state[e], ref_uprev[e], noise[e], torch.tensor(sig), lam)
+            ps = orc.make_problem(risks[e], 0.5, goals[e].tolist(), thr)
+            ps.slip_std = stds[e]
+            want_coll = eo.collision_check(ps, ref["opt_rec"], 0.1, xi_c[e].view(1, -1))
+            nxt, r_rew, r_term = eo.env_step(ps, ref_state[e].view(1, 3), ref["u_opt"][0].view(1, 2), goals[e].view(1, 2),
+                                             0.1, 1.0, xi[e].view(1))
+            np.testing.assert_allclose(u[e].cpu().numpy(), ref["u_opt"].numpy(), rtol=0, atol=2e-3 * (step + 1))
+            np.testing.assert_allclose(st[e].cpu().numpy(), nxt[0].numpy(), rtol=0, atol=1e-3 * (step + 1))
+            np.testing.assert_allclose(rew[e].item(), r_rew[0].item(), rtol=0, atol=1e-6)
+            assert bool(term[e]) == bool(r_term[0])
+            assert int((coll[e].cpu() != want_coll[0]).sum()) <= 1  # a position within rounding of a cell border
+            assert top_s.shape == (E, 16, T + 1, 3) and bool((top_w[e][:-1] >= top_w[e][1:]).all())
+            ref_state[e] = nxt[0]
+            ref_uprev[e] = ref["u_opt"]
+    moved = (env._robot_state[:, :2].cpu() - states0[:, :2]).norm(dim=1)
+    assert float(moved.min()) > 0.2  # the robots actually drive
