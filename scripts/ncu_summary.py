@@ -67,6 +67,28 @@ def main() -> None:
                 f.write(f"# share of the step (our kernels only): {k[:60]} {sum(v) / tot_ours * 100:5.1f}%\n")
         print(open(os.path.join(PROF, f"{args.tag}_launches_summary.txt")).read())
 
+    # extra full captures of the widened path (scripts/profile_targets.py): one summary file each
+    extra = {"prof_batch": ("batch_ncu_summary", "rollout_kernel<.., kBatch>: 8 environments x K=4096 x T=30 (config 3 per-GPU share)"),
+             "prof_stoch": ("stoch_ncu_summary", "rollout_kernel<.., kStoch>: G=256, K=32768, T=50 (config 4)"),
+             "prof_risk": ("risk_mc_ncu_summary", "risk_mc_kernel: G=256, 1000 draws per cell, CVaR")}
+    for stem, (name, what) in extra.items():
+        rep_x = os.path.join(OUT, stem + ".ncu-rep")
+        if not os.path.exists(rep_x):
+            continue
+        raw = subprocess.run(["ncu", "-i", rep_x, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(raw.splitlines()))
+        hdr, units, data = rows[0], rows[1], rows[2:]
+        with open(os.path.join(PROF, f"{args.tag}_{name}.txt"), "w") as f:
+            f.write(f"# {args.tag}: ncu --set full --clock-control none --import-source on, {what}\n")
+            f.write("# one column per captured launch; ncu flushes caches between replays (cold)\n")
+            if "Kernel Name" in hdr:
+                f.write("# kernel: " + data[0][hdr.index("Kernel Name")][:150] + "\n")
+            for m in METRICS:
+                if m in hdr:
+                    i = hdr.index(m)
+                    f.write(f"{m:70s} [{units[i]:>16s}] " + "  ".join(r[i] for r in data) + "\n")
+        print(open(os.path.join(PROF, f"{args.tag}_{name}.txt")).read())
+
     rep = os.path.join(OUT, "prof_rollout.ncu-rep")
     if os.path.exists(rep):
         raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
