@@ -82,33 +82,47 @@ __device__ __forceinline__ int cell_coord_rt(float p, float p_min, const GridGeo
 // kMagic: the position is known to lie inside the map limits (every state after the first step is clamped to
 // them), so floor() can use the magic-constant add; the bias stays in the index and is folded into the clamp
 // bounds and the table base.  Same cell as the F2I path for every in-range position.
-template <bool kPatch, bool kPow2, bool kMagic>
-__device__ __forceinline__ float lookup_tau(const StepConsts& c, float x, float y) {
-  int idx;
+//
+// cell_ref(): where the cell's entry lives -- the shared-memory byte address (kPatch) or the element index in the
+// global table -- for entries of kElem bytes; two positions are in the same cell iff their cell_ref is equal.
+template <bool kPatch, bool kPow2, bool kMagic, uint32_t kElem>
+__device__ __forceinline__ uint32_t cell_ref(const StepConsts& c, float x, float y) {
   if (kMagic) {
     float dx = __fsub_rn(x, c.x_min), dy = __fsub_rn(y, c.y_min);
     float qx = kPow2 ? __fmul_rn(dx, c.inv_res) : __fdiv_rn(dx, c.res);
     float qy = kPow2 ? __fmul_rn(dy, c.inv_res) : __fdiv_rn(dy, c.res);
     int ix = min(max(__float_as_int(__fadd_rd(qx, kMagicFloat)), c.mlo_x), c.mhi_x);
     int iy = min(max(__float_as_int(__fadd_rd(qy, kMagicFloat)), c.mlo_y), c.mhi_y);
-    if (kPatch) {
-      float t;
-      uint32_t a = c.mwin_addr + 4u * (static_cast<uint32_t>(iy) * static_cast<uint32_t>(c.pitch) + static_cast<uint32_t>(ix));
-      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(a));
-      return t;
-    }
-    idx = (iy - kMagicBits) * c.pitch + (ix - kMagicBits);
-  } else {
-    int ix = min(max(cell_coord<kPow2>(x, c.x_min, c.res, c.inv_res), c.lo_x), c.hi_x);
-    int iy = min(max(cell_coord<kPow2>(y, c.y_min, c.res, c.inv_res), c.lo_y), c.hi_y);
-    idx = iy * c.pitch + ix;
-    if (kPatch) {
-      float t;
-      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(c.win_addr + 4u * static_cast<uint32_t>(idx)));
-      return t;
-    }
+    if (kPatch)
+      return c.mwin_addr + kElem * (static_cast<uint32_t>(iy) * static_cast<uint32_t>(c.pitch) + static_cast<uint32_t>(ix));
+    return static_cast<uint32_t>((iy - kMagicBits) * c.pitch + (ix - kMagicBits));
   }
-  return __ldg(c.map + idx);
+  int ix = min(max(cell_coord<kPow2>(x, c.x_min, c.res, c.inv_res), c.lo_x), c.hi_x);
+  int iy = min(max(cell_coord<kPow2>(y, c.y_min, c.res, c.inv_res), c.lo_y), c.hi_y);
+  const uint32_t idx = static_cast<uint32_t>(iy * c.pitch + ix);
+  return kPatch ? c.win_addr + kElem * idx : idx;
+}
+template <bool kPatch>
+__device__ __forceinline__ float load_tau(const StepConsts& c, uint32_t ref) {
+  if (kPatch) {
+    float t;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(ref));
+    return t;
+  }
+  return __ldg(c.map + ref);
+}
+template <bool kPatch>
+__device__ __forceinline__ float2 load_slip(const StepConsts& c, uint32_t ref) {
+  if (kPatch) {
+    float2 t;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(t.x), "=f"(t.y) : "r"(ref));
+    return t;
+  }
+  return __ldg(reinterpret_cast<const float2*>(c.map) + ref);
+}
+template <bool kPatch, bool kPow2, bool kMagic>
+__device__ __forceinline__ float lookup_tau(const StepConsts& c, float x, float y) {
+  return load_tau<kPatch>(c, cell_ref<kPatch, kPow2, kMagic, 4u>(c, x, y));
 }
 
 // Stochastic-slip mode (BASELINE config 4; observation-mode lookup, traversability_model.py:65-69 +
@@ -116,31 +130,7 @@ __device__ __forceinline__ float lookup_tau(const StepConsts& c, float x, float 
 // Same cell index as lookup_tau; returns (mean, std).
 template <bool kPatch, bool kPow2, bool kMagic>
 __device__ __forceinline__ float2 lookup_slip(const StepConsts& c, float x, float y) {
-  int idx;
-  if (kMagic) {
-    float dx = __fsub_rn(x, c.x_min), dy = __fsub_rn(y, c.y_min);
-    float qx = kPow2 ? __fmul_rn(dx, c.inv_res) : __fdiv_rn(dx, c.res);
-    float qy = kPow2 ? __fmul_rn(dy, c.inv_res) : __fdiv_rn(dy, c.res);
-    int ix = min(max(__float_as_int(__fadd_rd(qx, kMagicFloat)), c.mlo_x), c.mhi_x);
-    int iy = min(max(__float_as_int(__fadd_rd(qy, kMagicFloat)), c.mlo_y), c.mhi_y);
-    if (kPatch) {
-      float2 t;
-      uint32_t a = c.mwin_addr + 8u * (static_cast<uint32_t>(iy) * static_cast<uint32_t>(c.pitch) + static_cast<uint32_t>(ix));
-      asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(t.x), "=f"(t.y) : "r"(a));
-      return t;
-    }
-    idx = (iy - kMagicBits) * c.pitch + (ix - kMagicBits);
-  } else {
-    int ix = min(max(cell_coord<kPow2>(x, c.x_min, c.res, c.inv_res), c.lo_x), c.hi_x);
-    int iy = min(max(cell_coord<kPow2>(y, c.y_min, c.res, c.inv_res), c.lo_y), c.hi_y);
-    idx = iy * c.pitch + ix;
-    if (kPatch) {
-      float2 t;
-      asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(t.x), "=f"(t.y) : "r"(c.win_addr + 8u * static_cast<uint32_t>(idx)));
-      return t;
-    }
-  }
-  return __ldg(reinterpret_cast<const float2*>(c.map) + idx);
+  return load_slip<kPatch>(c, cell_ref<kPatch, kPow2, kMagic, 8u>(c, x, y));
 }
 
 // 1 - clamp(sample, 0, 1) with sample = xi * std + mean: Normal(mean, std).sample() is ATen's
