@@ -26,6 +26,7 @@ int make_geom(const bnv_grid* g, bnv::GridGeom* out) {
   out->res = g->resolution;
   out->inv_res = 1.0f / g->resolution;
   out->res_pow2 = pow2_float(g->resolution) ? 1 : 0;
+  out->fast_grid = (out->res_pow2 && g->x_min == 0.0f && g->y_min == 0.0f) ? 1 : 0;
   return BNV_OK;
 }
 

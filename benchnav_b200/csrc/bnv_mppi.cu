@@ -168,7 +168,7 @@ RolloutFn pick_rollout1(bool b, bool c, bool d, bool e) {
   return b ? pick_rollout2<A, true>(c, d, e) : pick_rollout2<A, false>(c, d, e);
 }
 RolloutFn pick_rollout(const bnv_mppi* h, bool philox) {
-  const bool a = h->P.use_patch, b = h->P.geom.res_pow2, c = h->P.record, d = h->fast_angles;
+  const bool a = h->P.use_patch, b = h->P.geom.fast_grid, c = h->P.record, d = h->fast_angles;
   if (h->stoch || h->E > 1) return bnv_pick_rollout_ext(a, b, philox, h->stoch, h->E > 1);  // record + fast angles
   return a ? pick_rollout1<true>(b, c, d, philox) : pick_rollout1<false>(b, c, d, philox);
 }
@@ -177,7 +177,7 @@ FinalizeFn pick_finalize2(bool c) {
   return c ? bnv::finalize_kernel<A, B, true> : bnv::finalize_kernel<A, B, false>;
 }
 FinalizeFn pick_finalize(const bnv_mppi* h) {
-  const bool a = h->P.use_patch, b = h->P.geom.res_pow2, c = h->fast_angles;
+  const bool a = h->P.use_patch, b = h->P.geom.fast_grid, c = h->fast_angles;
   if (a) return b ? pick_finalize2<true, true>(c) : pick_finalize2<true, false>(c);
   return b ? pick_finalize2<false, true>(c) : pick_finalize2<false, false>(c);
 }
@@ -398,6 +398,7 @@ int bnv_mppi_set_problem_ex(bnv_mppi* h, const float* mean_dev, const float* std
   P.geom.res = resolution;
   P.geom.inv_res = 1.0f / resolution;
   P.geom.res_pow2 = is_pow2_float(resolution) ? 1 : 0;
+  P.geom.fast_grid = (P.geom.res_pow2 && x_min == 0.0f && y_min == 0.0f) ? 1 : 0;
   P.goal_x = P.term_gx = goals_xy[0];
   P.goal_y = P.term_gy = goals_xy[1];
   P.goals = E > 1 ? h->goals_dev : nullptr;

@@ -31,6 +31,9 @@ struct GridGeom {
   float x_min, y_min, x_max, y_max;
   float res, inv_res;
   int res_pow2;  // resolution is a power of two: (p - p_min) * inv_res == (p - p_min) / res exactly
+  int fast_grid; // ... and the map origin is (0, 0) (every GridMap built by grid_map.py:42-50): p - p_min == p, so the
+                 // biased cell coordinate is ONE round-down FMA, p * inv_res + magic (the product is exact) -- the
+                 // rollout kernels' kPow2 instantiations
 };
 struct Bounds {
   float u_min0, u_min1, u_max0, u_max1, dt;
@@ -85,18 +88,25 @@ __device__ __forceinline__ int cell_coord_rt(float p, float p_min, const GridGeo
 //
 // cell_ref(): where the cell's entry lives -- the shared-memory byte address (kPatch) or the element index in the
 // global table -- for entries of kElem bytes; two positions are in the same cell iff their cell_ref is equal.
+// kPow2 here means GridGeom::fast_grid (power-of-two resolution AND zero origin); otherwise true division.
 template <bool kPatch, bool kPow2, bool kMagic, uint32_t kElem>
 __device__ __forceinline__ uint32_t cell_ref(const StepConsts& c, float x, float y) {
   if (kMagic) {
-    float dx = __fsub_rn(x, c.x_min), dy = __fsub_rn(y, c.y_min);
-    float qx = kPow2 ? __fmul_rn(dx, c.inv_res) : __fdiv_rn(dx, c.res);
-    float qy = kPow2 ? __fmul_rn(dy, c.inv_res) : __fdiv_rn(dy, c.res);
-    int ix = min(max(__float_as_int(__fadd_rd(qx, kMagicFloat)), c.mlo_x), c.mhi_x);
-    int iy = min(max(__float_as_int(__fadd_rd(qy, kMagicFloat)), c.mlo_y), c.mhi_y);
+    float bx, by;  // floor((p - p_min) / res) + magic, rounded down
+    if (kPow2) {
+      bx = __fmaf_rd(x, c.inv_res, kMagicFloat);
+      by = __fmaf_rd(y, c.inv_res, kMagicFloat);
+    } else {
+      bx = __fadd_rd(__fdiv_rn(__fsub_rn(x, c.x_min), c.res), kMagicFloat);
+      by = __fadd_rd(__fdiv_rn(__fsub_rn(y, c.y_min), c.res), kMagicFloat);
+    }
+    int ix = min(max(__float_as_int(bx), c.mlo_x), c.mhi_x);
+    int iy = min(max(__float_as_int(by), c.mlo_y), c.mhi_y);
     if (kPatch)
       return c.mwin_addr + kElem * (static_cast<uint32_t>(iy) * static_cast<uint32_t>(c.pitch) + static_cast<uint32_t>(ix));
     return static_cast<uint32_t>((iy - kMagicBits) * c.pitch + (ix - kMagicBits));
   }
+  // general first lookup (position possibly outside the map): x - 0 == x, so kPow2 may keep the subtraction
   int ix = min(max(cell_coord<kPow2>(x, c.x_min, c.res, c.inv_res), c.lo_x), c.hi_x);
   int iy = min(max(cell_coord<kPow2>(y, c.y_min, c.res, c.inv_res), c.lo_y), c.hi_y);
   const uint32_t idx = static_cast<uint32_t>(iy * c.pitch + ix);
