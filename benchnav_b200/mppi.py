@@ -285,19 +285,34 @@ class MPPI(nn.Module):
 
     solve = forward  # north_star's name for the same call
 
-    def forward_host(self, state: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    def forward_host(self, state: torch.Tensor, out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
+                     ) -> Tuple[torch.Tensor, torch.Tensor]:
         """``forward`` for a HOST state, returning HOST tensors: the ABI's host-buffer form
-        (``bnv_mppi_forward_host``): H2D of the state, the iteration, D2H of both results, one sync."""
+        (``bnv_mppi_forward_host``): H2D of the state, the iteration, D2H of both results, one completion wait.
+
+        ``out = (u_opt [T,2], opt_states [1,T+1,3])``: optional caller-owned fp32 CPU tensors to write the results into
+        (as with the C ABI, where the caller owns every buffer); fresh tensors are allocated otherwise."""
+        if out is not None:
+            u_opt, opt_states = out
+            if not (u_opt.dtype == torch.float32 and opt_states.dtype == torch.float32 and u_opt.device.type == "cpu"
+                    and opt_states.device.type == "cpu" and u_opt.is_contiguous() and opt_states.is_contiguous()
+                    and u_opt.shape == (self._horizon, 2) and opt_states.shape == (1, self._horizon + 1, 3)):
+                raise ValueError("out must be contiguous fp32 CPU tensors of shapes [T,2] and [1,T+1,3]")
         if self._shard.world_size != 1 or self._noise_source != "philox":
-            out = self.forward(state)
-            return out[0].cpu(), out[1].cpu()
+            res = self.forward(state)
+            if out is not None:
+                u_opt.copy_(res[0])
+                opt_states.copy_(res[1])
+                return u_opt, opt_states
+            return res[0].cpu(), res[1].cpu()
         if not (torch.is_tensor(state) and state.dtype == torch.float32 and state.device.type == "cpu"
                 and state.is_contiguous()):
             state = torch.as_tensor(state, dtype=torch.float32).detach().cpu().contiguous()
         assert state.shape == (self._dim_state,)
         self._sync_problem()
-        u_opt = torch.empty(self._horizon, 2, dtype=torch.float32)
-        opt_states = torch.empty(1, self._horizon + 1, 3, dtype=torch.float32)
+        if out is None:
+            u_opt = torch.empty(self._horizon, 2, dtype=torch.float32)
+            opt_states = torch.empty(1, self._horizon + 1, 3, dtype=torch.float32)
         self._action_noises = self._engine_noise
         _cabi.check(self._lib.bnv_mppi_forward_host(self._handle, state.data_ptr(), None, u_opt.data_ptr(),
                                                     opt_states.data_ptr(), self._stream()))

@@ -1,4 +1,8 @@
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 scripts/multigpu_check.py 2>&1 | grep -v "^\[W\|^W1\|\*\*\*\*" | grep -E "it[0-9]|ok|Error|error|assert" | head -30
-for ex in p2p nccl; do timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 3000 --warmup 50 --exchange $ex 2>&1 | tail -1 | python -c "
+# two-GPU session: sharded-solver parity (NCCL + fused P2P exchange) and the N=2 bench lines for both exchange modes
+timeout 600 python -m pytest tests/test_multigpu_gpu.py -q -x 2>&1 | tail -3
+for ex in p2p nccl; do
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 3000 --warmup 50 --exchange $ex 2>/dev/null | tail -1 | python -c "
 import json,sys
-d=json.loads(sys.stdin.read()); print('$ex value',round(d['value']), 'ms/step',round(d['ms_per_step']*1e3,2),'us kernel_us',round(d['roofline']['kernel_us'],2),'b2b',round(d['config']['back_to_back_ms_per_step']*1e3,2), d['config']['parallelism'], 'launches', d['gpu_launches'])"; done
+d=json.loads(sys.stdin.read()); print('$ex', 'value',round(d['value']), 'us/step',round(d['ms_per_step']*1e3,2), d['config']['parallelism'])"
+done
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29534 bench.py --impl reference --gpus 2 --steps 3 --warmup 1 2>/dev/null | tail -1 | cut -c1-200

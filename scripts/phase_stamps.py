@@ -19,10 +19,12 @@ st = start.cuda()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 names = ["start", "loop0", "loop1", "partial", "last:enter", "last:merged", "last:u_out", "last:opt_done", "last:w_begin",
          "last:w_done", "last:exit", "m:fence", "m:ms_loaded", "m:M_sync", "m:S_sync", "m:fma_done"]
+INJECT = os.environ.get("BNV_STAMPS_INJECT") == "1"  # injected noise: the T-loop without the in-loop Philox draw
+nz = (torch.randn(K, T, 2, device="cuda") * 0.5) if INJECT else None
 for it in range(6):
     if it >= 3:
         flush.fill_(it)
-    s.forward(st)
+    s.forward(st, noise=nz)
     torch.cuda.synchronize()
     ts = (C.c_longlong * 16)()
     _cabi.check(s._lib.bnv_debug_timestamps(s._handle, ts))
