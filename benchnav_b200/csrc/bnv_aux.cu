@@ -149,7 +149,7 @@ int bnv_risk_map(int32_t metric, float confidence, int32_t method, const float* 
   int cpc = static_cast<int>(std::min<size_t>(32, (200 * 1024) / row_bytes));
   if (cpc < 1) return bnv_fail(BNV_ERR_UNSUPPORTED, "num_samples too large for shared memory");
   const size_t smem = cpc * row_bytes;
-  BNV_CUDA(cudaFuncSetAttribute(bnv::risk_mc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  BNV_CUDA(cudaFuncSetAttribute(bnv::risk_mc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   const long long ctas = (n_cells + cpc - 1) / cpc;
   if (ctas > 0x7FFFFFFFLL) return bnv_fail(BNV_ERR_UNSUPPORTED, "too many cells for one launch");
   bnv::risk_mc_kernel<<<static_cast<unsigned>(ctas), bnv::kRiskThreads, smem, s>>>(

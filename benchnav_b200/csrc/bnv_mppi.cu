@@ -182,29 +182,62 @@ FinalizeFn pick_finalize(const bnv_mppi* h) {
   return b ? pick_finalize2<false, true>(c) : pick_finalize2<false, false>(c);
 }
 
-// Choose warps per CTA so that noise + recorded-state slabs fit shared memory; prefer 4 (one per SM sub-partition).
-// Also sets the kernels' shared-memory attribute and asks the runtime how many CTAs can be resident at once
-// (short horizons leave room for several CTAs per SM): a grid within that bound is launched cooperatively.
+// Shared memory / occupancy of one candidate layout: sets the kernels' dynamic shared-memory attribute and returns
+// how many CTAs the device holds at once (min over the Philox / injected-noise instantiations), 0 if it does not fit.
+int layout_capacity(bnv_mppi* h, int w, int rec_split, size_t* smem_out, long long* cap_out) {
+  bnv::EngineParams& P = h->P;
+  bnv::RolloutSmem L = bnv::rollout_smem_layout(P.T, w, P.patch_w, P.patch_h, P.use_patch, P.record, h->stoch ? 2 : 1, rec_split);
+  *smem_out = L.total;
+  *cap_out = 0;
+  if (static_cast<size_t>(L.total) > kMaxDynSmem) return BNV_OK;
+  long long cap = 0;
+  for (bool philox : {false, true}) {
+    const void* fn = reinterpret_cast<const void*>(pick_rollout(h, philox));
+    // opt in to the full 220 KB once per kernel (a per-function limit, not a reservation): handles with different
+    // horizons share the instantiations, so the limit must never shrink under a live handle
+    BNV_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMaxDynSmem)));
+    int per_sm = 0;
+    BNV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, w * 32, L.total));
+    const long long c = static_cast<long long>(per_sm) * h->num_sms;
+    cap = philox ? std::min(cap, c) : c;
+  }
+  *cap_out = cap;
+  return BNV_OK;
+}
+
+// Choose warps per CTA so that noise + recorded-state slabs fit shared memory; prefer 4 (one per SM sub-partition),
+// and ask the runtime how many CTAs can be resident at once (short horizons leave room for several CTAs per SM): a
+// grid within that bound is launched cooperatively.
 int configure_launch(bnv_mppi* h) {
   bnv::EngineParams& P = h->P;
-  const int cell = h->stoch ? 2 : 1;
+  P.rec_split = 0;
   for (int w = bnv::kMaxWarps; w >= 1; w >>= 1) {
-    bnv::RolloutSmem L = bnv::rollout_smem_layout(P.T, w, P.patch_w, P.patch_h, P.use_patch, P.record, cell);
-    if (static_cast<size_t>(L.total) <= kMaxDynSmem) {
-      h->warps = w;
-      h->rollout_smem = L.total;
-      h->grid = (h->Kl + w * 32 - 1) / (w * 32);
-      h->resident_ctas = 0;
-      for (bool philox : {false, true}) {
-        const void* fn = reinterpret_cast<const void*>(pick_rollout(h, philox));
-        BNV_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h->rollout_smem)));
-        int per_sm = 0;
-        BNV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, w * 32, h->rollout_smem));
-        const long long cap = static_cast<long long>(per_sm) * h->num_sms;
-        h->resident_ctas = philox ? std::min(h->resident_ctas, cap) : cap;
+    size_t smem = 0;
+    long long cap = 0;
+    int rc = layout_capacity(h, w, 0, &smem, &cap);
+    if (rc != BNV_OK) return rc;
+    if (smem > kMaxDynSmem) continue;
+    h->warps = w;
+    h->grid = (h->Kl + w * 32 - 1) / (w * 32);
+    const long long total = static_cast<long long>(h->grid) * h->E;
+    // More CTAs than the device holds: flushing the recorded-state slab in two halves halves its footprint; adopt
+    // that layout when the whole grid then fits the device at once (K = 32768 at T = 50: two CTAs per SM, one wave).
+    const int tc = ((P.T + 1) / 2 + 1) & ~1;  // even split step, first half >= second half
+    if (P.record && total > cap && tc >= 2 && tc <= P.T - 2 && !(debug_disable() & 1024u)) {
+      size_t smem2 = 0;
+      long long cap2 = 0;
+      rc = layout_capacity(h, w, tc, &smem2, &cap2);
+      if (rc != BNV_OK) return rc;
+      if (cap2 >= total) {  // only when the launch becomes a single, co-resident wave (measured: 44.5 -> 37.8 us at
+                            // K = 32768; with several waves either way the extra flush costs what the occupancy gains)
+        P.rec_split = tc;
+        smem = smem2;
+        cap = cap2;
       }
-      return BNV_OK;
     }
+    h->rollout_smem = smem;
+    h->resident_ctas = cap;
+    return BNV_OK;
   }
   return fail(BNV_ERR_UNSUPPORTED, "horizon %d does not fit the rollout kernel's shared-memory staging", P.T);
 }
@@ -437,7 +470,7 @@ int bnv_mppi_set_problem_ex(bnv_mppi* h, const float* mean_dev, const float* std
   h->finalize_smem = 128 + (P.use_patch ? ((P.patch_w * P.patch_h + 31) / 32) * 32 * 4 : 0) + 2 * (2 * P.T + 4) * 4 + 16;
   if (!h->stoch && E == 1)
     BNV_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(pick_finalize(h)),
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h->finalize_smem)));
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMaxDynSmem)));
   h->problem_set = true;
   return BNV_OK;
 }

@@ -56,6 +56,9 @@ struct alignas(64) EngineParams {
   int use_patch;               // 0: window does not fit shared memory -> look up in the global map (L2)
   int world;                   // number of sample shards
   int record;                  // keep recorded states
+  int rec_split;               // 0, or the (even) step Tc at which the recorded-state slab is flushed mid-loop: the slab
+                               // then holds only max(Tc, T+1-Tc) slots per sample, which lets two CTAs share an SM when
+                               // a grid would otherwise need a second wave (K = 32768 at T = 50)
   int noise_bulk_ok, rec_bulk_ok;  // pointers 16 B aligned -> bulk copies allowed
   const float* state;   // [3] device-resident current state, or
   float state_val[3];   // ... the same three floats passed by value in the launch packet (state_inline != 0)
@@ -99,8 +102,11 @@ struct RolloutSmem {
 };
 constexpr int kMergeACap = 1024;    // fast grid merge: per-CTA rescale factors kept in shared memory
 constexpr int kMergeGrpCap = 1024;  // ... and ngrp x 2T partial column sums
+__host__ __device__ inline int rec_slab_slots(int T, int rec_split) {
+  return rec_split > 0 ? (rec_split > T + 1 - rec_split ? rec_split : T + 1 - rec_split) : T + 1;
+}
 __host__ __device__ inline RolloutSmem rollout_smem_layout(int T, int warps, int patch_w, int patch_h, int use_patch,
-                                                           int record, int cell_floats = 1) {
+                                                           int record, int cell_floats = 1, int rec_split = 0) {
   RolloutSmem s;
   int spb = warps * 32;
   int off = 128;  // [0,128): mbarriers (1 patch + kMaxWarps noise) and the last-CTA flag
@@ -109,7 +115,7 @@ __host__ __device__ inline RolloutSmem rollout_smem_layout(int T, int warps, int
   s.off_noise = off;
   off += ((spb * 2 * T * 4 + 127) / 128) * 128;
   s.off_rec = off;
-  off += record ? ((spb * 3 * (T + 1) * 4 + 127) / 128) * 128 : 0;
+  off += record ? ((spb * 3 * rec_slab_slots(T, rec_split) * 4 + 127) / 128) * 128 : 0;
   s.off_uprev = off;
   off += ((2 * T * 4 + 15) / 16) * 16;
   s.off_coef = off;
@@ -384,17 +390,31 @@ __device__ void finish_iteration(const EngineParams& P, const StepConsts& c, flo
 // Slabs -> HBM: recorded states (and the drawn noise), one bulk store per warp slab; asynchronous, the caller
 // waits for the shared-memory reads (bulk_wait_read_all) before the CTA exits.  rec_env / noise_env = this
 // environment's [Kl][T+1][3] / [Kl][T][2] arrays.
+// Coalesced warp copy of recorded-state slots [t0, t0 + nt) of `rows` samples from the slab (row stride `slab_slots`
+// slots, slot t0 at the row start) to HBM rows of T+1 slots: used when the slab is flushed in two halves (a half
+// row is not a 16-byte multiple, so it cannot go out as one bulk copy).  All 32 lanes participate.
+__device__ __forceinline__ void copy_rec_slots(float* rec_g, const float* rec_w, int rows, int T, int slab_slots, int t0,
+                                               int nt, int lane) {
+  const int n = 3 * nt;
+  for (int r = 0; r < rows; ++r) {
+    float* dst = rec_g + static_cast<size_t>(r) * 3 * (T + 1) + 3 * t0;
+    const float* src = rec_w + r * 3 * slab_slots;
+    for (int i = lane; i < n; i += 32) dst[i] = src[i];
+  }
+}
+
 template <bool kRecord, bool kPhilox>
 __device__ __forceinline__ void store_slabs(const EngineParams& P, float* rec_env, float* noise_env, float* rec_s,
                                             float* nz_w, int warp, int lane, int warp_first, int warp_rows,
                                             uint32_t nz_bytes) {
   if (warp_rows <= 0 || !(kRecord || kPhilox)) return;
   const int T = P.T;
+  const int slots = rec_slab_slots(T, P.rec_split);
   float* rec_g = rec_env + static_cast<size_t>(warp_first) * 3 * (T + 1);
   const uint32_t rec_bytes = static_cast<uint32_t>(warp_rows) * 3u * (T + 1) * 4u;
-  float* rec_w = rec_s + warp * 32 * 3 * (T + 1);
+  float* rec_w = rec_s + warp * 32 * 3 * slots;
   float* nz_g = noise_env + static_cast<size_t>(warp_first) * 2 * T;
-  const bool rec_bulk = kRecord && P.rec_bulk_ok && (rec_bytes & 15u) == 0u &&
+  const bool rec_bulk = kRecord && P.rec_split == 0 && P.rec_bulk_ok && (rec_bytes & 15u) == 0u &&
                         (reinterpret_cast<uintptr_t>(rec_g) & 15u) == 0u;
   const bool out_bulk = kPhilox && (nz_bytes & 15u) == 0u && (reinterpret_cast<uintptr_t>(nz_g) & 15u) == 0u;
   fence_proxy_async_smem();
@@ -404,8 +424,11 @@ __device__ __forceinline__ void store_slabs(const EngineParams& P, float* rec_en
     if (out_bulk) bulk_store_s2g(nz_g, nz_w, nz_bytes);
     bulk_commit();
   }
-  if (kRecord && !rec_bulk)
-    for (int i = lane; i < warp_rows * 3 * (T + 1); i += 32) rec_g[i] = rec_w[i];
+  if (kRecord && !rec_bulk) {
+    if (P.rec_split > 0) copy_rec_slots(rec_g, rec_w, warp_rows, T, slots, P.rec_split, T + 1 - P.rec_split, lane);
+    else
+      for (int i = lane; i < warp_rows * 3 * (T + 1); i += 32) rec_g[i] = rec_w[i];
+  }
   if (kPhilox && !out_bulk)
     for (int i = lane; i < warp_rows * 2 * T; i += 32) nz_g[i] = nz_w[i];
 }
@@ -495,7 +518,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
   const int nwarps = blockDim.x >> 5;
   const int spb = nwarps * 32;
   constexpr int kCell = kStoch ? 2 : 1;
-  const RolloutSmem L = rollout_smem_layout(T, nwarps, P.patch_w, P.patch_h, kPatch, kRecord, kCell);
+  const RolloutSmem L = rollout_smem_layout(T, nwarps, P.patch_w, P.patch_h, kPatch, kRecord, kCell, P.rec_split);
+  const int rec_slots = rec_slab_slots(T, P.rec_split);  // slots per sample in the recorded-state slab
   uint64_t* bar_patch = reinterpret_cast<uint64_t*>(smem);
   uint64_t* bar_noise = reinterpret_cast<uint64_t*>(smem) + 1;  // [kMaxWarps]
   int* last_flag = reinterpret_cast<int*>(smem + 64);
@@ -611,7 +635,25 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
   // ---- T-step rollout, one sample per thread
   float cost = FLT_MAX;
   float* nrow = nz_w + lane * 2 * T;
-  float* rrow = rec_s + (warp * 32 + lane) * 3 * (T + 1);
+  float* rrow = rec_s + (warp * 32 + lane) * 3 * rec_slots;
+  // mid-loop flush of the slab's first half (rec_split): coalesced by the whole warp when it is full, else (the one
+  // ragged warp of a launch) every lane writes its own row; afterwards slot t lives at rrow[3 (t - Tc)]
+  auto flush_first_half = [&]() {
+    if (kRecord) {
+      const int Tc = P.rec_split;
+      float* rec_g = rec_e + static_cast<size_t>(warp_first) * 3 * (T + 1);
+      if (warp_rows == 32) {
+        __syncwarp();
+        copy_rec_slots(rec_g, rec_s + warp * 32 * 3 * rec_slots, 32, T, rec_slots, 0, Tc, lane);
+        __syncwarp();
+      } else {
+        float* dst = rec_g + static_cast<size_t>(lane) * 3 * (T + 1);
+        for (int i = 0; i < 3 * Tc; ++i) dst[i] = rrow[i];
+      }
+      rrow -= 3 * Tc;
+    }
+  };
+  const int split_pair = (kRecord && P.rec_split > 0) ? (P.rec_split >> 1) : -1;
   if (valid) {
     SampleState s;
     s.x = sx; s.y = sy; s.th = sth; s.stage_sum = 0.0f; s.act0 = 0.0f; s.act1 = 0.0f;
@@ -660,6 +702,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
       sample_step<kPatch, kPow2, kRecord, false, kStoch>(s, C, 0, nz.x, nz.y, xq.x, xq.y, ucf_s, rrow);
       sample_step<kPatch, kPow2, kRecord, kFastAngles, kStoch>(s, C, 1, nz.z, nz.w, xq.z, xq.w, ucf_s, rrow);
       for (int p = 1; p < nfull; ++p) {
+        if (p == split_pair) flush_first_half();
         const float4 nq = fetch_pair(p);
         const float4 xp = fetch_xi(p);
         if (kPhilox) {
