@@ -701,16 +701,26 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
       }
       sample_step<kPatch, kPow2, kRecord, false, kStoch>(s, C, 0, nz.x, nz.y, xq.x, xq.y, ucf_s, rrow);
       sample_step<kPatch, kPow2, kRecord, kFastAngles, kStoch>(s, C, 1, nz.z, nz.w, xq.z, xq.w, ucf_s, rrow);
-      for (int p = 1; p < nfull; ++p) {
-        if (p == split_pair) flush_first_half();
-        const float4 nq = fetch_pair(p);
-        const float4 xp = fetch_xi(p);
-        if (kPhilox) {
-          *reinterpret_cast<float2*>(nrow + 4 * p) = make_float2(nq.x, nq.y);
-          *reinterpret_cast<float2*>(nrow + 4 * p + 2) = make_float2(nq.z, nq.w);
+      // The pair loop itself stays branch-free (the codegen of this loop is what the iteration's latency hangs
+      // on: a flush test inside it cost 50 cycles per step).  With a split slab it simply runs twice, around the flush.
+      auto run_pairs = [&](int p_begin, int p_end) {
+        for (int p = p_begin; p < p_end; ++p) {
+          const float4 nq = fetch_pair(p);
+          const float4 xp = fetch_xi(p);
+          if (kPhilox) {
+            *reinterpret_cast<float2*>(nrow + 4 * p) = make_float2(nq.x, nq.y);
+            *reinterpret_cast<float2*>(nrow + 4 * p + 2) = make_float2(nq.z, nq.w);
+          }
+          sample_step<kPatch, kPow2, kRecord, kFastAngles, kStoch>(s, C, 2 * p, nq.x, nq.y, xp.x, xp.y, ucf_s, rrow);
+          sample_step<kPatch, kPow2, kRecord, kFastAngles, kStoch>(s, C, 2 * p + 1, nq.z, nq.w, xp.z, xp.w, ucf_s, rrow);
         }
-        sample_step<kPatch, kPow2, kRecord, kFastAngles, kStoch>(s, C, 2 * p, nq.x, nq.y, xp.x, xp.y, ucf_s, rrow);
-        sample_step<kPatch, kPow2, kRecord, kFastAngles, kStoch>(s, C, 2 * p + 1, nq.z, nq.w, xp.z, xp.w, ucf_s, rrow);
+      };
+      if (split_pair < 0) {
+        run_pairs(1, nfull);
+      } else {
+        run_pairs(1, split_pair);
+        flush_first_half();
+        run_pairs(split_pair, nfull);
       }
     }
     if (T & 1) {  // last (or only) step of an odd horizon: first half of pair nfull
