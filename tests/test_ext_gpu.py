@@ -381,3 +381,18 @@ def test_closed_loop_planner_and_environment_follow_the_oracle():
             ref_uprev[e] = ref["u_opt"]
     moved = (env._robot_state[:, :2].cpu() - states0[:, :2]).norm(dim=1)
     assert float(moved.min()) > 0.2  # the robots actually drive
+
+
+def test_closed_loop_example_reaches_the_goals():
+    """examples/closed_loop.py: eight environments driven to their goals by the batched planner (the functional
+    outcome of Tutorial 3.3's loop)."""
+    import importlib.util
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "closed_loop.py")
+    spec = importlib.util.spec_from_file_location("closed_loop_example", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    steps, dist = mod.run(envs=8, samples=2048, horizon=30, max_steps=900, verbose=False)
+    assert int((steps > 0).sum()) >= 7, (steps.tolist(), dist.tolist())  # every robot (one straggler tolerated) arrives
+    assert float(dist.min()) < 1.0
