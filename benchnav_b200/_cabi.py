@@ -93,6 +93,7 @@ _SIGNATURES = {
     "bnv_mppi_reset": (C.c_int, [_VP, _VP]),
     "bnv_mppi_draw_noise": (C.c_int, [_VP, C.c_uint64, _VP]),
     "bnv_mppi_draw_xi": (C.c_int, [_VP, C.c_uint64, _VP, _VP, _VP]),
+    "bnv_mppi_device_counter": (C.c_int, [_VP, C.c_int32, _VP]),
     "bnv_mppi_set_keep_mean": (C.c_int, [_VP, C.c_int32]),
     "bnv_mppi_set_terminal_goal": (C.c_int, [_VP, _FP]),
     "bnv_mppi_set_goal_dev": (C.c_int, [_VP, _VP]),
@@ -105,9 +106,9 @@ _SIGNATURES = {
     "bnv_debug_timestamps": (C.c_int, [_VP, C.POINTER(C.c_longlong)]),
     "bnv_debug_sincos": (C.c_int, [_VP, _VP, _VP, C.c_int32, _VP]),
     "bnv_trav_lookup": (C.c_int, [C.POINTER(Grid), _VP, _VP, C.c_int64, C.c_int64, _VP, C.c_int64, C.c_int32, _VP,
-                                  C.c_uint64, C.c_uint64, C.c_float, _VP, _VP, _VP]),
+                                  C.c_uint64, C.c_uint64, _VP, C.c_float, _VP, _VP, _VP]),
     "bnv_env_step": (C.c_int, [C.POINTER(Grid), _VP, _VP, C.c_int64, C.c_int32, _VP, _VP, _VP, _VP, C.c_uint64,
-                               C.c_uint64, _FP, _FP, C.c_float, C.c_float, _VP, _VP, _VP]),
+                               C.c_uint64, _VP, _FP, _FP, C.c_float, C.c_float, _VP, _VP, _VP]),
     "bnv_risk_map": (C.c_int, [C.c_int32, C.c_float, C.c_int32, _VP, _VP, C.c_int64, _VP, C.c_int32, C.c_uint64, _VP,
                                _VP, _VP]),
     "bnv_dwa_actions": (C.c_int, [_VP, _FP, _FP, _FP, C.c_float, C.c_int32, C.c_int32, C.c_int32, _VP, _VP, _VP]),

@@ -128,6 +128,12 @@ class BatchedMPPI(nn.Module):
     def reset(self) -> None:
         _cabi.check(self._lib.bnv_mppi_reset(self._handle, self._stream()))
 
+    def graph_capturable(self, enable: bool = True) -> None:
+        """Keep the iteration counter (Philox counter word, launch epoch) in device memory so that ``forward`` can be
+        captured in a CUDA graph (``torch.cuda.graph``) and replayed: one graph launch per control step."""
+        with torch.cuda.device(self._device):
+            _cabi.check(self._lib.bnv_mppi_device_counter(self._handle, 1 if enable else 0, self._stream()))
+
     @property
     def launch_count(self) -> int:
         return int(self._lib.bnv_mppi_launch_count(self._handle))

@@ -49,11 +49,14 @@ __global__ void __launch_bounds__(256) trav_lookup_kernel(GridGeom geom, int G, 
                                                           long long env_stride, long long env_rows,
                                                           const float* __restrict__ pos, long long n, int pos_stride,
                                                           const float* __restrict__ xi, uint32_t seed_lo,
-                                                          uint32_t seed_hi, uint32_t ctr_lo, uint32_t ctr_hi, float thr,
+                                                          uint32_t seed_hi, unsigned long long ctr,
+                                                          const unsigned long long* __restrict__ ctr_dev, float thr,
                                                           float* __restrict__ trav_out,
                                                           unsigned char* __restrict__ stuck_out) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (ctr_dev != nullptr) ctr += *ctr_dev;  // device-resident draw counter (graph-capturable callers)
+  const uint32_t ctr_lo = static_cast<uint32_t>(ctr), ctr_hi = static_cast<uint32_t>(ctr >> 32);
   const float x = pos[i * pos_stride], y = pos[i * pos_stride + 1];
   const size_t cell = static_cast<size_t>(cell_of(geom, G, pitch, x, y)) +
                       (env_rows > 0 ? static_cast<size_t>(i / env_rows) * env_stride : 0);
@@ -82,11 +85,14 @@ __global__ void __launch_bounds__(128) env_step_kernel(GridGeom geom, int G, con
                                                        int E, float* __restrict__ states,
                                                        const float* __restrict__ actions,
                                                        const float* __restrict__ goals, const float* __restrict__ xi,
-                                                       uint32_t seed_lo, uint32_t seed_hi, uint32_t ctr_lo,
-                                                       uint32_t ctr_hi, Bounds b, float goal_threshold,
-                                                       float* __restrict__ reward, unsigned char* __restrict__ terminated) {
+                                                       uint32_t seed_lo, uint32_t seed_hi, unsigned long long ctr,
+                                                       const unsigned long long* __restrict__ ctr_dev, Bounds b,
+                                                       float goal_threshold, float* __restrict__ reward,
+                                                       unsigned char* __restrict__ terminated) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= E) return;
+  if (ctr_dev != nullptr) ctr += *ctr_dev;  // device-resident draw counter (graph-capturable callers)
+  const uint32_t ctr_lo = static_cast<uint32_t>(ctr), ctr_hi = static_cast<uint32_t>(ctr >> 32);
   float x = states[3 * e], y = states[3 * e + 1], th = states[3 * e + 2];
   const size_t cell = static_cast<size_t>(cell_of(geom, G, pitch, x, y)) + static_cast<size_t>(e) * env_stride;
   const float z = xi ? xi[e] : aux_normal(static_cast<uint32_t>(e), kStreamEnvStep, ctr_lo, ctr_hi, make_uint2(seed_lo, seed_hi));

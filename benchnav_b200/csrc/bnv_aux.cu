@@ -77,8 +77,8 @@ extern "C" {
 
 int bnv_trav_lookup(const bnv_grid* grid, const float* mean_dev, const float* std_dev, int64_t env_stride,
                     int64_t rows_per_env, const float* pos_dev, int64_t n, int32_t pos_stride, const float* xi_dev,
-                    uint64_t seed, uint64_t counter, float stuck_threshold, float* trav_out_dev,
-                    uint8_t* stuck_out_dev, void* stream) {
+                    uint64_t seed, uint64_t counter, const uint64_t* counter_dev, float stuck_threshold,
+                    float* trav_out_dev, uint8_t* stuck_out_dev, void* stream) {
   bnv::GridGeom geom;
   int rc = make_geom(grid, &geom);
   if (rc != BNV_OK) return rc;
@@ -89,16 +89,17 @@ int bnv_trav_lookup(const bnv_grid* grid, const float* mean_dev, const float* st
   if (blocks > 0x7FFFFFFFLL) return bnv_fail(BNV_ERR_UNSUPPORTED, "too many positions for one launch");
   bnv::trav_lookup_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       geom, grid->grid_size, mean_dev, std_dev, grid->pitch, env_stride, rows_per_env, pos_dev, n, pos_stride, xi_dev,
-      static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), static_cast<uint32_t>(counter),
-      static_cast<uint32_t>(counter >> 32), stuck_threshold, trav_out_dev, stuck_out_dev);
+      static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), static_cast<unsigned long long>(counter),
+      reinterpret_cast<const unsigned long long*>(counter_dev), stuck_threshold, trav_out_dev, stuck_out_dev);
   BNV_CUDA(cudaGetLastError());
   return BNV_OK;
 }
 
 int bnv_env_step(const bnv_grid* grid, const float* mean_dev, const float* std_dev, int64_t env_stride,
                  int32_t num_envs, float* states_dev, const float* actions_dev, const float* goals_dev,
-                 const float* xi_dev, uint64_t seed, uint64_t counter, const float u_min[2], const float u_max[2],
-                 float delta_t, float goal_threshold, float* reward_out_dev, uint8_t* terminated_out_dev, void* stream) {
+                 const float* xi_dev, uint64_t seed, uint64_t counter, const uint64_t* counter_dev, const float u_min[2],
+                 const float u_max[2], float delta_t, float goal_threshold, float* reward_out_dev,
+                 uint8_t* terminated_out_dev, void* stream) {
   bnv::GridGeom geom;
   int rc = make_geom(grid, &geom);
   if (rc != BNV_OK) return rc;
@@ -109,8 +110,8 @@ int bnv_env_step(const bnv_grid* grid, const float* mean_dev, const float* std_d
   bnv::Bounds b{u_min[0], u_min[1], u_max[0], u_max[1], delta_t};
   bnv::env_step_kernel<<<(num_envs + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
       geom, grid->grid_size, mean_dev, std_dev, grid->pitch, env_stride, num_envs, states_dev, actions_dev, goals_dev,
-      xi_dev, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), static_cast<uint32_t>(counter),
-      static_cast<uint32_t>(counter >> 32), b, goal_threshold, reward_out_dev, terminated_out_dev);
+      xi_dev, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), static_cast<unsigned long long>(counter),
+      reinterpret_cast<const unsigned long long*>(counter_dev), b, goal_threshold, reward_out_dev, terminated_out_dev);
   BNV_CUDA(cudaGetLastError());
   return BNV_OK;
 }

@@ -110,6 +110,7 @@ struct bnv_mppi {
   size_t top_pairs_cap = 0, top_idx_cap = 0;
   float* io_host = nullptr;  // pinned mirror of io_dev
   float* io_host_dev = nullptr;  // its device-side address (zero-copy)
+  unsigned long long* iter_dev = nullptr;  // device-resident iteration counter (graph-capturable launches)
   int grid = 0, warps = 0;
   long long resident_ctas = 0;  // how many rollout CTAs the device can hold at once (cooperative-launch bound)
   bool fast_angles = false;
@@ -125,6 +126,7 @@ namespace {
 void free_all(bnv_mppi* h) {
   cudaFree(h->tau);
   cudaFree(h->goals_dev);
+  cudaFree(h->iter_dev);
   cudaFree(h->noise);
   cudaFree(h->rec);
   cudaFree(h->costs);
@@ -343,6 +345,7 @@ int bnv_mppi_create(bnv_mppi** out, const bnv_mppi_cfg* cfg) {
   P.goals = nullptr;
   P.keep_mean = 1;
   P.done_flag = nullptr;
+  P.iter_dev = nullptr;
   P.xi_in = nullptr;
   P.xi_opt_in = nullptr;
   P.Kl = Kl;
@@ -530,7 +533,13 @@ static int launch_forward(bnv_mppi* h, const float* state_dev, const float* stat
     h->ev_used += 2;
   }
   h->launches++;
-  if (philox) h->iteration++;
+  if (h->iter_dev) {  // the counter advances on the device, in stream order (and on every replay of a captured graph)
+    bnv::bump_iteration_kernel<<<1, 1, 0, s>>>(h->iter_dev);
+    BNV_CUDA(cudaGetLastError());
+    h->launches++;
+  } else if (philox) {
+    h->iteration++;
+  }
   h->have_weights = (P.world == 1) || h->peers_attached;
   return BNV_OK;
 }
@@ -726,6 +735,7 @@ int bnv_mppi_reset(bnv_mppi* h, void* stream) {
   BNV_CUDA(cudaSetDevice(h->cfg.device));
   BNV_CUDA(cudaMemsetAsync(h->u_prev, 0, sizeof(float) * h->E * h->P.T * 2, static_cast<cudaStream_t>(stream)));
   h->iteration = 0;
+  if (h->iter_dev) BNV_CUDA(cudaMemsetAsync(h->iter_dev, 0, sizeof(unsigned long long), static_cast<cudaStream_t>(stream)));
   h->have_weights = false;
   return BNV_OK;
 }
@@ -756,6 +766,30 @@ int bnv_mppi_draw_xi(bnv_mppi* h, uint64_t iteration, float* xi_out_dev, float* 
       static_cast<uint32_t>(h->cfg.seed >> 32), static_cast<uint32_t>(iteration), static_cast<uint32_t>(iteration >> 32));
   BNV_CUDA(cudaGetLastError());
   h->launches++;
+  return BNV_OK;
+}
+
+int bnv_mppi_device_counter(bnv_mppi* h, int32_t enable, void* stream) {
+  if (!h) return fail(BNV_ERR_INVALID, "null argument");
+  if (h->cfg.world_size != 1) return fail(BNV_ERR_INVALID, "graph-capturable launches need world_size == 1");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  BNV_CUDA(cudaSetDevice(h->cfg.device));
+  if (enable) {
+    if (!h->iter_dev) BNV_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->iter_dev), sizeof(unsigned long long)));
+    const unsigned long long it = h->iteration;
+    BNV_CUDA(cudaMemcpyAsync(h->iter_dev, &it, sizeof(it), cudaMemcpyHostToDevice, s));
+    // the "merge done" flags hold by-value epochs of earlier launches: clear them (0 is never a valid epoch)
+    BNV_CUDA(cudaMemsetAsync(h->ticket, 0, 2 * static_cast<size_t>(h->E) * sizeof(unsigned int), s));
+    BNV_CUDA(cudaStreamSynchronize(s));
+    h->P.iter_dev = h->iter_dev;
+  } else if (h->iter_dev && h->P.iter_dev) {
+    BNV_CUDA(cudaMemsetAsync(h->ticket, 0, 2 * static_cast<size_t>(h->E) * sizeof(unsigned int), s));
+    unsigned long long it = 0;
+    BNV_CUDA(cudaMemcpyAsync(&it, h->iter_dev, sizeof(it), cudaMemcpyDeviceToHost, s));
+    BNV_CUDA(cudaStreamSynchronize(s));
+    h->iteration = it;
+    h->P.iter_dev = nullptr;
+  }
   return BNV_OK;
 }
 

@@ -75,6 +75,9 @@ struct alignas(64) EngineParams {
   unsigned int* ticket;  // [0] arrival counter of the last-CTA election, [1] "merge done" epoch flag (coop)
   float* stats;          // [2] (M, S) of the last merge, published to the waiting CTAs (coop)
   unsigned int epoch;    // unique per launch
+  const unsigned long long* iter_dev;  // graph-capturable launches: the iteration counter lives in device memory (the
+                                       // launch packet of a captured graph is frozen); then iteration = *iter_dev,
+                                       // epoch = low word + 1, and bump_iteration_kernel advances it after the launch
   unsigned int* done_flag;  // optional, mapped HOST memory: set to `epoch` once u_out / opt_rec are complete, so that a
                             // host thread polling it sees the results without waiting for the kernel's tail
   int keep_mean;         // write u* back as the next call's mean sequence (mppi.py:217); 0 for DWA's constant actions
@@ -181,6 +184,9 @@ __global__ void __launch_bounds__(256) noise_kernel(float* __restrict__ noise, i
   *reinterpret_cast<float2*>(dst) = make_float2(n.x, n.y);
   if (2 * p + 1 < T) *reinterpret_cast<float2*>(dst + 2) = make_float2(n.z, n.w);
 }
+
+// Graph-capturable launches: advance the device-resident iteration counter after the rollout kernel.
+__global__ void bump_iteration_kernel(unsigned long long* iter_dev) { *iter_dev += 1ull; }
 
 // Stand-alone draw of the stochastic mode's lookup normals (same xi_quad() calls as the rollout kernel):
 // xi [E][Kl][2T+1] = (transit 0, stage 0, transit 1, stage 1, ..., terminal), xi_opt [E][T] for the optimal rollout.
@@ -545,7 +551,19 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
   float* const part_u_e = P.part_u + eB * 2 * T;
   unsigned int* const ticket_e = P.ticket + 2 * env;  // [0] arrival counter, [1] "merge done" epoch flag
   float* const stats_e = P.stats + 2 * env;
-  const uint32_t iter_hi_e = P.iter_hi + (static_cast<uint32_t>(env) << 16);  // Philox counter word 3 carries the env
+  // iteration counter and launch epoch: by value, or from device memory when the launch is replayed from a CUDA graph
+  uint32_t iter_lo = P.iter_lo, iter_hi = P.iter_hi, epoch = P.epoch;
+  if (P.iter_dev != nullptr) {
+    const unsigned long long it = __ldcg(P.iter_dev);
+    iter_lo = static_cast<uint32_t>(it);
+    iter_hi = static_cast<uint32_t>(it >> 32);
+    // epoch = it mod (2^32 - 1) + 1: never 0, and different for consecutive iterations for ever (2^32 = 1 mod 2^32 - 1)
+    unsigned long long f = (it >> 32) + (it & 0xFFFFFFFFull);
+    f = (f >> 32) + (f & 0xFFFFFFFFull);
+    if (f >= 0xFFFFFFFFull) f -= 0xFFFFFFFFull;
+    epoch = static_cast<uint32_t>(f) + 1u;
+  }
+  const uint32_t iter_hi_e = iter_hi + (static_cast<uint32_t>(env) << 16);  // Philox counter word 3 carries the env
 
   const int cta_first = blockIdx.x * spb;
   const int warp_first = cta_first + warp * 32;
@@ -609,8 +627,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
   float sig0 = P.sigma0, sig1 = P.sigma1;
   float4 nz_cur = make_float4(0.f, 0.f, 0.f, 0.f);
   float4 xi_cur = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (kPhilox) nz_cur = noise_pair(kg, 0u, P.iter_lo, iter_hi_e, key, sig0, sig1);
-  if (kPhilox && kStoch) xi_cur = xi_quad(kg, 0u, P.iter_lo, iter_hi_e, key);
+  if (kPhilox) nz_cur = noise_pair(kg, 0u, iter_lo, iter_hi_e, key, sig0, sig1);
+  if (kPhilox && kStoch) xi_cur = xi_quad(kg, 0u, iter_lo, iter_hi_e, key);
 
   // mean sequence and the per-step action-cost coefficients u_prev[t] Sigma^-1 (mppi.py:178-181)
   for (int i = tid; i < 2 * T; i += blockDim.x) {
@@ -672,7 +690,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
       float4 nz;
       if (kPhilox) {
         nz = nz_cur;
-        nz_cur = noise_pair(kg, static_cast<uint32_t>(p + 1), P.iter_lo, iter_hi_e, key, sig0, sig1);
+        nz_cur = noise_pair(kg, static_cast<uint32_t>(p + 1), iter_lo, iter_hi_e, key, sig0, sig1);
       } else {
         const float2 a = *reinterpret_cast<const float2*>(nrow + 4 * p);
         const float2 b = *reinterpret_cast<const float2*>(nrow + 4 * p + 2);
@@ -685,7 +703,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
       if (kStoch) {
         if (kPhilox) {
           xq = xi_cur;
-          xi_cur = xi_quad(kg, static_cast<uint32_t>(p + 1), P.iter_lo, iter_hi_e, key);
+          xi_cur = xi_quad(kg, static_cast<uint32_t>(p + 1), iter_lo, iter_hi_e, key);
         } else {
           xq = make_float4(__ldg(xrow + 4 * p), __ldg(xrow + 4 * p + 1), __ldg(xrow + 4 * p + 2), __ldg(xrow + 4 * p + 3));
         }
@@ -745,7 +763,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
     // terminal cost (mppi.py:184; objectives.py:65): same cell as the last stage cost, its own draw when stochastic
     float tau_term = s.tau;
     if (kStoch) {
-      const float xt = kPhilox ? xi_quad(kg, kXiTerminalPair, P.iter_lo, iter_hi_e, key).x : __ldg(xrow + 2 * T);
+      const float xt = kPhilox ? xi_quad(kg, kXiTerminalPair, iter_lo, iter_hi_e, key).x : __ldg(xrow + 2 * T);
       tau_term = slip_to_trav(s.ms, xt);
     }
     const float terminal = goal_and_stuck_cost_at(C, term_gx, term_gy, s.x, s.y, tau_term);
@@ -981,7 +999,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
     if (coop && tid == 0) {  // publish (M, S) and release the waiting CTAs as early as possible
       stats_e[0] = M;
       stats_e[1] = S;
-      st_release_gpu(ticket_e + 1, P.epoch);
+      st_release_gpu(ticket_e + 1, epoch);
     }
     if (complete) {
       float* u_out_e = P.u_out + static_cast<size_t>(env) * ncol;
@@ -1011,7 +1029,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
       auto scale_of = [&](int g) { return fast_merge ? a_s[g] : __expf(__ldcg(part_ms_e + 2 * g) - m_shard); };
       if (complete && tid == 0) {
         const XiSource xs{(kStoch && !kPhilox) ? P.xi_opt_in + static_cast<size_t>(env) * T : nullptr, kOptimalSample,
-                          P.iter_lo, iter_hi_e, key};
+                          iter_lo, iter_hi_e, key};
         optimal_rollout<kPatch, kPow2, kFastAngles, kStoch>(T, C, warpu_s, sx, sy, sth,
                                                             P.opt_rec + static_cast<size_t>(env) * 3 * (T + 1), xs);
         signal_done(P);
@@ -1027,7 +1045,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
   } else if (coop) {
     // wait for the last CTA's merge (all CTAs are co-resident: cooperative launch), then pick up (M, S)
     if (tid == 0) {
-      while (ld_acquire_gpu(ticket_e + 1) != P.epoch) __nanosleep(32);
+      while (ld_acquire_gpu(ticket_e + 1) != epoch) __nanosleep(32);
     }
     __syncthreads();
     M = __ldcg(stats_e);
@@ -1040,7 +1058,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
     store_slabs<kRecord, kPhilox>(P, rec_e, noise_out_e, rec_s, nz_w, warp, lane, warp_first, warp_rows, nz_bytes);
     if (is_last && complete && tid == 0) {
       const XiSource xs{(kStoch && !kPhilox) ? P.xi_opt_in + static_cast<size_t>(env) * T : nullptr, kOptimalSample,
-                        P.iter_lo, iter_hi_e, key};
+                        iter_lo, iter_hi_e, key};
       optimal_rollout<kPatch, kPow2, kFastAngles, kStoch>(T, C, warpu_s, sx, sy, sth,
                                                           P.opt_rec + static_cast<size_t>(env) * 3 * (T + 1), xs);
       signal_done(P);

@@ -61,7 +61,7 @@ def traversability(grid_map, states: torch.Tensor, *, mean: torch.Tensor, std: O
     grid = _grid_of(grid_map, mean.stride(0))
     with torch.cuda.device(dev):
         _cabi.check(lib.bnv_trav_lookup(C.byref(grid), mean.data_ptr(), std_ptr, 0, 0, pos.data_ptr(), n, stride, xi_ptr,
-                                        int(seed), int(counter), float(stuck_threshold or 0.0), trav.data_ptr(),
+                                        int(seed), int(counter), None, float(stuck_threshold or 0.0), trav.data_ptr(),
                                         stuck.data_ptr() if stuck is not None else None,
                                         torch.cuda.current_stream(dev).cuda_stream))
     return (trav, stuck) if stuck is not None else trav
@@ -86,7 +86,8 @@ class BatchedPlanetaryEnv:
 
     def __init__(self, grid_maps, start_pos: torch.Tensor, goal_pos: torch.Tensor, delta_t: float = 0.1,
                  time_limit: float = 100, stuck_threshold: float = 0.1, goal_threshold: float = 1.0, seed: int = 0,
-                 device=torch.device("cuda"), min_action=(0.0, -1.0), max_action=(1.0, 1.0)) -> None:
+                 device=torch.device("cuda"), min_action=(0.0, -1.0), max_action=(1.0, 1.0),
+                 graph_capturable: bool = False) -> None:
         dev = torch.device(device)
         if dev.type != "cuda" or not torch.cuda.is_available():
             raise RuntimeError("benchnav_b200.BatchedPlanetaryEnv runs on CUDA (sm_100a) only; there is no CPU fallback")
@@ -107,6 +108,9 @@ class BatchedPlanetaryEnv:
         self._delta_t, self._time_limit = float(delta_t), time_limit
         self.stuck_threshold, self._goal_threshold = stuck_threshold, float(goal_threshold)
         self._seed, self._counter = int(seed), 0
+        # graph_capturable: the draw counter lives in device memory and is advanced by a (capturable) in-place add, so a
+        # captured step()/collision_check() draws fresh normals on every replay of the graph
+        self._counter_dev = torch.zeros(1, dtype=torch.int64, device=dev) if graph_capturable else None
         self._u_min = (C.c_float * 2)(*min_action)
         self._u_max = (C.c_float * 2)(*max_action)
         assert tuple(start_pos.shape) == (E, 2) and tuple(goal_pos.shape) == (E, 2)
@@ -124,6 +128,8 @@ class BatchedPlanetaryEnv:
         if seed is not None:
             self._seed = int(seed)
         self._counter, self._elapsed_time = 0, 0
+        if self._counter_dev is not None:
+            self._counter_dev.zero_()
         self._robot_state = self._initial_state()
         self._reward.fill_(float("nan"))
         return self._robot_state
@@ -142,9 +148,11 @@ class BatchedPlanetaryEnv:
             _cabi.check(self._lib.bnv_env_step(
                 C.byref(self._grid), self._mean.data_ptr(), self._std.data_ptr(), self._mean.stride(0), E,
                 self._robot_state.data_ptr(), actions.data_ptr(), self._goal_pos.data_ptr(), xi_ptr, self._seed,
-                self._counter, self._u_min, self._u_max, self._delta_t, self._goal_threshold,
-                self._reward.data_ptr(), self._terminated.data_ptr(), torch.cuda.current_stream(self._device).cuda_stream))
-        self._counter += 1
+                0 if self._counter_dev is not None else self._counter,
+                self._counter_dev.data_ptr() if self._counter_dev is not None else None, self._u_min, self._u_max,
+                self._delta_t, self._goal_threshold, self._reward.data_ptr(), self._terminated.data_ptr(),
+                torch.cuda.current_stream(self._device).cuda_stream))
+        self._advance_counter()
         self._elapsed_time += self._delta_t  # planetary_env.py:210
         self._keepalive = (actions, xi)
         return self._robot_state, self._reward, self._terminated.bool(), self._elapsed_time > self._time_limit
@@ -163,7 +171,14 @@ class BatchedPlanetaryEnv:
         with torch.cuda.device(self._device):
             _cabi.check(self._lib.bnv_trav_lookup(
                 C.byref(self._grid), self._mean.data_ptr(), self._std.data_ptr(), self._mean.stride(0), rows,
-                pos.data_ptr(), n, pos.shape[-1], xi_ptr, self._seed, (1 << 40) + self._counter,
+                pos.data_ptr(), n, pos.shape[-1], xi_ptr, self._seed,
+                (1 << 40) + (0 if self._counter_dev is not None else self._counter),
+                self._counter_dev.data_ptr() if self._counter_dev is not None else None,
                 float(self.stuck_threshold), None, stuck.data_ptr(), torch.cuda.current_stream(self._device).cuda_stream))
-        self._counter += 1
+        self._advance_counter()
         return stuck.bool()
+
+    def _advance_counter(self) -> None:
+        self._counter += 1
+        if self._counter_dev is not None:
+            self._counter_dev += 1

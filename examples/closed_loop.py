@@ -49,37 +49,65 @@ def build(envs: int, grid: int = 128, resolution: float = 0.5, slip_scale: float
     return dyns, objs, gms, start, goal
 
 
-def run(envs: int = 8, samples: int = 4096, horizon: int = 30, max_steps: int = 900, seed: int = 0, verbose: bool = True):
+def run(envs: int = 8, samples: int = 4096, horizon: int = 30, max_steps: int = 900, seed: int = 0, verbose: bool = True,
+        use_graph: bool = True):
+    """Drive every environment to its goal.  `use_graph`: capture ONE control step (planner launch, environment launch,
+    collision check and the bookkeeping around them) in a CUDA graph and replay it -- one graph launch per control
+    step instead of ~15 host-issued launches."""
     dev = torch.device("cuda")
     dyns, objs, gms, start, goal = build(envs)
     planner = BatchedMPPI(horizon, samples, dyns, objs, torch.tensor([0.5, 0.5]), 0.5, device=dev, seed=seed)
     env = BatchedPlanetaryEnv(gms, start, goal, delta_t=0.1, time_limit=100, stuck_threshold=0.1, goal_threshold=1.0,
-                              seed=seed, device=dev)
-    state = env.reset(seed=seed)
+                              seed=seed, device=dev, graph_capturable=use_graph)
+    state = env.reset(seed=seed)  # updated in place by env.step: the graph's static input
     done = torch.zeros(envs, dtype=torch.bool, device=dev)
     steps_to_goal = torch.full((envs,), -1, dtype=torch.long, device=dev)
+    step_no = torch.zeros((), dtype=torch.long, device=dev)
     zero = torch.zeros(envs, 2, device=dev)
-    t0 = time.perf_counter()
-    for step in range(max_steps):
+    collisions = torch.zeros(envs, horizon + 1, dtype=torch.bool, device=dev)
+
+    def control_step():
         actions, state_seqs = planner.forward(state)                       # [E,T,2], [E,1,T+1,3]
         a0 = torch.where(done.unsqueeze(1), zero, actions[:, 0, :])        # arrived robots stop
-        state, reward, terminated, truncated = env.step(a0)
-        collisions = env.collision_check(state_seqs[:, 0])                 # [E,T+1] on the planned trajectory
-        steps_to_goal = torch.where(terminated & ~done, step + 1, steps_to_goal)  # no host sync in the loop
-        done |= terminated
-        if step % 50 == 49 or truncated:
-            if bool(done.all()) or truncated:  # one host sync every 50 steps
-                break
+        _, _, terminated, _ = env.step(a0)
+        collisions.copy_(env.collision_check(state_seqs[:, 0]))            # [E,T+1] on the planned trajectory
+        step_no.add_(1)
+        steps_to_goal.copy_(torch.where(terminated & ~done, step_no, steps_to_goal))  # no host sync in the loop
+        done.logical_or_(terminated)
+
+    graph = None
+    if use_graph:
+        planner.graph_capturable(True)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            control_step()  # warm-up outside the capture (allocator, lazy module loads)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                control_step()
+        torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    n_steps = 0
+    for step in range(max_steps):
+        if graph is not None:
+            graph.replay()
+        else:
+            control_step()
+        n_steps += 1
+        if step % 50 == 49 and bool(done.all()):  # one host sync every 50 steps
+            break
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     top_states, top_weights = planner.get_top_samples(min(100, samples))
+    dist = (state[:, :2] - goal.to(dev)).norm(dim=1)
     if verbose:
-        print(f"{envs} environments, K={samples}, T={horizon}: {step + 1} control steps in {wall * 1e3:.1f} ms "
-              f"({wall / (step + 1) * 1e6:.1f} us per step of all environments)")
+        print(f"{envs} environments, K={samples}, T={horizon}, {'CUDA graph' if graph is not None else 'host-issued launches'}: "
+              f"{n_steps} control steps in {wall * 1e3:.1f} ms ({wall / n_steps * 1e6:.1f} us per step of all environments)")
         print("steps to goal per environment:", steps_to_goal.tolist())
-        print("final distance to goal [m]:", [round(float(x), 2) for x in (state[:, :2] - goal.to(dev)).norm(dim=1)])
+        print("final distance to goal [m]:", [round(float(x), 2) for x in dist])
         print("planned-trajectory collisions flagged at the last step:", int(collisions.sum()))
-    return steps_to_goal.cpu(), (state[:, :2].cpu() - goal).norm(dim=1)
+    return steps_to_goal.cpu(), dist.cpu(), wall / n_steps
 
 
 if __name__ == "__main__":
@@ -88,5 +116,6 @@ if __name__ == "__main__":
     ap.add_argument("--samples", type=int, default=4096)
     ap.add_argument("--horizon", type=int, default=30)
     ap.add_argument("--max-steps", type=int, default=900)
+    ap.add_argument("--no-graph", action="store_true")
     a = ap.parse_args()
-    run(a.envs, a.samples, a.horizon, a.max_steps)
+    run(a.envs, a.samples, a.horizon, a.max_steps, use_graph=not a.no_graph)

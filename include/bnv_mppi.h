@@ -186,6 +186,14 @@ int bnv_mppi_draw_noise(bnv_mppi* h, uint64_t iteration, void* stream);
  * caller-owned.  Lets a test replay an in-engine-noise iteration through the oracle. */
 int bnv_mppi_draw_xi(bnv_mppi* h, uint64_t iteration, float* xi_out_dev, float* xi_opt_out_dev, void* stream);
 
+/* Graph-capturable launches.  A captured CUDA graph freezes the kernel's launch packet, which normally carries the
+ * iteration counter (the Philox counter word) and the launch epoch.  With enable != 0 both are read from a
+ * device-resident counter instead, advanced by a one-thread kernel after every forward in stream order -- so a
+ * stream capture of forward (+ the environment step, collision check, ...) can be replayed as one graph launch per
+ * control step, with the same noise stream as uncaptured calls.  enable = 0 returns to by-value counters, keeping
+ * the count.  Synchronises `stream`; world_size must be 1; bnv_mppi_forward_host is not capturable. */
+int bnv_mppi_device_counter(bnv_mppi* h, int32_t enable, void* stream);
+
 /* ---- hooks used by the DWA planner built on the same rollout kernel (src/planners/local_planners/dwa.py) ----
  * DWA.forward (dwa.py:116-149) = the MPPI rollout/cost machinery with K = num_lin_vel * num_ang_vel constant
  * action sequences injected as "noise" around a zero mean (bnv_mppi_forward with noise_dev = the held actions),
@@ -248,23 +256,26 @@ typedef struct bnv_grid {
  * (planetary_env.py:221-232).
  *   std_dev == NULL  inference mode: trav = 1 - clamp(mean[cell], 0, 1) with mean = the risk map
  *   std_dev != NULL  observation mode: trav = 1 - clamp(mean[cell] + std[cell] * xi, 0, 1); xi_dev [n] standard
- *                    normals, or NULL to draw them from Philox(seed, counter)
+ *                    normals, or NULL to draw them from Philox(seed, counter + *counter_dev); counter_dev is an
+ *                    optional device-resident 64-bit draw counter (NULL = 0) that the caller advances in stream order,
+ *                    so that the call can be captured in a CUDA graph and still draw fresh normals on every replay
  *   rows_per_env > 0 positions are [E][rows_per_env] and environment e reads the map at mean_dev + e * env_stride
  *   trav_out_dev [n] and/or stuck_out_dev [n] (uint8, trav <= stuck_threshold); either may be NULL. */
 int bnv_trav_lookup(const bnv_grid* grid, const float* mean_dev, const float* std_dev, int64_t env_stride,
                     int64_t rows_per_env, const float* pos_dev, int64_t n, int32_t pos_stride, const float* xi_dev,
-                    uint64_t seed, uint64_t counter, float stuck_threshold, float* trav_out_dev,
-                    uint8_t* stuck_out_dev, void* stream);
+                    uint64_t seed, uint64_t counter, const uint64_t* counter_dev, float stuck_threshold,
+                    float* trav_out_dev, uint8_t* stuck_out_dev, void* stream);
 
 /* PlanetaryEnv.step (planetary_env.py:189-219) for E independent environments in one launch:
  * observation-mode transit of states_dev [E,3] (updated in place) under actions_dev [E,2], reward_out_dev [E] = the
  * traversability drawn for the step, terminated_out_dev [E] (uint8) = ||p - goal|| < goal_threshold.  Maps as in
- * bnv_trav_lookup (env_stride 0 = shared).  xi_dev [E] or NULL (Philox(seed, counter)).  The elapsed-time /
+ * bnv_trav_lookup (env_stride 0 = shared).  xi_dev [E] or NULL (Philox(seed, counter + *counter_dev)).  The elapsed-time /
  * truncation bookkeeping (two scalars) stays with the caller. */
 int bnv_env_step(const bnv_grid* grid, const float* mean_dev, const float* std_dev, int64_t env_stride,
                  int32_t num_envs, float* states_dev, const float* actions_dev, const float* goals_dev,
-                 const float* xi_dev, uint64_t seed, uint64_t counter, const float u_min[2], const float u_max[2],
-                 float delta_t, float goal_threshold, float* reward_out_dev, uint8_t* terminated_out_dev, void* stream);
+                 const float* xi_dev, uint64_t seed, uint64_t counter, const uint64_t* counter_dev, const float u_min[2],
+                 const float u_max[2], float delta_t, float goal_threshold, float* reward_out_dev,
+                 uint8_t* terminated_out_dev, void* stream);
 
 /* TraversabilityModel._infer_risk_map (traversability_model.py:28-51) over n_cells cells.
  *   metric      0 expected value, 1 VaR, 2 CVaR (utils.py:18); confidence = ModelConfig.confidence_value

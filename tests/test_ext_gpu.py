@@ -393,6 +393,49 @@ def test_closed_loop_example_reaches_the_goals():
     spec = importlib.util.spec_from_file_location("closed_loop_example", path)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
-    steps, dist = mod.run(envs=8, samples=2048, horizon=30, max_steps=900, verbose=False)
-    assert int((steps > 0).sum()) >= 7, (steps.tolist(), dist.tolist())  # every robot (one straggler tolerated) arrives
-    assert float(dist.min()) < 1.0
+    for use_graph in (True, False):  # one CUDA-graph launch per control step, or host-issued launches
+        steps, dist, _ = mod.run(envs=8, samples=2048, horizon=30, max_steps=900, verbose=False, use_graph=use_graph)
+        assert int((steps > 0).sum()) >= 7, (use_graph, steps.tolist(), dist.tolist())  # one straggler tolerated
+        assert float(dist.min()) < 1.0
+
+
+# ------------------------------------------------------------------------------------------------ CUDA graphs
+def test_forward_captured_in_a_cuda_graph_replays_the_same_noise_stream():
+    """With the iteration counter in device memory, forward() is captured once and replayed: every replay advances
+    the Philox stream exactly like an uncaptured call (bit-equal recorded states and controls)."""
+    from tests.gpu_common import make_solver
+    from benchnav_b200.synthetic import benchmark_problem
+
+    risk, start, goal, thr = benchmark_problem(64, 0.5, seed=0)
+    K, T = 1024, 20
+    plain = make_solver(risk, 0.5, goal.tolist(), thr, K, T, [0.5, 0.5], 0.5, seed=11)
+    graphed = make_solver(risk, 0.5, goal.tolist(), thr, K, T, [0.5, 0.5], 0.5, seed=11)
+    state = start.cuda()
+    ref = []
+    for _ in range(4):
+        u, opt = plain.forward(state)
+        torch.cuda.synchronize()
+        ref.append((u.clone(), opt.clone(), plain._state_seq_batch.clone(), plain._weights.clone()))
+    graphed.graph_capturable(True)
+    u0, opt0 = graphed.forward(state)  # iteration 0, uncaptured but on the device counter
+    torch.cuda.synchronize()
+    assert torch.equal(u0, ref[0][0]) and torch.equal(graphed._state_seq_batch, ref[0][2])
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            ug, optg = graphed.forward(state)
+    torch.cuda.current_stream().wait_stream(side)
+    for i in range(1, 4):  # the capture itself launched nothing; replays are iterations 1, 2, 3
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(ug, ref[i][0]), f"replay {i}: controls differ"
+        assert torch.equal(optg, ref[i][1])
+        assert torch.equal(graphed._state_seq_batch, ref[i][2])
+        assert torch.equal(graphed._weights, ref[i][3])
+    graphed.graph_capturable(False)  # back to by-value counters, the count carries over
+    u4, _ = graphed.forward(state)
+    u4p, _ = plain.forward(state)
+    torch.cuda.synchronize()
+    assert torch.equal(u4, u4p)

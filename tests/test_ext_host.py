@@ -24,12 +24,12 @@ def test_aux_entry_points_reject_bad_arguments():
     one = C.c_void_p(16)  # never dereferenced: validation fails first
     f2 = (C.c_float * 2)(0.0, 1.0)
     cases = [
-        (lambda: lib.bnv_trav_lookup(None, one, None, 0, 0, one, 4, 3, None, 0, 0, 0.1, one, None, None), b"null grid"),
-        (lambda: lib.bnv_trav_lookup(C.byref(_grid(pitch=8)), one, None, 0, 0, one, 4, 3, None, 0, 0, 0.1, one, None, None), b"pitch"),
-        (lambda: lib.bnv_trav_lookup(C.byref(_grid()), one, None, 0, 0, one, 4, 1, None, 0, 0, 0.1, one, None, None), b"size"),
-        (lambda: lib.bnv_trav_lookup(C.byref(_grid()), one, None, 0, 0, one, 4, 3, None, 0, 0, 0.1, None, None, None), b"null"),
-        (lambda: lib.bnv_env_step(C.byref(_grid(resolution=0.0)), one, one, 0, 1, one, one, one, None, 0, 0, f2, f2, 0.1, 1.0, one, one, None), b"resolution"),
-        (lambda: lib.bnv_env_step(C.byref(_grid()), one, one, 0, 0, one, one, one, None, 0, 0, f2, f2, 0.1, 1.0, one, one, None), b"size"),
+        (lambda: lib.bnv_trav_lookup(None, one, None, 0, 0, one, 4, 3, None, 0, 0, None, 0.1, one, None, None), b"null grid"),
+        (lambda: lib.bnv_trav_lookup(C.byref(_grid(pitch=8)), one, None, 0, 0, one, 4, 3, None, 0, 0, None, 0.1, one, None, None), b"pitch"),
+        (lambda: lib.bnv_trav_lookup(C.byref(_grid()), one, None, 0, 0, one, 4, 1, None, 0, 0, None, 0.1, one, None, None), b"size"),
+        (lambda: lib.bnv_trav_lookup(C.byref(_grid()), one, None, 0, 0, one, 4, 3, None, 0, 0, None, 0.1, None, None, None), b"null"),
+        (lambda: lib.bnv_env_step(C.byref(_grid(resolution=0.0)), one, one, 0, 1, one, one, one, None, 0, 0, None, f2, f2, 0.1, 1.0, one, one, None), b"resolution"),
+        (lambda: lib.bnv_env_step(C.byref(_grid()), one, one, 0, 0, one, one, one, None, 0, 0, None, f2, f2, 0.1, 1.0, one, one, None), b"size"),
         (lambda: lib.bnv_risk_map(3, 0.9, 0, one, one, 16, None, 100, 0, one, None, None), b"metric"),
         (lambda: lib.bnv_risk_map(1, 1.5, 0, one, one, 16, None, 100, 0, one, None, None), b"confidence"),
         (lambda: lib.bnv_risk_map(2, 0.9, 1, one, one, 16, None, 0, 0, one, None, None), b"num_samples"),
