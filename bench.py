@@ -15,9 +15,10 @@ Numbers
   value        device-timed: per-step CUDA-event pairs around forward() (state resident in HBM), L2 flushed
                between steps by writing a 256 MiB buffer, max over ranks; unit = iterations of one
                (16384-sample x 50-step) shard per second summed over ranks (= control iterations/s x N).
-  e2e          forward_host(): every step the 12-byte state goes host -> device in the kernel's launch packet, the
-               iteration runs, the kernel stores u* and the optimal state sequence (1012 bytes) device -> host into
-               pinned mapped memory, one stream sync; wall clock per step (L2 flushed between steps, flush not counted).
+  e2e          forward_host(state, out=...): every step the 12-byte state goes host -> device in the kernel's launch
+               packet, the iteration runs, the kernel stores u* and the optimal state sequence (1012 bytes) device ->
+               host into pinned mapped memory and raises a completion word the host polls; wall clock per step (L2
+               flushed between steps, flush not counted).
   roofline     rollout kernel alone: SURVEY 8d algorithmic bytes / its CUDA-event duration (second pass with the
                engine's kernel-event recorder on), against MEASURED_PEAKS.json hbm_gbs.
   cpu_baseline the oracle port of the reference loop (oracle/mppi_oracle.py, PyTorch CPU ops) on the host cores.

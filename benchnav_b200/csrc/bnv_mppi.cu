@@ -847,7 +847,7 @@ int bnv_mppi_launch_geometry(const bnv_mppi* h, int32_t out[4]) {
   const bool coop = h->coop_ok && static_cast<long long>(h->grid) * h->E <= h->resident_ctas;
   out[0] = h->grid;
   out[1] = h->warps;
-  out[2] = 1;  // thread-block clusters: measured slower than the L2 merge for this epilogue, not used
+  out[2] = h->P.rec_split;
   out[3] = coop ? 1 : 0;
   return BNV_OK;
 }

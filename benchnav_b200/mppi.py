@@ -358,10 +358,10 @@ class MPPI(nn.Module):
 
     @property
     def launch_geometry(self) -> dict:
-        """Rollout-kernel launch shape: CTAs, warps per CTA, thread-block cluster size, cooperative or not."""
+        """Rollout-kernel launch shape: CTAs, warps per CTA, recorded-state slab split step (0 = one flush), cooperative."""
         out = (C.c_int32 * 4)()
         _cabi.check(self._lib.bnv_mppi_launch_geometry(self._handle, out))
-        return {"ctas": out[0], "warps_per_cta": out[1], "cluster": out[2], "cooperative": bool(out[3])}
+        return {"ctas": out[0], "warps_per_cta": out[1], "rec_split": out[2], "cooperative": bool(out[3])}
 
     def kernel_timing(self, max_launches: int) -> None:
         """Record CUDA-event pairs around the rollout kernel of the next ``max_launches`` iterations."""

@@ -221,7 +221,8 @@ int bnv_mppi_dwa_subgoal(bnv_mppi* h, const float* path_dev, int32_t n, const fl
 uint64_t bnv_mppi_launch_count(const bnv_mppi* h);
 
 /* Launch geometry chosen for the rollout kernel by the last bnv_mppi_set_problem*: out = {CTAs per environment,
- * warps per CTA, thread-block cluster size (1 = none), 1 if the grid is co-resident and launched cooperatively}. */
+ * warps per CTA, the step at which the recorded-state slab is flushed mid-loop (0 = one flush at the end),
+ * 1 if the grid is co-resident and launched cooperatively}. */
 int bnv_mppi_launch_geometry(const bnv_mppi* h, int32_t out[4]);
 
 /* Measurement hook: record a CUDA-event pair around the rollout kernel of each of the next `max_launches`
