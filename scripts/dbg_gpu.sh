@@ -1,3 +1,1 @@
-python examples/closed_loop.py
-python examples/closed_loop.py --no-graph
-timeout 600 python -m pytest tests/test_ext_gpu.py -m gpu -q -x -k "closed_loop or graph or env_step or collision" 2>&1 | tail -3
+timeout 600 python -m pytest tests/test_ext_gpu.py -m gpu -q -x -k "without_a_staged or batch_of_one" 2>&1 | tail -12

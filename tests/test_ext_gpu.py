@@ -439,3 +439,57 @@ def test_forward_captured_in_a_cuda_graph_replays_the_same_noise_stream():
     u4p, _ = plain.forward(state)
     torch.cuda.synchronize()
     assert torch.equal(u4, u4p)
+
+
+# ------------------------------------------------------------------------------------------------ more shapes
+def test_batched_and_stochastic_without_a_staged_window():
+    """Fine resolution + long reach: the traversability window exceeds shared memory, lookups go to the global map
+    (batched: per-environment base pointer; stochastic: interleaved (mean, std) pairs); non-power-of-two resolution."""
+    from benchnav_b200 import BatchedMPPI
+    from benchnav_b200.problem import GoalObjectives, GridSpec, UnicycleProblem
+
+    g, res, K, T, sig, lam, thr = 200, 0.06, 300, 60, [0.5, 0.5], 0.5, 0.3
+    gen = torch.Generator().manual_seed(5)
+    E = 3
+    risks = [torch.rand(g, g, generator=gen) * 0.8 for _ in range(E)]
+    goals = [torch.tensor([9.0 - e, 8.0 + 0.5 * e]) for e in range(E)]
+    states = torch.tensor([[3.0, 3.0, 0.3], [6.0, 5.0, -2.0], [11.9, 0.05, 1.0]])
+    dyns = [UnicycleProblem(GridSpec(g, res), r) for r in risks]
+    objs = [GoalObjectives(d, gl, thr) for d, gl in zip(dyns, goals)]
+    solver = BatchedMPPI(T, K, dyns, objs, torch.tensor(sig), lam, seed=2)
+    noise = torch.randn(E, K, T, 2, generator=gen) * torch.tensor(sig)
+    u, opt = solver.forward(states, noise=noise)
+    torch.cuda.synchronize()
+    for e in range(E):
+        p = orc.make_problem(risks[e], res, goals[e].tolist(), thr)
+        ref = oracle_outputs(p, states[e], torch.zeros(T, 2), noise[e], sig, lam)
+        eng = {"u_opt": u[e].cpu().numpy(), "opt_rec": opt[e].cpu().numpy(), "weights": solver._weights[e].cpu().numpy(),
+               "costs": solver._costs[e].cpu().numpy(), "rec": solver._state_seq_batch[e].cpu().numpy()}
+        assert_iteration_close(eng, ref, f"no-window batch env {e}")
+    # stochastic, same geometry
+    std = torch.rand(g, g, generator=gen) * 0.2
+    st = _stoch_solver(risks[0], std, res, goals[0].tolist(), thr, K, T, sig, lam, seed=4)
+    xi = torch.randn(K, 2 * T + 1, generator=gen)
+    xi_opt = torch.randn(T, generator=gen)
+    u1, opt1 = st.forward(states[0], noise=noise[0], xi=xi, xi_opt=xi_opt)
+    p = orc.make_problem(risks[0], res, goals[0].tolist(), thr)
+    p.slip_std = std
+    ref = orc.mppi_iteration(p, states[0], torch.zeros(T, 2), noise[0], torch.tensor(sig), lam, xi=xi, xi_opt=xi_opt)
+    assert_iteration_close(engine_outputs(st, u1, opt1), {k: v.numpy() for k, v in ref.items()}, "no-window stochastic")
+
+
+def test_batch_of_one_equals_the_single_solver():
+    from benchnav_b200 import BatchedMPPI
+
+    dyns, objs, risks, goals, states, thr = _batch_problems(1, 64)
+    K, T, sig, lam = 640, 25, [0.5, 0.5], 0.5
+    b = BatchedMPPI(T, K, dyns, objs, torch.tensor(sig), lam, seed=8)
+    s = make_solver(risks[0], 0.5, goals[0].tolist(), thr, K, T, sig, lam, seed=8)
+    for _ in range(2):  # in-engine Philox noise: same seed, same stream (environment 0 adds nothing to the counter)
+        ub, ob = b.forward(states)
+        us, os_ = s.forward(states[0])
+        torch.cuda.synchronize()
+        assert torch.equal(b._action_noises[0], s._action_noises)
+        assert torch.equal(b._state_seq_batch[0], s._state_seq_batch)
+        np.testing.assert_allclose(ub[0].cpu().numpy(), us.cpu().numpy(), rtol=0, atol=2e-6)
+        np.testing.assert_allclose(ob[0].cpu().numpy(), os_.cpu().numpy(), rtol=0, atol=1e-5)
