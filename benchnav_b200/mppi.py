@@ -164,6 +164,8 @@ class MPPI(nn.Module):
         self._gathered = (torch.empty(self._shard.world_size, plen, device=dev, dtype=torch.float32)
                           if self._shard.world_size > 1 else None)
         self._state_dev = torch.zeros(3, device=dev, dtype=torch.float32)
+        self._forward_host_fn = self._lib.bnv_mppi_forward_host
+        self._slow_host_path = self._shard.world_size != 1 or noise_source != "philox"
         self._fused_exchange = False
         if self._shard.world_size > 1 and exchange == "p2p":
             self._fused_exchange = attach_peer_mailboxes(self._lib, self._handle, self._shard)
@@ -188,8 +190,8 @@ class MPPI(nn.Module):
         risks, goal = dyn._traversability_model._risks, obj._goal_pos
         if self._stochastic:
             risks = _slip_distribution(dyn._grid_map)[0]
-        quick = (id(risks), risks._version if torch.is_tensor(risks) else None, id(goal),
-                 goal._version if torch.is_tensor(goal) else None, obj._stuck_threshold, id(dyn._grid_map))
+        quick = (id(risks), risks._version, id(goal), goal._version if torch.is_tensor(goal) else None,
+                 obj._stuck_threshold, id(dyn._grid_map))
         if not force and quick == self._risk_key:
             return
         risks, g, res, x_lim, y_lim, goal, thr, _ = _introspect_problem(dyn, obj)
@@ -291,31 +293,45 @@ class MPPI(nn.Module):
         (``bnv_mppi_forward_host``): H2D of the state, the iteration, D2H of both results, one completion wait.
 
         ``out = (u_opt [T,2], opt_states [1,T+1,3])``: optional caller-owned fp32 CPU tensors to write the results into
-        (as with the C ABI, where the caller owns every buffer); fresh tensors are allocated otherwise."""
+        (as with the C ABI, where the caller owns every buffer); fresh tensors are allocated otherwise.
+
+        The call is the end-to-end path of a control loop, so its per-call Python work is kept minimal: argument
+        objects that were validated on the previous call (same tensor objects) are not validated again."""
+        d = self.__dict__  # plain attributes only: bypasses nn.Module's __getattr__/__setattr__ machinery
         if out is not None:
-            u_opt, opt_states = out
-            if not (u_opt.dtype == torch.float32 and opt_states.dtype == torch.float32 and u_opt.device.type == "cpu"
-                    and opt_states.device.type == "cpu" and u_opt.is_contiguous() and opt_states.is_contiguous()
-                    and u_opt.shape == (self._horizon, 2) and opt_states.shape == (1, self._horizon + 1, 3)):
-                raise ValueError("out must be contiguous fp32 CPU tensors of shapes [T,2] and [1,T+1,3]")
-        if self._shard.world_size != 1 or self._noise_source != "philox":
+            if out is not d.get("_host_out_ok"):
+                u_opt, opt_states = out
+                if not (u_opt.dtype == torch.float32 and opt_states.dtype == torch.float32
+                        and u_opt.device.type == "cpu" and opt_states.device.type == "cpu" and u_opt.is_contiguous()
+                        and opt_states.is_contiguous() and u_opt.shape == (self._horizon, 2)
+                        and opt_states.shape == (1, self._horizon + 1, 3)):
+                    raise ValueError("out must be contiguous fp32 CPU tensors of shapes [T,2] and [1,T+1,3]")
+                d["_host_out_ok"] = out
+            else:
+                u_opt, opt_states = out
+        if d["_slow_host_path"]:
             res = self.forward(state)
             if out is not None:
                 u_opt.copy_(res[0])
                 opt_states.copy_(res[1])
                 return u_opt, opt_states
             return res[0].cpu(), res[1].cpu()
-        if not (torch.is_tensor(state) and state.dtype == torch.float32 and state.device.type == "cpu"
-                and state.is_contiguous()):
-            state = torch.as_tensor(state, dtype=torch.float32).detach().cpu().contiguous()
-        assert state.shape == (self._dim_state,)
+        if state is not d.get("_host_state_ok"):
+            if not (torch.is_tensor(state) and state.dtype == torch.float32 and state.device.type == "cpu"
+                    and state.is_contiguous()):
+                state = torch.as_tensor(state, dtype=torch.float32).detach().cpu().contiguous()
+            assert state.shape == (self._dim_state,)
+            d["_host_state_ok"] = state
         self._sync_problem()
         if out is None:
             u_opt = torch.empty(self._horizon, 2, dtype=torch.float32)
             opt_states = torch.empty(1, self._horizon + 1, 3, dtype=torch.float32)
-        self._action_noises = self._engine_noise
-        _cabi.check(self._lib.bnv_mppi_forward_host(self._handle, state.data_ptr(), None, u_opt.data_ptr(),
-                                                    opt_states.data_ptr(), self._stream()))
+        if d["_action_noises"] is not d["_engine_noise"]:
+            d["_action_noises"] = d["_engine_noise"]
+        rc = d["_forward_host_fn"](d["_handle"], state.data_ptr(), None, u_opt.data_ptr(), opt_states.data_ptr(),
+                                   self._stream())
+        if rc != 0:
+            _cabi.check(rc)
         return u_opt, opt_states
 
     def get_top_samples(self, num_samples: int) -> Tuple[torch.Tensor, torch.Tensor]:
