@@ -493,3 +493,36 @@ def test_batch_of_one_equals_the_single_solver():
         assert torch.equal(b._state_seq_batch[0], s._state_seq_batch)
         np.testing.assert_allclose(ub[0].cpu().numpy(), us.cpu().numpy(), rtol=0, atol=2e-6)
         np.testing.assert_allclose(ob[0].cpu().numpy(), os_.cpu().numpy(), rtol=0, atol=1e-5)
+
+
+def test_error_behaviour_of_the_widened_path():
+    from benchnav_b200 import DWA, MPPI, BatchedMPPI, _cabi
+    from benchnav_b200.problem import GoalObjectives, GridSpec, UnicycleProblem
+
+    sig = torch.tensor([0.5, 0.5])
+    dyn = UnicycleProblem(GridSpec(16, 0.5), torch.zeros(16, 16))
+    obj = GoalObjectives(dyn, torch.tensor([4.0, 4.0]), 0.3)
+    with pytest.raises(_cabi.BnvError) as ei:  # a horizon whose slabs cannot fit shared memory even with one warp
+        MPPI(3000, 64, 3, 2, dyn, obj, sig, 0.5)
+    assert ei.value.code == -3
+    other = UnicycleProblem(GridSpec(32, 0.5), torch.zeros(32, 32))
+    with pytest.raises(ValueError):  # environments of a batch share the grid geometry
+        BatchedMPPI(10, 64, [dyn, other], [obj, GoalObjectives(other, torch.tensor([4.0, 4.0]), 0.3)], sig, 0.5)
+    with pytest.raises(ValueError):
+        BatchedMPPI(10, 64, [dyn], [obj, obj], sig, 0.5)
+    b = BatchedMPPI(10, 64, [dyn, dyn], [obj, obj], sig, 0.5)
+    with pytest.raises(AssertionError):
+        b.forward(torch.zeros(3, 3))
+    with pytest.raises(ValueError):
+        b.forward(torch.zeros(2, 3), noise=torch.zeros(2, 64, 9, 2))
+    with pytest.raises(_cabi.BnvError):  # top samples before any forward
+        b.get_top_samples(4)
+    with pytest.raises(AssertionError):  # dwa.py:70-72
+        DWA(10, 3, 2, dyn, obj, torch.tensor([0.5]), 0.1)
+    with pytest.raises(TypeError):  # stochastic slip needs the slip distribution on the grid map
+        MPPI(10, 64, 3, 2, dyn, obj, sig, 0.5, stochastic_slip=True)
+    d = DWA(10, 3, 2, dyn, obj, torch.tensor([0.5, 1.5]), 0.1)
+    with pytest.raises(AssertionError):  # dwa.py:129-131
+        d.forward(torch.zeros(2))
+    with pytest.raises(AssertionError):  # dwa.py:154-156
+        d.update_reference_path(torch.zeros(5, 3))
