@@ -996,19 +996,27 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
       __syncthreads();
     }
     const bool complete = P.world == 1 || fused;  // (M, S, U) now cover every sample of the solver
-    if (coop && tid == 0) {  // publish (M, S) and release the waiting CTAs as early as possible
+    // publish (M, S) and release the waiting CTAs as early as possible -- from the LAST thread: the release is a
+    // membar that stalls its warp for several hundred cycles, and warp 0 (thread 0 runs the serial optimal rollout
+    // next) must not wait for it.  So with more than one warp the last warp only publishes, the other warps compute
+    // u* and meet at a named barrier of their own.
+    const bool split_pub = coop && blockDim.x > 32;
+    const int nwork = split_pub ? static_cast<int>(blockDim.x) - 32 : static_cast<int>(blockDim.x);
+    if (coop && tid == static_cast<int>(blockDim.x) - 1) {
       stats_e[0] = M;
       stats_e[1] = S;
       st_release_gpu(ticket_e + 1, epoch);
     }
     if (complete) {
       float* u_out_e = P.u_out + static_cast<size_t>(env) * ncol;
-      for (int c = tid; c < ncol; c += blockDim.x) {
-        const float u = __fdiv_rn(uprev_s[c], S);  // u* = U / S (mppi.py:196-199)
-        uprev_s[c] = u;
-        warpu_s[c] = clampf(u, (c & 1) ? C.u_min1 : C.u_min0, (c & 1) ? C.u_max1 : C.u_max0);  // for the optimal rollout
-        u_out_e[c] = u;
-        if (P.keep_mean) u_prev_e[c] = u;  // next call's mean sequence, unshifted (mppi.py:217)
+      if (tid < nwork) {
+        for (int c = tid; c < ncol; c += nwork) {
+          const float u = __fdiv_rn(uprev_s[c], S);  // u* = U / S (mppi.py:196-199)
+          uprev_s[c] = u;
+          warpu_s[c] = clampf(u, (c & 1) ? C.u_min1 : C.u_min0, (c & 1) ? C.u_max1 : C.u_max0);  // for the optimal rollout
+          u_out_e[c] = u;
+          if (P.keep_mean) u_prev_e[c] = u;  // next call's mean sequence, unshifted (mppi.py:217)
+        }
       }
     } else {  // unfused sharding: hand the shard partial to the host-side exchange + finalize_kernel
       if (tid == 0) {
@@ -1017,7 +1025,11 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
       }
       for (int c = tid; c < ncol; c += blockDim.x) P.shard_partial[2 + c] = uprev_s[c];
     }
-    __syncthreads();
+    if (split_pub) {
+      if (tid < nwork) asm volatile("bar.sync 1, %0;" ::"r"(nwork) : "memory");
+    } else {
+      __syncthreads();
+    }
     if (stamp) BNV_STAMP(5);
     if (tid == 0) *ticket_e = 0u;  // re-arm for the next launch
     if (stamp) BNV_STAMP(6);
