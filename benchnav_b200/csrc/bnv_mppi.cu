@@ -609,7 +609,9 @@ int bnv_mppi_forward_host(bnv_mppi* h, const float state_host[3], const float* n
       seen = true;
       break;
     }
-    if ((spins & 1023) == 1023 && cudaStreamQuery(s) != cudaErrorNotReady) break;
+    // a rare liveness check (about once a millisecond): a stream query costs a microsecond or two, which must not
+    // land inside the ~20 us the kernel normally takes
+    if ((spins & 0xFFFF) == 0xFFFF && cudaStreamQuery(s) != cudaErrorNotReady) break;
 #if defined(__x86_64__) || defined(__i386__)
     __builtin_ia32_pause();
 #endif

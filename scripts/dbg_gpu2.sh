@@ -1,3 +1,4 @@
+#!/bin/bash
 # two-GPU session: sharded-solver parity (NCCL + fused P2P exchange) and the N=2 bench lines for both exchange modes
 timeout 600 python -m pytest tests/test_multigpu_gpu.py -q -x 2>&1 | tail -3
 for ex in p2p nccl; do
@@ -5,4 +6,3 @@ python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.
 import json,sys
 d=json.loads(sys.stdin.read()); print('$ex', 'value',round(d['value']), 'us/step',round(d['ms_per_step']*1e3,2), d['config']['parallelism'])"
 done
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29534 bench.py --impl reference --gpus 2 --steps 3 --warmup 1 2>/dev/null | tail -1 | cut -c1-200
