@@ -6,7 +6,8 @@
 //   env_step_kernel        PlanetaryEnv.step for E independent environments (planetary_env.py:189-219)
 //   risk_closed_kernel     risk map, closed form for a Normal slip distribution (expected value / VaR / CVaR)
 //   risk_mc_kernel         risk map by Monte-Carlo exactly as TraversabilityModel._infer_risk_map
-//                          (traversability_model.py:28-51): S draws per cell, torch.quantile (linear), tail nanmean
+//                          (traversability_model.py:28-51): S draws per cell, torch.quantile (linear) by radix
+//                          selection of the two order statistics, tail nanmean
 //   dwa_actions_kernel     DWA._generate_actions (dwa.py:151-184): dynamic window, linspace, cartesian product
 //   dwa_subgoal_kernel     DWA._select_sub_goal (dwa.py:260-285)
 //   argmin_gather_kernel   DWA.forward's argmin + gathers (dwa.py:141-144)
@@ -131,7 +132,7 @@ enum RiskMetric { kRiskExpected = 0, kRiskVar = 1, kRiskCvar = 2 };
 // (linear interpolation between order statistics floor/ceil(q (S-1)), ATen lerp), CVaR = mean of the samples
 // strictly above VaR (nanmean of the masked tail; NaN when the tail is empty).
 // One CTA = `cpc` consecutive cells, samples staged in shared memory as rows of S_pad (+1 pad) floats, +inf padded;
-// one warp bitonic-sorts a row (ascending), then reads the order statistics / reduces the tail.
+// one warp per row selects the two order statistics (radix select on order-preserving keys) and reduces the tail.
 // `samples_out` (optional, [S][n]) receives the drawn samples so that tests can replay them through the oracle.
 __global__ void __launch_bounds__(kRiskThreads) risk_mc_kernel(const float* __restrict__ mean,
                                                                const float* __restrict__ stdv, long long n,
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(kRiskThreads) risk_mc_kernel(const float* __re
       vals[c * rs + s] = v;
     }
   } else {
-    const int quads = S_pad >> 2;  // S_pad is a power of two >= 4
+    const int quads = S_pad >> 2;  // S_pad is a multiple of 32
     const uint2 key = make_uint2(seed_lo, seed_hi);
     for (int idx = tid; idx < cpc * quads; idx += blockDim.x) {
       const int c = idx % cpc, j = idx / cpc;
@@ -181,28 +182,47 @@ __global__ void __launch_bounds__(kRiskThreads) risk_mc_kernel(const float* __re
   }
   __syncthreads();
   const float rank = __fmul_rn(q, static_cast<float>(S - 1));  // ATen quantile: ranks = q * (n - 1) in the input dtype
-  const float rlo = floorf(rank), rhi = ceilf(rank);
-  const float wgt = __fsub_rn(rank, rlo);
+  const float rlo_f = floorf(rank), rhi_f = ceilf(rank);
+  const float wgt = __fsub_rn(rank, rlo_f);
+  const unsigned int rlo = static_cast<unsigned int>(rlo_f), rhi = static_cast<unsigned int>(rhi_f);
+  const int per_lane = S_pad >> 5;  // S_pad is a multiple of 32
+  // One warp per cell.  Instead of sorting the row, the two order statistics torch.quantile interpolates between are
+  // SELECTED: the samples are mapped to order-preserving unsigned keys and the rank-rlo key is found bit by bit from
+  // the top (32 counting passes over the row, warp-reduced with REDUX); its successor needs one more pass.
   for (int c = warp; c < cpc; c += nwarps) {
     const long long cell = cell0 + c;
     if (cell >= n) break;
-    float* row = vals + c * rs;
-    for (int size = 2; size <= S_pad; size <<= 1) {
-      for (int stride = size >> 1; stride > 0; stride >>= 1) {
-        for (int i = lane; i < (S_pad >> 1); i += 32) {
-          const int lo = 2 * i - (i & (stride - 1));
-          const int hi = lo + stride;
-          const bool asc = ((lo & size) == 0);
-          const float a = row[lo], bq = row[hi];
-          if ((a > bq) == asc) {
-            row[lo] = bq;
-            row[hi] = a;
-          }
-        }
-        __syncwarp();
+    unsigned int* keys = reinterpret_cast<unsigned int*>(vals + c * rs);
+    for (int j = 0; j < per_lane; ++j) {  // float -> sortable key, in place (+inf pads sort last)
+      const unsigned int bits = keys[j * 32 + lane];
+      keys[j * 32 + lane] = bits ^ ((bits >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+    }
+    __syncwarp();
+    unsigned int prefix = 0u, r = rlo;
+    for (int bit = 31; bit >= 0; --bit) {
+      unsigned int cnt0 = 0u;  // keys that agree with the prefix above `bit` and have this bit clear
+      for (int j = 0; j < per_lane; ++j) cnt0 += (((keys[j * 32 + lane] ^ prefix) >> bit) == 0u) ? 1u : 0u;
+      cnt0 = __reduce_add_sync(0xffffffffu, cnt0);
+      if (r >= cnt0) {
+        prefix |= 1u << bit;
+        r -= cnt0;
       }
     }
-    const float a = row[static_cast<int>(rlo)], bq = row[static_cast<int>(rhi)];
+    const unsigned int key_lo = prefix;
+    unsigned int key_hi = key_lo;
+    if (rhi != rlo) {  // the next order statistic: key_lo again if it has duplicates reaching rank rhi, else its successor
+      unsigned int n_le = 0u, succ = 0xFFFFFFFFu;
+      for (int j = 0; j < per_lane; ++j) {
+        const unsigned int k = keys[j * 32 + lane];
+        n_le += (k <= key_lo) ? 1u : 0u;
+        if (k > key_lo) succ = min(succ, k);
+      }
+      n_le = __reduce_add_sync(0xffffffffu, n_le);
+      succ = __reduce_min_sync(0xffffffffu, succ);
+      key_hi = (n_le >= rhi + 1u) ? key_lo : succ;
+    }
+    auto key_to_float = [](unsigned int k) { return __uint_as_float(k ^ ((k >> 31) ? 0x80000000u : 0xFFFFFFFFu)); };
+    const float a = key_to_float(key_lo), bq = key_to_float(key_hi);
     // ATen lerp (vectorised CPU form): weight < 0.5 ? a + w (b - a) : b - (b - a)(1 - w), as one fused multiply-add
     const float diff = __fsub_rn(bq, a);
     const float var = (wgt < 0.5f) ? fmaf(wgt, diff, a) : fmaf(__fsub_rn(wgt, 1.0f), diff, bq);
@@ -211,7 +231,7 @@ __global__ void __launch_bounds__(kRiskThreads) risk_mc_kernel(const float* __re
       float sum = 0.0f;
       int cnt = 0;
       for (int i = lane; i < S; i += 32) {
-        const float v = row[i];
+        const float v = key_to_float(keys[i]);
         if (v > var) {
           sum += v;
           ++cnt;

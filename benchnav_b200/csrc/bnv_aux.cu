@@ -144,8 +144,7 @@ int bnv_risk_map(int32_t metric, float confidence, int32_t method, const float* 
   if (method != BNV_RISK_MONTE_CARLO) return bnv_fail(BNV_ERR_INVALID, "unknown method %d", method);
   if (num_samples < 1 || num_samples > 32768) return bnv_fail(BNV_ERR_INVALID, "num_samples %d outside [1, 32768]", num_samples);
   if (!samples_dev && !std_dev) return bnv_fail(BNV_ERR_INVALID, "std map required to draw samples");
-  int s_pad = 4;
-  while (s_pad < num_samples) s_pad <<= 1;
+  const int s_pad = (num_samples + 31) & ~31;  // whole warps of samples per row; the pads hold +inf
   const size_t row_bytes = static_cast<size_t>(s_pad + 1) * sizeof(float);
   int cpc = static_cast<int>(std::min<size_t>(32, (200 * 1024) / row_bytes));
   if (cpc < 1) return bnv_fail(BNV_ERR_UNSUPPORTED, "num_samples too large for shared memory");
