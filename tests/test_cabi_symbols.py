@@ -88,3 +88,28 @@ def test_invalid_arguments_are_rejected_before_touching_the_device():
     assert lib.bnv_mppi_create(None, None) == -1
     assert lib.bnv_mppi_forward(None, None, None, None, None, None) == -1
     assert lib.bnv_mppi_launch_count(None) == 0
+
+
+def test_header_is_valid_c_and_a_plain_c_client_links():
+    """include/bnv_mppi.h compiles as C99 (no C++-isms behind the extern "C" guard) and a C program links against the
+    shared library and reaches it (examples/c_abi_demo.c)."""
+    import shutil
+    import tempfile
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    build.ensure_built()
+    with tempfile.TemporaryDirectory() as tmp:
+        exe = os.path.join(tmp, "c_abi_demo")
+        cmd = [gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(root, "include"),
+               os.path.join(root, "examples", "c_abi_demo.c"), "-L", build.LIB_DIR, "-lbnvmppi",
+               "-Wl,-rpath," + build.LIB_DIR, "-o", exe]
+        out = subprocess.run(cmd, capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
+        run = subprocess.run([exe], capture_output=True, text=True)
+        assert run.returncode == 0, run.stdout + run.stderr
+        assert f"bnv_abi_version = {_cabi.ABI_VERSION}" in run.stdout
+        if not torch.cuda.is_available():
+            assert "bnv_mppi_create -> -2" in run.stdout  # BNV_ERR_CUDA: fails loudly without a device
