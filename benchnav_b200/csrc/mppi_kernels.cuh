@@ -571,6 +571,11 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
   const int k = warp_first + lane;
   const bool valid = lane < warp_rows;
 
+  // the state (a cold load when it lives in HBM) is requested first: its latency runs under the barrier set-up
+  const float* state_e = P.state + 3 * env;
+  const float sx = P.state_inline ? P.state_val[0] : __ldg(state_e);
+  const float sy = P.state_inline ? P.state_val[1] : __ldg(state_e + 1);
+  const float sth = P.state_inline ? P.state_val[2] : __ldg(state_e + 2);
   if (tid == 0) {
     mbar_init(bar_patch, 1);
     for (int w = 0; w < kMaxWarps; ++w) mbar_init(bar_noise + w, 1);
@@ -600,11 +605,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
   // controls rebuilt from them by 0)
   for (int i = warp_rows * 2 * T + lane; i < 32 * 2 * T; i += 32) nz_w[i] = 0.0f;
 
-  // ---- state, window geometry, traversability window via TMA
-  const float* state_e = P.state + 3 * env;
-  const float sx = P.state_inline ? P.state_val[0] : __ldg(state_e);
-  const float sy = P.state_inline ? P.state_val[1] : __ldg(state_e + 1);
-  const float sth = P.state_inline ? P.state_val[2] : __ldg(state_e + 2);
+  // ---- window geometry, traversability window via TMA
   const WindowGeom wg = window_for_state(P, sx, sy);
   if (kPatch) {
     if (warp == 0) {
