@@ -63,3 +63,29 @@ def test_synthetic_problem_is_deterministic_and_sane():
     assert float(risk[16, 16]) <= 0.2 + 1e-6  # start cell drivable
     np.testing.assert_allclose(goal.numpy(), [48.0, 48.0])
     assert 0.01 < float((1 - risk <= thr).float().mean()) < 0.5  # some, not all, cells are "stuck"
+
+
+def test_product_code_never_imports_the_oracle_or_the_reference():
+    """The oracle is test infrastructure: nothing under benchnav_b200/ (nor the example) may import it, or the
+    reference package, or fall back to CPU arithmetic (static check over the package sources)."""
+    import ast
+    import glob
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = glob.glob(os.path.join(root, "benchnav_b200", "*.py")) + glob.glob(os.path.join(root, "examples", "*.py"))
+    assert len(files) >= 10
+    for path in files:
+        tree = ast.parse(open(path).read(), filename=path)
+        for node in ast.walk(tree):
+            names = []
+            if isinstance(node, ast.Import):
+                names = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom):
+                names = [node.module or ""]
+            for n in names:
+                top = n.split(".")[0]
+                assert top not in ("oracle", "src", "simulator", "planners", "environments"), f"{path} imports {n}"
+    for path in glob.glob(os.path.join(root, "benchnav_b200", "csrc", "*")):
+        text = open(path).read()
+        assert "oracle" not in text.lower(), path
