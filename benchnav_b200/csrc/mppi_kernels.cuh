@@ -3,14 +3,15 @@
 //   trav_map_kernel     risk map -> tau = 1 - clamp(risk,0,1), padded pitch            (traversability_model.py:71-72)
 //   rollout_kernel      noise draw (Philox, interleaved with the rollout), clamp, T-step unicycle rollout, costs,
 //                       per-CTA softmax partial; last CTA: grid merge, weights, optimal rollout (mppi.py:149-217)
-//   noise_kernel        the same Philox stream as a stand-alone kernel (tests / bnv_mppi_draw_noise)
+//   noise_kernel        the same Philox stream as a stand-alone kernel (tests / bnv_mppi_draw_noise); xi_kernel,
+//                       slip_map_kernel, bump_iteration_kernel: stochastic-mode and graph-capture helpers
 //   finalize_kernel     multi-GPU: merge gathered shard partials, weights, optimal rollout
 //   top-n kernels       radix select + sort + gather                                    (mppi.py:221-240)
 //
 // Work decomposition of rollout_kernel: one thread = one sample, state and running cost in registers;
 // one warp = 32 consecutive samples with its own slabs in shared memory -- noise (bulk-loaded from HBM when
-// injected, or produced in the loop and bulk-stored), clamped controls v, recorded states (bulk-stored) -- so
-// warps never synchronise inside the T-loop; one CTA = up to 4 warps (one per SM sub-partition) sharing the
+// injected, or produced in the loop and bulk-stored) and recorded states (bulk-stored; the clamped controls are
+// rebuilt from the noise when the weighted sum needs them) -- so warps never synchronise inside the T-loop; one CTA = up to 4 warps (one per SM sub-partition) sharing the
 // traversability window staged by one 2-D TMA load.  At K = 16384 there is at most one warp per scheduler: the
 // kernel is bound by the per-step dependency chain, not by bandwidth, so the loop body is branch-free, keeps
 // every invariant in registers, and fills the chain's stall slots with the next step pair's Philox draw.
