@@ -890,6 +890,14 @@ int bnv_debug_timestamps(bnv_mppi* h, long long out[16]) {
   return BNV_OK;
 }
 
+int bnv_debug_philox(const uint32_t* in_dev, uint32_t* out_dev, int32_t n, void* stream) {
+  if (!in_dev || !out_dev || n < 0) return fail(BNV_ERR_INVALID, "bad argument");
+  if (n == 0) return BNV_OK;
+  bnv::philox_debug_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(in_dev, out_dev, n);
+  BNV_CUDA(cudaGetLastError());
+  return BNV_OK;
+}
+
 int bnv_debug_sincos(const float* theta_dev, float* sin_dev, float* cos_dev, int32_t n, void* stream) {
   if (!theta_dev || !sin_dev || !cos_dev || n < 0) return fail(BNV_ERR_INVALID, "bad argument");
   if (n == 0) return BNV_OK;

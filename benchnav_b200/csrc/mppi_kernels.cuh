@@ -1229,6 +1229,15 @@ __global__ void gather_rows_kernel(const float* __restrict__ rec, const int* __r
 }
 
 // --------------------------------------------------------------------------------------------- debug
+// in [n][6] = (counter x, y, z, w, key lo, key hi) -> out [n][4]: the raw Philox4x32-10 block (known-answer tests)
+__global__ void philox_debug_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint4 r = philox4x32_10(make_uint4(in[6 * i], in[6 * i + 1], in[6 * i + 2], in[6 * i + 3]),
+                                make_uint2(in[6 * i + 4], in[6 * i + 5]));
+  out[4 * i] = r.x; out[4 * i + 1] = r.y; out[4 * i + 2] = r.z; out[4 * i + 3] = r.w;
+}
+
 __global__ void sincos_debug_kernel(const float* __restrict__ th, float* __restrict__ s, float* __restrict__ c, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) sincos_heading<false>(th[i], &s[i], &c[i]);

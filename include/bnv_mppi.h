@@ -235,6 +235,11 @@ int bnv_mppi_kernel_time(bnv_mppi* h, double* total_ms, uint64_t* launches);
  * see mppi_kernels.cuh BNV_STAMP).  Only recorded when the handle was created with BNV_DEBUG_TS set. */
 int bnv_debug_timestamps(bnv_mppi* h, long long out[16]);
 
+/* Test hook: the raw Philox4x32-10 block function behind the engine's noise stream, for known-answer tests
+ * (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3", SC'11; Random123 kat_vectors).
+ * in_dev [n][6] = (counter x, y, z, w, key lo, key hi) -> out_dev [n][4]. */
+int bnv_debug_philox(const uint32_t* in_dev, uint32_t* out_dev, int32_t n, void* stream);
+
 /* Test hook: evaluates the engine's in-range sin/cos (used by the state update in place of
  * torch.cos/torch.sin, robot_model.py:86-87) on n device floats. */
 int bnv_debug_sincos(const float* theta_dev, float* sin_dev, float* cos_dev, int32_t n, void* stream);

@@ -90,3 +90,10 @@ def test_product_code_never_imports_the_oracle_or_the_reference():
         for line in open(path):
             if line.lstrip().startswith("#include"):
                 assert "oracle" not in line.lower() and "reference" not in line.lower(), (path, line)
+
+
+def test_python_restatement_of_philox_matches_the_published_known_answers():
+    from tests.helpers import PHILOX_KAT, philox4x32_10
+
+    for counter, key, want in PHILOX_KAT:
+        assert philox4x32_10(counter, key) == want

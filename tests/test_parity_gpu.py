@@ -413,3 +413,36 @@ def test_error_behaviour():
     h = C.c_void_p()
     cfg = _cabi.MppiCfg(num_samples=0, horizon=5, world_size=1)
     assert lib.bnv_mppi_create(C.byref(h), C.byref(cfg)) == -1 and b"num_samples" in lib.bnv_last_error()
+
+
+def test_philox_known_answers_and_noise_stream_definition():
+    """The generator behind the in-kernel noise is Philox4x32-10: Random123's known-answer vectors through the device
+    function, random blocks against the plain-Python restatement, and the solver's drawn noise recomputed from the
+    stream's definition (counter = (sample, step pair, iteration), key = seed, Box-Muller) on the host."""
+    from benchnav_b200 import _cabi
+    from tests.helpers import PHILOX_KAT, engine_noise_pair, philox4x32_10
+
+    lib = _cabi.load()
+    rng = np.random.default_rng(3)
+    rows = [list(c) + list(k) for c, k, _ in PHILOX_KAT] + rng.integers(0, 2 ** 32, size=(61, 6)).tolist()
+    inp = torch.tensor(np.array(rows, dtype=np.uint32).view(np.int32), device="cuda")
+    out = torch.empty(len(rows), 4, dtype=torch.int32, device="cuda")
+    _cabi.check(lib.bnv_debug_philox(inp.data_ptr(), out.data_ptr(), len(rows), None))
+    got = out.cpu().numpy().view(np.uint32)
+    for i, row in enumerate(rows):
+        assert tuple(int(x) for x in got[i]) == philox4x32_10(row[:4], row[4:]), i
+    for i, (_, _, want) in enumerate(PHILOX_KAT):
+        assert tuple(int(x) for x in got[i]) == want
+
+    K, T, seed, sig = 300, 9, 0x1234567890ABCDEF % (2 ** 63), (0.5, 0.8)
+    risk = torch.rand(32, 32, generator=torch.Generator().manual_seed(1)) * 0.5
+    solver = make_solver(risk, 0.5, [10.0, 10.0], 0.3, K, T, list(sig), 0.5, seed=seed)
+    for it in range(2):
+        solver.forward(torch.tensor([4.0, 4.0, 0.3]))
+        noise = solver._action_noises.cpu().numpy()
+        for k in (0, 1, 137, K - 1):
+            for p in range((T + 1) // 2):
+                want = engine_noise_pair(k, p, it, seed, *sig)
+                np.testing.assert_allclose(noise[k, 2 * p], want[:2], rtol=0, atol=2e-5)
+                if 2 * p + 1 < T:
+                    np.testing.assert_allclose(noise[k, 2 * p + 1], want[2:], rtol=0, atol=2e-5)
