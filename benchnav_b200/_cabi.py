@@ -94,6 +94,7 @@ _SIGNATURES = {
     "bnv_mppi_draw_noise": (C.c_int, [_VP, C.c_uint64, _VP]),
     "bnv_mppi_draw_xi": (C.c_int, [_VP, C.c_uint64, _VP, _VP, _VP]),
     "bnv_mppi_device_counter": (C.c_int, [_VP, C.c_int32, _VP]),
+    "bnv_mppi_prelaunch": (C.c_int, [_VP, C.c_int32, C.c_uint32]),
     "bnv_mppi_set_keep_mean": (C.c_int, [_VP, C.c_int32]),
     "bnv_mppi_set_terminal_goal": (C.c_int, [_VP, _FP]),
     "bnv_mppi_set_goal_dev": (C.c_int, [_VP, _VP]),

@@ -6,6 +6,8 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <time.h>
+
 #include <algorithm>
 #include <atomic>
 #include <cmath>
@@ -111,6 +113,17 @@ struct bnv_mppi {
   float* io_host = nullptr;  // pinned mirror of io_dev
   float* io_host_dev = nullptr;  // its device-side address (zero-copy)
   unsigned long long* iter_dev = nullptr;  // device-resident iteration counter (graph-capturable launches)
+  // pre-launched iterations of forward_host (bnv_mppi_prelaunch)
+  bool pre_enabled = false, pre_pending = false;
+  cudaStream_t pre_stream = nullptr;        // internal stream of the pre-launched kernels
+  unsigned int* pre_host = nullptr;         // pinned + mapped: [2 slots][4] {x, y, theta, seq}, [8] abort word
+  unsigned int* pre_host_dev = nullptr;     // its device-side address
+  unsigned int* pre_decision = nullptr;     // device word: the grid-wide go / abort decision of the pending launch
+  unsigned int pre_seq = 0;                 // sequence number of the pending launch
+  unsigned int pre_epoch = 0;               // its epoch (value of the completion / abort words)
+  unsigned int pre_timeout_us = 2000;
+  bool user_work = false;                   // work was queued on a caller's stream since the last pre-launched step
+  cudaStream_t user_stream = nullptr;
   int grid = 0, warps = 0;
   long long resident_ctas = 0;  // how many rollout CTAs the device can hold at once (cooperative-launch bound)
   bool fast_angles = false;
@@ -127,6 +140,9 @@ void free_all(bnv_mppi* h) {
   cudaFree(h->tau);
   cudaFree(h->goals_dev);
   cudaFree(h->iter_dev);
+  cudaFree(h->pre_decision);
+  if (h->pre_host) cudaFreeHost(h->pre_host);
+  if (h->pre_stream) cudaStreamDestroy(h->pre_stream);
   cudaFree(h->noise);
   cudaFree(h->rec);
   cudaFree(h->costs);
@@ -246,6 +262,33 @@ int configure_launch(bnv_mppi* h) {
 
 }  // namespace
 
+struct PreStats {
+  double t_sync = 0, t_post = 0, t_launch = 0, t_wait = 0;
+  long calls = 0, posted = 0, fallbacks = 0, retries = 0;
+};
+static PreStats g_pre_stats;
+static double now_us() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
+}
+
+extern "C" {
+static int drain_prelaunch(bnv_mppi* h);
+}
+// Every entry point that touches the solver outside forward_host first cancels a pre-launched iteration that is still
+// waiting for its state, and remembers that work now sits on the caller's stream.
+#define BNV_DRAIN(h)                   \
+  do {                                 \
+    int rc__ = drain_prelaunch(h);     \
+    if (rc__ != BNV_OK) return rc__;   \
+  } while (0)
+#define BNV_USER_WORK(h, s)                        \
+  do {                                             \
+    (h)->user_work = true;                         \
+    (h)->user_stream = static_cast<cudaStream_t>(s); \
+  } while (0)
+
 extern "C" {
 
 int bnv_abi_version(void) { return BNV_ABI_VERSION; }
@@ -346,6 +389,9 @@ int bnv_mppi_create(bnv_mppi** out, const bnv_mppi_cfg* cfg) {
   P.keep_mean = 1;
   P.done_flag = nullptr;
   P.iter_dev = nullptr;
+  P.state_mailbox = nullptr;
+  P.prelaunch_decision = nullptr;
+  P.abort_flag = nullptr;
   P.xi_in = nullptr;
   P.xi_opt_in = nullptr;
   P.Kl = Kl;
@@ -377,6 +423,7 @@ int bnv_mppi_create(bnv_mppi** out, const bnv_mppi_cfg* cfg) {
 void bnv_mppi_destroy(bnv_mppi* h) {
   if (!h) return;
   cudaSetDevice(h->cfg.device);
+  drain_prelaunch(h);
   cudaDeviceSynchronize();
   free_all(h);
   delete h;
@@ -403,6 +450,8 @@ int bnv_mppi_set_problem_ex(bnv_mppi* h, const float* mean_dev, const float* std
   if (!(x_min < x_max) || !(y_min < y_max)) return fail(BNV_ERR_INVALID, "empty map limits");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   BNV_CUDA(cudaSetDevice(h->cfg.device));
+  BNV_DRAIN(h);
+  BNV_USER_WORK(h, stream);
   bnv::EngineParams& P = h->P;
   const int G = grid_size, E = h->E;
   const int cell = h->stoch ? 2 : 1;
@@ -480,7 +529,7 @@ int bnv_mppi_set_problem_ex(bnv_mppi* h, const float* mean_dev, const float* std
 
 static int launch_forward(bnv_mppi* h, const float* state_dev, const float* state_host, const float* noise_dev,
                           float* u_out_dev, float* opt_states_dev, cudaStream_t s, const float* xi_dev = nullptr,
-                          const float* xi_opt_dev = nullptr) {
+                          const float* xi_opt_dev = nullptr, unsigned int mailbox_seq = 0) {
   if (state_host && h->E > 1) return fail(BNV_ERR_INVALID, "batched solver: states must be device-resident [E,3]");
   if (state_host) {  // state travels by value in the launch packet; remembered for finalize (world_size > 1)
     for (int i = 0; i < 3; ++i) h->P.state_val[i] = state_host[i];
@@ -504,6 +553,14 @@ static int launch_forward(bnv_mppi* h, const float* state_dev, const float* stat
   h->P.state = state_dev;  // finalize (world_size > 1) re-reads the state of the iteration in flight
   P.u_out = u_out_dev;
   P.opt_rec = opt_states_dev;
+  if (mailbox_seq != 0u) {  // pre-launched: the state arrives later through the host-mapped mailbox
+    P.state_mailbox = h->pre_host_dev;
+    P.mailbox_seq = mailbox_seq;
+    P.mailbox_timeout_us = h->pre_timeout_us;
+    P.prelaunch_decision = h->pre_decision;
+    P.abort_flag = h->pre_host_dev + 8;
+    BNV_CUDA(cudaMemsetAsync(h->pre_decision, 0, sizeof(unsigned int), s));
+  }
   // The grid is co-resident iff it has at most resident_ctas CTAs (occupancy x SMs; one CTA per SM at long
   // horizons).  Then launch cooperatively (residency guaranteed by the driver) and use the deferred-store epilogue.
   const bool coop = h->coop_ok && static_cast<long long>(h->grid) * h->E <= h->resident_ctas;
@@ -544,6 +601,47 @@ static int launch_forward(bnv_mppi* h, const float* state_dev, const float* stat
   return BNV_OK;
 }
 
+// Cancel a pre-launched iteration that is still waiting for its state (every entry point that touches the solver
+// outside forward_host calls this first): mark its mailbox slot, wait for the launch to abort, and give back the
+// iteration number it had taken, so that the noise stream is the same as without pre-launching.
+static int drain_prelaunch(bnv_mppi* h) {
+  if (!h->pre_pending) return BNV_OK;
+  volatile unsigned int* slot = h->pre_host + 4u * (h->pre_seq & 1u);
+  slot[3] = 0xFFFFFFFFu;
+  std::atomic_thread_fence(std::memory_order_seq_cst);
+  BNV_CUDA(cudaStreamSynchronize(h->pre_stream));
+  h->pre_pending = false;
+  if (h->iteration > 0) h->iteration--;
+  return BNV_OK;
+}
+int bnv_mppi_prelaunch(bnv_mppi* h, int32_t enable, uint32_t timeout_us) {
+  if (!h) return fail(BNV_ERR_INVALID, "null argument");
+  if (h->cfg.world_size != 1 || h->E != 1) return fail(BNV_ERR_INVALID, "pre-launching needs a single, unsharded solver");
+  BNV_CUDA(cudaSetDevice(h->cfg.device));
+  BNV_DRAIN(h);
+  if (enable) {
+    if (!h->pre_stream) BNV_CUDA(cudaStreamCreateWithFlags(&h->pre_stream, cudaStreamNonBlocking));
+    if (!h->pre_host) {
+      BNV_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h->pre_host), 16 * sizeof(unsigned int), cudaHostAllocMapped));
+      std::memset(h->pre_host, 0, 16 * sizeof(unsigned int));
+      BNV_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->pre_host_dev), h->pre_host, 0));
+    }
+    if (!h->pre_decision) BNV_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->pre_decision), 8 * sizeof(unsigned int)));
+    h->pre_timeout_us = timeout_us ? timeout_us : 2000u;
+  } else if (h->pre_stream) {
+    BNV_CUDA(cudaStreamSynchronize(h->pre_stream));
+  }
+  h->pre_enabled = enable != 0;
+  if (!enable && std::getenv("BNV_DEBUG_PRE") && g_pre_stats.calls > 0) {
+    const PreStats& p = g_pre_stats;
+    std::fprintf(stderr, "[bnv prelaunch] calls %ld posted %ld fallbacks %ld retries %ld | per call us: sync %.2f post/plain %.2f "
+                 "launch-next %.2f wait %.2f\n", p.calls, p.posted, p.fallbacks, p.retries, p.t_sync / p.calls,
+                 p.t_post / p.calls, p.t_launch / p.calls, p.t_wait / p.calls);
+    g_pre_stats = PreStats();
+  }
+  return BNV_OK;
+}
+
 int bnv_mppi_forward(bnv_mppi* h, const float* state_dev, const float* noise_dev, float* u_out_dev,
                      float* opt_states_dev, void* stream) {
   if (!h || !state_dev) return fail(BNV_ERR_INVALID, "null argument");
@@ -552,6 +650,8 @@ int bnv_mppi_forward(bnv_mppi* h, const float* state_dev, const float* noise_dev
     return fail(BNV_ERR_INVALID, "null output buffer");
   if (h->stoch && noise_dev) return fail(BNV_ERR_INVALID, "stochastic-slip solver: inject noise through bnv_mppi_forward_ex");
   BNV_CUDA(cudaSetDevice(h->cfg.device));
+  BNV_DRAIN(h);
+  BNV_USER_WORK(h, stream);
   return launch_forward(h, state_dev, nullptr, noise_dev, u_out_dev, opt_states_dev, static_cast<cudaStream_t>(stream));
 }
 
@@ -566,6 +666,8 @@ int bnv_mppi_forward_ex(bnv_mppi* h, const float* state_dev, const float* noise_
     return fail(BNV_ERR_INVALID, "lookup normals given to a deterministic solver");
   }
   BNV_CUDA(cudaSetDevice(h->cfg.device));
+  BNV_DRAIN(h);
+  BNV_USER_WORK(h, stream);
   return launch_forward(h, state_dev, nullptr, noise_dev, u_out_dev, opt_states_dev, static_cast<cudaStream_t>(stream),
                         xi_dev, xi_opt_dev);
 }
@@ -577,7 +679,122 @@ int bnv_mppi_forward_state(bnv_mppi* h, const float state_host[3], const float* 
   if ((h->cfg.world_size == 1 || h->peers_attached) && (!u_out_dev || !opt_states_dev))
     return fail(BNV_ERR_INVALID, "null output buffer");
   BNV_CUDA(cudaSetDevice(h->cfg.device));
+  BNV_DRAIN(h);
+  BNV_USER_WORK(h, stream);
   return launch_forward(h, nullptr, state_host, noise_dev, u_out_dev, opt_states_dev, static_cast<cudaStream_t>(stream));
+}
+
+// Spin on the completion word of launch `epoch` (and, for a pre-launched one, on its abort word).  Returns 1 when the
+// results are in the staging buffer, 0 when the launch aborted, negative on error.
+static int wait_host_results(bnv_mppi* h, cudaStream_t s, unsigned int epoch, bool may_abort) {
+  const int T = h->P.T;
+  const size_t flag_off = 3 + 2 * static_cast<size_t>(T) + 3 * static_cast<size_t>(T + 1);
+  volatile unsigned int* flag = reinterpret_cast<volatile unsigned int*>(h->io_host + flag_off);
+  volatile unsigned int* aborted = h->pre_host ? h->pre_host + 8 : nullptr;
+  bool seen = false;
+  for (long spins = 0; spins < 50000000L; ++spins) {  // a fault or a stuck device ends in the synchronise below
+    if (*flag == epoch) {
+      seen = true;
+      break;
+    }
+    if (may_abort && *aborted == epoch) return 0;
+    // a rare liveness check (about once a millisecond): a stream query costs a microsecond or two, which must not
+    // land inside the ~20 us the kernel normally takes
+    if ((spins & 0xFFFF) == 0xFFFF && !may_abort && cudaStreamQuery(s) != cudaErrorNotReady) break;
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#endif
+  }
+  if (!seen) {
+    BNV_CUDA(cudaStreamSynchronize(s));
+    if (*flag != epoch) return (may_abort && *aborted == epoch) ? 0 : fail(BNV_ERR_CUDA, "the iteration did not complete");
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  return 1;
+}
+
+// forward_host with pre-launching (bnv_mppi_prelaunch): every call posts its state to the kernel that the PREVIOUS call
+// queued -- already resident, its prologue done, polling the host-mapped mailbox -- and queues the next iteration's
+// kernel behind it before waiting, so that neither the launch call nor the launch latency is on the step's critical
+// path.  A launch whose state does not arrive within the timeout aborts itself (every CTA follows one grid-wide
+// decision) and the step falls back to a plain launch; iteration numbers are given back, so the noise stream is the
+// one of the plain path.
+static int forward_host_prelaunched(bnv_mppi* h, const float state_host[3], float* u_out_host, float* opt_states_host,
+                                    int depth) {
+  const int T = h->P.T;
+  const double t_a = now_us();
+  g_pre_stats.calls++;
+  cudaStream_t ps = h->pre_stream;
+  if (h->user_work) {  // order the internal stream after whatever the caller queued on its own stream
+    BNV_CUDA(cudaStreamSynchronize(h->user_stream));
+    h->user_work = false;
+  }
+  if (!h->io_host_dev) BNV_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->io_host_dev), h->io_host, 0));
+  float* out_dev = h->io_host_dev;
+  const size_t flag_off = 3 + 2 * static_cast<size_t>(T) + 3 * static_cast<size_t>(T + 1);
+  volatile unsigned int* aborted = h->pre_host + 8;
+  unsigned int cur_epoch = 0;
+  bool posted = false;
+  if (h->pre_pending && *aborted == h->pre_epoch) {  // the waiting launch timed out before this call
+    BNV_CUDA(cudaStreamSynchronize(ps));
+    h->pre_pending = false;
+    if (h->iteration > 0) h->iteration--;
+    g_pre_stats.fallbacks++;
+  }
+  const double t_b = now_us();
+  h->P.done_flag = reinterpret_cast<unsigned int*>(out_dev + flag_off);
+  if (h->pre_pending) {
+    volatile unsigned int* slot = h->pre_host + 4u * (h->pre_seq & 1u);
+    unsigned int bits[3];
+    std::memcpy(bits, state_host, sizeof(bits));
+    slot[0] = bits[0];
+    slot[1] = bits[1];
+    slot[2] = bits[2];
+    std::atomic_thread_fence(std::memory_order_release);
+    slot[3] = h->pre_seq;
+    cur_epoch = h->pre_epoch;
+    posted = true;
+    g_pre_stats.posted++;
+  } else {
+    int rc = launch_forward(h, nullptr, state_host, nullptr, out_dev + 3, out_dev + 3 + 2 * T, ps);
+    if (rc != BNV_OK) {
+      h->P.done_flag = nullptr;
+      return rc;
+    }
+    cur_epoch = h->epoch;
+  }
+  const double t_c = now_us();
+  // queue the next iteration behind the current one
+  unsigned int next_seq = h->pre_seq + 1u;
+  if (next_seq == 0u || next_seq == 0xFFFFFFFFu) next_seq = 1u;
+  h->pre_host[4u * (next_seq & 1u) + 3u] = 0u;  // the slot last carried the sequence number before the previous one
+  std::atomic_thread_fence(std::memory_order_seq_cst);
+  int rc = launch_forward(h, nullptr, nullptr, nullptr, out_dev + 3, out_dev + 3 + 2 * T, ps, nullptr, nullptr, next_seq);
+  h->P.done_flag = nullptr;
+  if (rc != BNV_OK) return rc;
+  h->pre_seq = next_seq;
+  h->pre_epoch = h->epoch;
+  h->pre_pending = true;
+  const double t_d = now_us();
+  const int got = wait_host_results(h, ps, cur_epoch, posted);
+  const double t_e = now_us();
+  g_pre_stats.t_sync += t_b - t_a;
+  g_pre_stats.t_post += t_c - t_b;
+  g_pre_stats.t_launch += t_d - t_c;
+  g_pre_stats.t_wait += t_e - t_d;
+  if (got < 0) return got;
+  if (got == 0) {
+    // the posted launch aborted in the same instant: cancel the queued one, give both iteration numbers back, retry
+    g_pre_stats.retries++;
+    if (depth > 2) return fail(BNV_ERR_CUDA, "pre-launched iterations keep aborting");
+    rc = drain_prelaunch(h);
+    if (rc != BNV_OK) return rc;
+    if (h->iteration > 0) h->iteration--;
+    return forward_host_prelaunched(h, state_host, u_out_host, opt_states_host, depth + 1);
+  }
+  std::memcpy(u_out_host, h->io_host + 3, 2 * static_cast<size_t>(T) * sizeof(float));
+  std::memcpy(opt_states_host, h->io_host + 3 + 2 * T, 3 * static_cast<size_t>(T + 1) * sizeof(float));
+  return BNV_OK;
 }
 
 int bnv_mppi_forward_host(bnv_mppi* h, const float state_host[3], const float* noise_dev, float* u_out_host,
@@ -588,36 +805,25 @@ int bnv_mppi_forward_host(bnv_mppi* h, const float state_host[3], const float* n
   if (h->stoch && noise_dev) return fail(BNV_ERR_INVALID, "stochastic-slip solver: inject noise through bnv_mppi_forward_ex");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   BNV_CUDA(cudaSetDevice(h->cfg.device));
+  if (h->pre_enabled && !noise_dev && !h->iter_dev)
+    return forward_host_prelaunched(h, state_host, u_out_host, opt_states_host, 0);
+  BNV_DRAIN(h);
   const int T = h->P.T;
   // Host -> device: the 12-byte state rides in the kernel's launch packet.  Device -> host: the kernel stores u* and
   // the optimal state sequence straight into the handle's pinned, device-mapped staging buffer (zero-copy over
-  // PCIe); one stream synchronisation makes them visible, then they are copied out to the caller's buffers.
+  // PCIe) and raises a completion word as soon as both are written (before its tail: slab stores draining, CTAs
+  // exiting); the host polls that word instead of paying a stream synchronisation.
   if (!h->io_host_dev) BNV_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->io_host_dev), h->io_host, 0));
   float* out_dev = h->io_host_dev;
-  // Completion: the kernel raises a word in the same pinned buffer as soon as both results are written (before its
-  // tail: slab stores draining, CTAs exiting); the host polls it instead of paying a stream synchronisation.
   const size_t flag_off = 3 + 2 * static_cast<size_t>(T) + 3 * static_cast<size_t>(T + 1);
-  volatile unsigned int* flag = reinterpret_cast<volatile unsigned int*>(h->io_host + flag_off);
   h->P.done_flag = reinterpret_cast<unsigned int*>(out_dev + flag_off);
   int rc = launch_forward(h, nullptr, state_host, noise_dev, out_dev + 3, out_dev + 3 + 2 * T, s);
   h->P.done_flag = nullptr;
   if (rc != BNV_OK) return rc;
-  const unsigned int want = h->epoch;
-  bool seen = false;
-  for (long spins = 0; spins < 50000000L; ++spins) {  // a fault or a stuck device ends in the synchronise below
-    if (*flag == want) {
-      seen = true;
-      break;
-    }
-    // a rare liveness check (about once a millisecond): a stream query costs a microsecond or two, which must not
-    // land inside the ~20 us the kernel normally takes
-    if ((spins & 0xFFFF) == 0xFFFF && cudaStreamQuery(s) != cudaErrorNotReady) break;
-#if defined(__x86_64__) || defined(__i386__)
-    __builtin_ia32_pause();
-#endif
-  }
-  if (!seen) BNV_CUDA(cudaStreamSynchronize(s));
-  std::atomic_thread_fence(std::memory_order_acquire);
+  h->user_work = true;
+  h->user_stream = s;
+  const int got = wait_host_results(h, s, h->epoch, false);
+  if (got < 0) return got;
   std::memcpy(u_out_host, h->io_host + 3, 2 * static_cast<size_t>(T) * sizeof(float));
   std::memcpy(opt_states_host, h->io_host + 3 + 2 * T, 3 * static_cast<size_t>(T + 1) * sizeof(float));
   return BNV_OK;
@@ -690,6 +896,8 @@ int bnv_mppi_top_samples(bnv_mppi* h, int32_t n, float* states_out_dev, float* w
   if (n < 1 || n > h->Kl) return fail(BNV_ERR_INVALID, "num_samples %d outside [1, %d]", n, h->Kl);  // mppi.py:229
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   BNV_CUDA(cudaSetDevice(h->cfg.device));
+  BNV_DRAIN(h);
+  BNV_USER_WORK(h, stream);
   int n_pad = 1;
   while (n_pad < n) n_pad <<= 1;
   const size_t nE = static_cast<size_t>(h->E);
@@ -735,6 +943,8 @@ int32_t bnv_mppi_sample_offset(const bnv_mppi* h) { return h ? h->k_offset : 0; 
 int bnv_mppi_reset(bnv_mppi* h, void* stream) {
   if (!h) return fail(BNV_ERR_INVALID, "null argument");
   BNV_CUDA(cudaSetDevice(h->cfg.device));
+  BNV_DRAIN(h);
+  BNV_USER_WORK(h, stream);
   BNV_CUDA(cudaMemsetAsync(h->u_prev, 0, sizeof(float) * h->E * h->P.T * 2, static_cast<cudaStream_t>(stream)));
   h->iteration = 0;
   if (h->iter_dev) BNV_CUDA(cudaMemsetAsync(h->iter_dev, 0, sizeof(unsigned long long), static_cast<cudaStream_t>(stream)));
@@ -745,6 +955,8 @@ int bnv_mppi_reset(bnv_mppi* h, void* stream) {
 int bnv_mppi_draw_noise(bnv_mppi* h, uint64_t iteration, void* stream) {
   if (!h) return fail(BNV_ERR_INVALID, "null argument");
   BNV_CUDA(cudaSetDevice(h->cfg.device));
+  BNV_DRAIN(h);
+  BNV_USER_WORK(h, stream);
   const int T = h->P.T;
   const long long work = static_cast<long long>(h->Kl) * ((T + 1) / 2);
   const int blocks = static_cast<int>((work + 255) / 256);
@@ -760,6 +972,8 @@ int bnv_mppi_draw_xi(bnv_mppi* h, uint64_t iteration, float* xi_out_dev, float* 
   if (!h || !xi_out_dev || !xi_opt_out_dev) return fail(BNV_ERR_INVALID, "null argument");
   if (!h->stoch) return fail(BNV_ERR_STATE, "not a stochastic-slip solver");
   BNV_CUDA(cudaSetDevice(h->cfg.device));
+  BNV_DRAIN(h);
+  BNV_USER_WORK(h, stream);
   const int T = h->P.T;
   const long long work = static_cast<long long>(h->Kl + 1) * ((T + 1) / 2);
   const int blocks = static_cast<int>((work + 255) / 256);
@@ -776,6 +990,7 @@ int bnv_mppi_device_counter(bnv_mppi* h, int32_t enable, void* stream) {
   if (h->cfg.world_size != 1) return fail(BNV_ERR_INVALID, "graph-capturable launches need world_size == 1");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   BNV_CUDA(cudaSetDevice(h->cfg.device));
+  BNV_DRAIN(h);
   if (enable) {
     if (!h->iter_dev) BNV_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->iter_dev), sizeof(unsigned long long)));
     const unsigned long long it = h->iteration;
@@ -822,6 +1037,8 @@ int bnv_mppi_argmin(bnv_mppi* h, const float* actions_dev, float* action_out_dev
   if (!h->P.record) return fail(BNV_ERR_STATE, "argmin needs BNV_FLAG_RECORD_STATES");
   if (!h->have_weights || h->E > 1) return fail(BNV_ERR_STATE, "argmin needs a completed forward of a single solver");
   BNV_CUDA(cudaSetDevice(h->cfg.device));
+  BNV_DRAIN(h);
+  BNV_USER_WORK(h, stream);
   int rc = bnv_launch_argmin(h->costs, h->Kl, actions_dev, h->rec, 3 * (h->P.T + 1), action_out_dev, states_out_dev,
                              index_out_dev, static_cast<cudaStream_t>(stream));
   if (rc == BNV_OK) h->launches++;
@@ -835,6 +1052,8 @@ int bnv_mppi_dwa_subgoal(bnv_mppi* h, const float* path_dev, int32_t n, const fl
   if (!h->problem_set) return fail(BNV_ERR_STATE, "bnv_mppi_set_problem must be called first");
   if (h->stoch || h->E > 1) return fail(BNV_ERR_INVALID, "needs a deterministic single solver");
   BNV_CUDA(cudaSetDevice(h->cfg.device));
+  BNV_DRAIN(h);
+  BNV_USER_WORK(h, stream);
   int rc = bnv_launch_dwa_subgoal(h->P.geom, h->P.G, h->tau, h->P.pitch, h->P.bounds, actions_dev, path_dev, n, state_dev,
                                   lookahead_distance, goal_out_dev, static_cast<cudaStream_t>(stream));
   if (rc == BNV_OK) h->launches++;

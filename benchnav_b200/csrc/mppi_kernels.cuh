@@ -81,6 +81,13 @@ struct alignas(64) EngineParams {
                                        // epoch = low word + 1, and bump_iteration_kernel advances it after the launch
   unsigned int* done_flag;  // optional, mapped HOST memory: set to `epoch` once u_out / opt_rec are complete, so that a
                             // host thread polling it sees the results without waiting for the kernel's tail
+  // pre-launched iterations (bnv_mppi_prelaunch): the kernel is already resident when the state arrives.  It polls a
+  // host-mapped slot {x, y, theta, sequence number} and every CTA follows one grid-wide decision (go / abort):
+  const unsigned int* state_mailbox;   // mapped host memory, [2 slots][4 words]; null = state from P.state / P.state_val
+  unsigned int mailbox_seq;            // sequence number this launch waits for (slot = seq & 1)
+  unsigned int mailbox_timeout_us;     // give up (abort the launch) when no state arrives for this long
+  unsigned int* prelaunch_decision;    // device word, zeroed before the launch: 0 undecided, 1 go, 2 abort
+  unsigned int* abort_flag;            // mapped host word: set to `epoch` when the launch aborted
   int keep_mean;         // write u* back as the next call's mean sequence (mppi.py:217); 0 for DWA's constant actions
   int coop;              // grid is co-resident (cooperative launch): deferred slab stores, in-register weights
   float* const* peer_mbox;  // [world] device pointers to every rank's mailbox (peer memory over NVLink), or null
@@ -573,10 +580,68 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
   const bool valid = lane < warp_rows;
 
   // the state (a cold load when it lives in HBM) is requested first: its latency runs under the barrier set-up
-  const float* state_e = P.state + 3 * env;
-  const float sx = P.state_inline ? P.state_val[0] : __ldg(state_e);
-  const float sy = P.state_inline ? P.state_val[1] : __ldg(state_e + 1);
-  const float sth = P.state_inline ? P.state_val[2] : __ldg(state_e + 2);
+  float sx, sy, sth;
+  if (P.state_mailbox != nullptr) {
+    // Pre-launched iteration.  ONE thread of the grid (CTA 0) polls the host-mapped slot over PCIe until it carries
+    // this launch's sequence number (measured: 128 CTAs polling host memory serialise at ~1 us per read), then
+    // publishes the state and the decision "go" in device memory; a cancel mark or a timeout publishes "abort".
+    // Every other CTA polls the decision word in L2.
+    unsigned int* box_s = reinterpret_cast<unsigned int*>(smem + 96);
+    if (tid == 0) {
+      unsigned int decision = 0u, w0 = 0u, w1 = 0u, w2 = 0u, w3 = 0u;
+      unsigned int* dec = P.prelaunch_decision;  // [0] decision, [4..6] state words
+      if (blockIdx.x == 0 && blockIdx.y == 0) {
+        const unsigned int* slot = P.state_mailbox + 4u * (P.mailbox_seq & 1u);
+        unsigned long long t0, now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        const unsigned long long limit = static_cast<unsigned long long>(P.mailbox_timeout_us) * 1000ull;
+        for (;;) {
+          asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                       : "l"(slot)
+                       : "memory");
+          if (w3 == P.mailbox_seq) {
+            decision = 1u;
+            break;
+          }
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+          if (w3 == 0xFFFFFFFFu || now - t0 > limit) {
+            decision = 2u;
+            break;
+          }
+        }
+        if (decision == 1u) {
+          dec[4] = w0;
+          dec[5] = w1;
+          dec[6] = w2;
+        } else {
+          asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(P.abort_flag), "r"(P.epoch) : "memory");
+        }
+        st_release_gpu(dec, decision);
+      } else {
+        while ((decision = ld_acquire_gpu(dec)) == 0u) __nanosleep(100);
+        if (decision == 1u) {
+          w0 = __ldcg(dec + 4);
+          w1 = __ldcg(dec + 5);
+          w2 = __ldcg(dec + 6);
+        }
+      }
+      box_s[0] = w0;
+      box_s[1] = w1;
+      box_s[2] = w2;
+      box_s[3] = (decision == 1u) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (box_s[3] == 0u) return;  // aborted launch: nothing was touched
+    sx = __uint_as_float(box_s[0]);
+    sy = __uint_as_float(box_s[1]);
+    sth = __uint_as_float(box_s[2]);
+  } else {
+    const float* state_e = P.state + 3 * env;
+    sx = P.state_inline ? P.state_val[0] : __ldg(state_e);
+    sy = P.state_inline ? P.state_val[1] : __ldg(state_e + 1);
+    sth = P.state_inline ? P.state_val[2] : __ldg(state_e + 2);
+  }
   if (tid == 0) {
     mbar_init(bar_patch, 1);
     for (int w = 0; w < kMaxWarps; ++w) mbar_init(bar_noise + w, 1);

@@ -362,6 +362,13 @@ class MPPI(nn.Module):
         """Zero the mean sequence and restart the engine's noise stream (a freshly built solver)."""
         _cabi.check(self._lib.bnv_mppi_reset(self._handle, self._stream()))
 
+    def prelaunch(self, enable: bool = True, timeout_us: int = 2000) -> None:
+        """Pre-launch the next iteration's kernel from every ``forward_host`` call (``bnv_mppi_prelaunch``): the kernel is
+        resident and polling a host-mapped mailbox when the next state arrives, which takes the launch call and the
+        launch latency off the control loop's critical path.  Results are identical to the plain path."""
+        with torch.cuda.device(self._device):
+            _cabi.check(self._lib.bnv_mppi_prelaunch(self._handle, 1 if enable else 0, int(timeout_us)))
+
     def graph_capturable(self, enable: bool = True) -> None:
         """Keep the iteration counter (Philox counter word, launch epoch) in device memory so that ``forward`` can be
         captured in a CUDA graph (``torch.cuda.graph``) and replayed: one graph launch per control step."""

@@ -194,6 +194,18 @@ int bnv_mppi_draw_xi(bnv_mppi* h, uint64_t iteration, float* xi_out_dev, float* 
  * the count.  Synchronises `stream`; world_size must be 1; bnv_mppi_forward_host is not capturable. */
 int bnv_mppi_device_counter(bnv_mppi* h, int32_t enable, void* stream);
 
+/* Pre-launched iterations for the host-buffer call.  With enable != 0, bnv_mppi_forward_host queues the NEXT
+ * iteration's kernel (on an internal stream) before it waits for the current one; that kernel becomes resident as soon
+ * as the current one finishes, does its prologue and polls a host-mapped {state, sequence} word -- so the following
+ * bnv_mppi_forward_host call is a 16-byte store plus the completion poll: neither the launch call nor the launch
+ * latency is on the step's critical path.  A pre-launched kernel whose state does not arrive within `timeout_us`
+ * (0 = 2000) aborts itself (all CTAs follow one grid-wide decision) and the step falls back to a plain launch;
+ * every other entry point cancels a waiting launch first.  Iteration numbers of cancelled / aborted launches are
+ * given back, so results are identical to the plain path.  While a launch waits it occupies its SMs: work the caller
+ * queues on other streams runs on the remaining ones, and a device-wide synchronisation lasts until the timeout.
+ * Engine-owned tensors (weights, recorded states, ...) are ordered for the caller's stream by any other entry point. */
+int bnv_mppi_prelaunch(bnv_mppi* h, int32_t enable, uint32_t timeout_us);
+
 /* ---- hooks used by the DWA planner built on the same rollout kernel (src/planners/local_planners/dwa.py) ----
  * DWA.forward (dwa.py:116-149) = the MPPI rollout/cost machinery with K = num_lin_vel * num_ang_vel constant
  * action sequences injected as "noise" around a zero mean (bnv_mppi_forward with noise_dev = the held actions),

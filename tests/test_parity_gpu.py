@@ -446,3 +446,40 @@ def test_philox_known_answers_and_noise_stream_definition():
                 np.testing.assert_allclose(noise[k, 2 * p], want[:2], rtol=0, atol=2e-5)
                 if 2 * p + 1 < T:
                     np.testing.assert_allclose(noise[k, 2 * p + 1], want[2:], rtol=0, atol=2e-5)
+
+
+def test_prelaunched_forward_host_matches_plain_path():
+    """bnv_mppi_prelaunch: every forward_host call queues the next iteration's kernel, which waits (resident) for its
+    state in a host-mapped mailbox.  Results must equal the plain path bit for bit -- also across a timed-out launch
+    (falls back to a plain launch, iteration number given back) and across calls that cancel the waiting launch."""
+    import time
+
+    from benchnav_b200.synthetic import benchmark_problem
+
+    risk, start, goal, thr = benchmark_problem(64, 0.5, seed=0)
+    K, T = 2048, 20
+    plain = make_solver(risk, 0.5, goal.tolist(), thr, K, T, [0.5, 0.5], 0.5, seed=5)
+    pre = make_solver(risk, 0.5, goal.tolist(), thr, K, T, [0.5, 0.5], 0.5, seed=5)
+    pre.prelaunch(True, timeout_us=3000)
+    state = start.clone()
+    out = (torch.empty(T, 2), torch.empty(1, T + 1, 3))
+    for step in range(12):
+        if step == 4:
+            time.sleep(0.02)  # the waiting launch times out and aborts: this step falls back to a plain launch
+        if step == 7:
+            ts, tw = pre.get_top_samples(8)  # any other entry point cancels the waiting launch first
+            ts_ref, tw_ref = plain.get_top_samples(8)
+            torch.cuda.synchronize()
+            assert torch.equal(tw, tw_ref) and torch.equal(ts, ts_ref)
+        u_ref, opt_ref = plain.forward_host(state)
+        u, opt = pre.forward_host(state, out=out)
+        assert torch.equal(u, u_ref), f"step {step}: controls differ"
+        assert torch.equal(opt, opt_ref), f"step {step}"
+        state = opt_ref[0, 1].clone()  # move on: every step posts a different state
+        state[2] = ((state[2] + np.pi) % (2 * np.pi)) - np.pi
+    pre.prelaunch(False)
+    u, opt = pre.forward_host(state)
+    u_ref, opt_ref = plain.forward_host(state)
+    assert torch.equal(u, u_ref)
+    torch.cuda.synchronize()
+    assert torch.equal(pre._weights, plain._weights) and torch.equal(pre._state_seq_batch, plain._state_seq_batch)
