@@ -290,9 +290,17 @@ def run_native(args) -> None:
 
         acc_plain = e2e_pass(n_e)
         # pre-launched iterations: the next kernel is already resident when the state arrives (bnv_mppi_prelaunch)
-        solver.prelaunch(True)
-        acc = e2e_pass(n_e)
-        solver.prelaunch(False)
+        e2e_mode = "pre-launched iterations"
+        try:
+            solver.prelaunch(True)
+            acc = e2e_pass(n_e)
+        except Exception as exc:  # keep the bench line: report the plain-launch path as the end-to-end number
+            acc, e2e_mode = acc_plain, f"plain launches (pre-launching failed: {exc})"
+        finally:
+            try:
+                solver.prelaunch(False)
+            except Exception:
+                pass
         # the reference-style call that allocates fresh result tensors every step, for comparison
         acc_alloc = 0.0
         for i in range(min(n_e, 500)):
@@ -303,7 +311,7 @@ def run_native(args) -> None:
             acc_alloc += time.perf_counter() - t0
         e2e = {"value": n_e / acc, "unit": UNIT, "h2d_bytes_per_step": 12,
                "d2h_bytes_per_step": 4 * (2 * HORIZON + 3 * (HORIZON + 1)), "steps": n_e,
-               "value_plain_launch": n_e / acc_plain,
+               "mode": e2e_mode, "value_plain_launch": n_e / acc_plain,
                "value_allocating_outputs": min(n_e, 500) / acc_alloc,
                "timing": "wall clock around forward_host(state, out=caller buffers) per step with pre-launched "
                          "iterations (solver.prelaunch(): the 12-byte state is posted to a pinned, device-mapped mailbox "
