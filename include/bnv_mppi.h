@@ -130,8 +130,10 @@ int bnv_mppi_forward_state(bnv_mppi* h, const float state_host[3], const float* 
 
 /* Same call with HOST buffers (the reference-facing form: `forward(state)` takes and returns tensors the
  * caller reads on the host).  Host->device: the state rides in the launch packet.  Device->host: the kernel
- * stores u_out/opt_states into pinned, device-mapped staging (zero-copy over PCIe); the call synchronises
- * `stream` and copies them to the caller's buffers.  world_size must be 1. */
+ * stores u_out/opt_states into pinned, device-mapped staging (zero-copy over PCIe) and raises a completion word
+ * there as soon as both are written; the call polls that word (falling back to a stream synchronisation if the
+ * device faults or stalls) and copies the results to the caller's buffers.  world_size must be 1.
+ * See bnv_mppi_prelaunch for the variant in which the kernel is already resident when the state arrives. */
 int bnv_mppi_forward_host(bnv_mppi* h, const float state_host[3], const float* noise_dev, float* u_out_host,
                           float* opt_states_host, void* stream);
 
@@ -196,7 +198,8 @@ int bnv_mppi_device_counter(bnv_mppi* h, int32_t enable, void* stream);
 
 /* Pre-launched iterations for the host-buffer call.  With enable != 0, bnv_mppi_forward_host queues the NEXT
  * iteration's kernel (on an internal stream) before it waits for the current one; that kernel becomes resident as soon
- * as the current one finishes, does its prologue and polls a host-mapped {state, sequence} word -- so the following
+ * as the current one finishes and polls a host-mapped {state, sequence} word (one thread over PCIe, broadcast to the
+ * other CTAs through device memory) -- so the following
  * bnv_mppi_forward_host call is a 16-byte store plus the completion poll: neither the launch call nor the launch
  * latency is on the step's critical path.  A pre-launched kernel whose state does not arrive within `timeout_us`
  * (0 = 2000) aborts itself (all CTAs follow one grid-wide decision) and the step falls back to a plain launch;
