@@ -11,6 +11,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import re
+import weakref
 from typing import List
 
 from . import build as _build
@@ -147,6 +148,35 @@ def load() -> C.CDLL:
         raise ImportError(f"ABI mismatch: library {lib.bnv_abi_version()} vs binding {ABI_VERSION}")
     _lib = lib
     return lib
+
+
+def _destroy_handle(lib, raw: C.c_void_p) -> None:
+    if raw.value:
+        lib.bnv_mppi_destroy(raw)
+        raw.value = None
+
+
+class SolverHandle:
+    """Owner of one ``bnv_mppi*`` (bnv_mppi_create / bnv_mppi_destroy).
+
+    The solver object and every zero-copy view of an engine buffer hold a reference to THIS object, never to the
+    solver, so there is no reference cycle through the C++ side of ``torch.as_tensor``: the handle is destroyed when
+    the last of them goes away, or at once through ``close()`` (afterwards every ABI call fails with "null argument").
+    ctypes passes the object wherever a ``bnv_mppi*`` is expected (``_as_parameter_``)."""
+
+    def __init__(self, lib: C.CDLL, cfg: "MppiCfg") -> None:
+        raw = C.c_void_p()
+        check(lib.bnv_mppi_create(C.byref(raw), C.byref(cfg)))
+        self._as_parameter_ = raw
+        self._finalizer = weakref.finalize(self, _destroy_handle, lib, raw)
+        self._finalizer.atexit = False  # at interpreter exit the CUDA context may already be gone
+
+    @property
+    def value(self):
+        return self._as_parameter_.value
+
+    def close(self) -> None:
+        self._finalizer()
 
 
 def make_grid(grid_size: int, pitch: int, resolution: float, x_limits, y_limits) -> Grid:

@@ -55,12 +55,11 @@ class BatchedMPPI(nn.Module):
         sig, lo, hi = (t.detach().cpu().to(torch.float32).tolist() for t in (sigmas, d0.min_action, d0.max_action))
         for i in range(2):
             cfg.sigma[i], cfg.u_min[i], cfg.u_max[i] = sig[i], lo[i], hi[i]
-        self._handle = C.c_void_p()
-        _cabi.check(self._lib.bnv_mppi_create(C.byref(self._handle), C.byref(cfg)))
+        self._handle = _cabi.SolverHandle(self._lib, cfg)
         self._geom = (g, res, x_lim, y_lim, thr)
         self.sync_problems()
         k, t = self._num_samples, self._horizon
-        view = lambda ptr, shape: torch.as_tensor(_DevView(ptr, shape, self), device=dev)  # noqa: E731
+        view = lambda ptr, shape: torch.as_tensor(_DevView(ptr, shape, self._handle), device=dev)  # noqa: E731
         self._weights = view(self._lib.bnv_mppi_weights(self._handle), (E, k))
         self._costs = view(self._lib.bnv_mppi_costs(self._handle), (E, k))
         self._previous_action_seq = view(self._lib.bnv_mppi_u_prev(self._handle), (E, t, 2))
@@ -84,13 +83,10 @@ class BatchedMPPI(nn.Module):
                 self._handle, self._risk_dev.data_ptr(), None, g, self._risk_dev.stride(1), self._risk_dev.stride(0),
                 res, x_lim[0], x_lim[1], y_lim[0], y_lim[1], goals, thr, self._stream()))
 
-    def __del__(self):
-        try:
-            if getattr(self, "_handle", None) is not None and self._handle.value:
-                self._lib.bnv_mppi_destroy(self._handle)
-                self._handle = C.c_void_p()
-        except Exception:  # interpreter shutdown
-            pass
+    def close(self) -> None:
+        """Destroy the engine handle now (device buffers, pinned staging, streams).  Without it the handle lives until
+        the solver AND every tensor view of its buffers (``_weights``, ``_state_seq_batch``, ...) are gone."""
+        self._handle.close()
 
     def forward(self, states: torch.Tensor, noise: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
         """One control iteration of every environment (mppi.py:130-219 x E).

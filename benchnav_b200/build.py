@@ -8,10 +8,12 @@ source is newer than the library.
 
 from __future__ import annotations
 
+import fcntl
 import os
 import shutil
 import subprocess
 import sys
+import warnings
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
@@ -53,9 +55,22 @@ def is_stale() -> bool:
 
 
 def build_library(verbose: bool = False) -> str:
-    """Compile every translation unit (in parallel: the rollout kernel's template space dominates) and link."""
-    srcs, _ = _sources()
+    """Compile every translation unit (in parallel: the rollout kernel's template space dominates) and link.
+
+    Safe against concurrent callers (every rank of a torchrun job may find the library stale at once): the build runs
+    under an exclusive file lock, objects go to a per-process directory and the library is linked to a temporary
+    path and moved into place atomically, so no process ever loads a half-written file."""
     os.makedirs(LIB_DIR, exist_ok=True)
+    with open(os.path.join(LIB_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose: bool) -> str:
+    srcs, _ = _sources()
     obj_dir = os.path.join(LIB_DIR, "obj")
     os.makedirs(obj_dir, exist_ok=True)
     nvcc = nvcc_path()
@@ -74,11 +89,15 @@ def build_library(verbose: bool = False) -> str:
                     other.kill()
             raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + out)
         objs.append(obj)
-    link = [nvcc, *LINK_FLAGS, "-o", LIB_PATH, *objs]
+    tmp_lib = LIB_PATH + f".tmp{os.getpid()}"
+    link = [nvcc, *LINK_FLAGS, "-o", tmp_lib, *objs]
     proc = subprocess.run(link, capture_output=True, text=True)
     log += " ".join(link) + "\n" + proc.stdout + proc.stderr
     if proc.returncode != 0:
+        if os.path.exists(tmp_lib):
+            os.remove(tmp_lib)
         raise RuntimeError("link failed:\n" + " ".join(link) + "\n" + proc.stdout + proc.stderr)
+    os.replace(tmp_lib, LIB_PATH)
     with open(os.path.join(LIB_DIR, "build.log"), "w") as f:
         f.write(log)
     if verbose:
@@ -87,13 +106,23 @@ def build_library(verbose: bool = False) -> str:
 
 
 def ensure_built() -> str:
-    """Build if missing or stale and nvcc is present; otherwise return the existing library path."""
+    """Build if missing or stale.  A stale library that cannot be rebuilt is an error when nvcc is present (the sources
+    changed and do not compile); without nvcc (a deployment box that received a prebuilt library) it is loaded with a
+    loud warning -- the ABI-version check in ``_cabi.load`` is then the only guard."""
     if is_stale():
-        try:
-            build_library()
-        except RuntimeError:
-            if not os.path.exists(LIB_PATH):
-                raise
+        have_nvcc = bool(shutil.which("nvcc")) or os.path.exists("/usr/local/cuda/bin/nvcc")
+        if have_nvcc:
+            os.makedirs(LIB_DIR, exist_ok=True)
+            with open(os.path.join(LIB_DIR, ".build.lock"), "a") as lock:  # another rank may be building right now
+                fcntl.flock(lock, fcntl.LOCK_EX)
+                fcntl.flock(lock, fcntl.LOCK_UN)
+            if is_stale():
+                build_library()
+        elif not os.path.exists(LIB_PATH):
+            raise RuntimeError("libbnvmppi.so is missing and nvcc is not available to build it")
+        else:
+            warnings.warn("libbnvmppi.so is older than its sources and nvcc is not available to rebuild it: "
+                          "loading the existing library", RuntimeWarning, stacklevel=2)
     return LIB_PATH
 
 

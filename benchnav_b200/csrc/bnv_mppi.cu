@@ -116,7 +116,7 @@ struct bnv_mppi {
   // pre-launched iterations of forward_host (bnv_mppi_prelaunch)
   bool pre_enabled = false, pre_pending = false;
   cudaStream_t pre_stream = nullptr;        // internal stream of the pre-launched kernels
-  unsigned int* pre_host = nullptr;         // pinned + mapped: [2 slots][4] {x, y, theta, seq}, [8] abort word
+  unsigned int* pre_host = nullptr;         // pinned + mapped: [2 slots][4] {x, y, theta, seq}, [8 + slot] abort words
   unsigned int* pre_host_dev = nullptr;     // its device-side address
   unsigned int* pre_decision = nullptr;     // device word: the grid-wide go / abort decision of the pending launch
   unsigned int pre_seq = 0;                 // sequence number of the pending launch
@@ -558,7 +558,7 @@ static int launch_forward(bnv_mppi* h, const float* state_dev, const float* stat
     P.mailbox_seq = mailbox_seq;
     P.mailbox_timeout_us = h->pre_timeout_us;
     P.prelaunch_decision = h->pre_decision;
-    P.abort_flag = h->pre_host_dev + 8;
+    P.abort_flag = h->pre_host_dev + 8 + (mailbox_seq & 1u);  // one abort word per mailbox slot
     BNV_CUDA(cudaMemsetAsync(h->pre_decision, 0, sizeof(unsigned int), s));
   }
   // The grid is co-resident iff it has at most resident_ctas CTAs (occupancy x SMs; one CTA per SM at long
@@ -686,11 +686,11 @@ int bnv_mppi_forward_state(bnv_mppi* h, const float state_host[3], const float* 
 
 // Spin on the completion word of launch `epoch` (and, for a pre-launched one, on its abort word).  Returns 1 when the
 // results are in the staging buffer, 0 when the launch aborted, negative on error.
-static int wait_host_results(bnv_mppi* h, cudaStream_t s, unsigned int epoch, bool may_abort) {
+static int wait_host_results(bnv_mppi* h, cudaStream_t s, unsigned int epoch, bool may_abort, unsigned int seq = 0) {
   const int T = h->P.T;
   const size_t flag_off = 3 + 2 * static_cast<size_t>(T) + 3 * static_cast<size_t>(T + 1);
   volatile unsigned int* flag = reinterpret_cast<volatile unsigned int*>(h->io_host + flag_off);
-  volatile unsigned int* aborted = h->pre_host ? h->pre_host + 8 : nullptr;
+  volatile unsigned int* aborted = h->pre_host ? h->pre_host + 8 + (seq & 1u) : nullptr;  // the awaited launch's own word
   bool seen = false;
   for (long spins = 0; spins < 50000000L; ++spins) {  // a fault or a stuck device ends in the synchronise below
     if (*flag == epoch) {
@@ -732,8 +732,9 @@ static int forward_host_prelaunched(bnv_mppi* h, const float state_host[3], floa
   if (!h->io_host_dev) BNV_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->io_host_dev), h->io_host, 0));
   float* out_dev = h->io_host_dev;
   const size_t flag_off = 3 + 2 * static_cast<size_t>(T) + 3 * static_cast<size_t>(T + 1);
-  volatile unsigned int* aborted = h->pre_host + 8;
+  volatile unsigned int* aborted = h->pre_host + 8 + (h->pre_seq & 1u);  // abort word of the pending launch's slot
   unsigned int cur_epoch = 0;
+  const unsigned int cur_seq = h->pre_seq;
   bool posted = false;
   if (h->pre_pending && *aborted == h->pre_epoch) {  // the waiting launch timed out before this call
     BNV_CUDA(cudaStreamSynchronize(ps));
@@ -776,7 +777,7 @@ static int forward_host_prelaunched(bnv_mppi* h, const float state_host[3], floa
   h->pre_epoch = h->epoch;
   h->pre_pending = true;
   const double t_d = now_us();
-  const int got = wait_host_results(h, ps, cur_epoch, posted);
+  const int got = wait_host_results(h, ps, cur_epoch, posted, cur_seq);
   const double t_e = now_us();
   g_pre_stats.t_sync += t_b - t_a;
   g_pre_stats.t_post += t_c - t_b;
@@ -878,6 +879,7 @@ int bnv_mppi_finalize(bnv_mppi* h, const float* gathered_partials_dev, float* u_
   if (!h->problem_set) return fail(BNV_ERR_STATE, "finalize needs a preceding forward");
   if (!h->P.state && !h->P.state_inline) return fail(BNV_ERR_STATE, "finalize needs a preceding forward");
   BNV_CUDA(cudaSetDevice(h->cfg.device));
+  BNV_DRAIN(h);
   bnv::EngineParams P = h->P;
   P.u_out = u_out_dev;
   P.opt_rec = opt_states_dev;
@@ -1012,6 +1014,8 @@ int bnv_mppi_device_counter(bnv_mppi* h, int32_t enable, void* stream) {
 
 int bnv_mppi_set_keep_mean(bnv_mppi* h, int32_t keep) {
   if (!h) return fail(BNV_ERR_INVALID, "null argument");
+  BNV_CUDA(cudaSetDevice(h->cfg.device));
+  BNV_DRAIN(h);  // a pre-launched kernel carries a by-value copy of the old parameters
   h->P.keep_mean = keep ? 1 : 0;
   return BNV_OK;
 }
@@ -1019,6 +1023,8 @@ int bnv_mppi_set_keep_mean(bnv_mppi* h, int32_t keep) {
 int bnv_mppi_set_terminal_goal(bnv_mppi* h, const float goal_xy[2]) {
   if (!h || !goal_xy) return fail(BNV_ERR_INVALID, "null argument");
   if (h->E > 1) return fail(BNV_ERR_INVALID, "not available on a batched solver");
+  BNV_CUDA(cudaSetDevice(h->cfg.device));
+  BNV_DRAIN(h);
   h->P.term_gx = goal_xy[0];
   h->P.term_gy = goal_xy[1];
   return BNV_OK;
@@ -1027,6 +1033,8 @@ int bnv_mppi_set_terminal_goal(bnv_mppi* h, const float goal_xy[2]) {
 int bnv_mppi_set_goal_dev(bnv_mppi* h, const float* goal_dev) {
   if (!h) return fail(BNV_ERR_INVALID, "null argument");
   if (h->E > 1) return fail(BNV_ERR_INVALID, "not available on a batched solver");
+  BNV_CUDA(cudaSetDevice(h->cfg.device));
+  BNV_DRAIN(h);
   h->P.goals = goal_dev;
   return BNV_OK;
 }
@@ -1076,6 +1084,7 @@ int bnv_mppi_launch_geometry(const bnv_mppi* h, int32_t out[4]) {
 int bnv_mppi_kernel_timing(bnv_mppi* h, int32_t max_launches) {
   if (!h || max_launches < 0) return fail(BNV_ERR_INVALID, "bad argument");
   BNV_CUDA(cudaSetDevice(h->cfg.device));
+  BNV_DRAIN(h);
   while (h->ev.size() < 2 * static_cast<size_t>(max_launches)) {
     cudaEvent_t e;
     BNV_CUDA(cudaEventCreate(&e));
@@ -1089,6 +1098,7 @@ int bnv_mppi_kernel_timing(bnv_mppi* h, int32_t max_launches) {
 int bnv_mppi_kernel_time(bnv_mppi* h, double* total_ms, uint64_t* launches) {
   if (!h || !total_ms || !launches) return fail(BNV_ERR_INVALID, "null argument");
   BNV_CUDA(cudaSetDevice(h->cfg.device));
+  BNV_DRAIN(h);  // else the event of a launch still waiting for its state would block until the time-out
   double sum = 0.0;
   for (size_t i = 0; i + 1 < h->ev_used; i += 2) {
     float ms = 0.0f;

@@ -58,8 +58,7 @@ class DWA(nn.Module):
                             device=dev.index, flags=_cabi.BNV_FLAG_RECORD_STATES)
         for i in range(2):
             cfg.sigma[i], cfg.u_min[i], cfg.u_max[i] = 1.0, lo[i], hi[i]
-        self._handle = C.c_void_p()
-        _cabi.check(self._lib.bnv_mppi_create(C.byref(self._handle), C.byref(cfg)))
+        self._handle = _cabi.SolverHandle(self._lib, cfg)
         _cabi.check(self._lib.bnv_mppi_set_keep_mean(self._handle, 0))
         self._risk_dev = risks.detach().to(dev, torch.float32).contiguous()
         goal_xy = torch.as_tensor(goal).detach().to("cpu", torch.float32).reshape(-1)[:2].tolist()
@@ -69,7 +68,7 @@ class DWA(nn.Module):
                 self._handle, self._risk_dev.data_ptr(), g, self._risk_dev.stride(0), res, x_lim[0], x_lim[1],
                 y_lim[0], y_lim[1], self._goal_host, thr, self._stream()))
         T = self._horizon
-        view = lambda ptr, shape: torch.as_tensor(_DevView(ptr, shape, self), device=dev)  # noqa: E731
+        view = lambda ptr, shape: torch.as_tensor(_DevView(ptr, shape, self._handle), device=dev)  # noqa: E731
         self._weights = view(self._lib.bnv_mppi_weights(self._handle), (K,))
         self._costs = view(self._lib.bnv_mppi_costs(self._handle), (K,))
         self._state_seq_batch = view(self._lib.bnv_mppi_states(self._handle), (K, T + 1, 3))
@@ -85,13 +84,10 @@ class DWA(nn.Module):
     def _stream(self) -> int:
         return torch.cuda.current_stream(self._device).cuda_stream
 
-    def __del__(self):
-        try:
-            if getattr(self, "_handle", None) is not None and self._handle.value:
-                self._lib.bnv_mppi_destroy(self._handle)
-                self._handle = C.c_void_p()
-        except Exception:  # interpreter shutdown
-            pass
+    def close(self) -> None:
+        """Destroy the engine handle now (device buffers, pinned staging, streams).  Without it the handle lives until
+        the solver AND every tensor view of its buffers (``_weights``, ``_state_seq_batch``, ...) are gone."""
+        self._handle.close()
 
     def update_reference_path(self, reference_path: torch.Tensor) -> None:
         """dwa.py:151-158."""

@@ -135,8 +135,7 @@ class MPPI(nn.Module):
         sig, lo, hi = (t.detach().cpu().to(torch.float32).tolist() for t in (sigmas, dynamics.min_action, dynamics.max_action))
         for i in range(2):
             cfg.sigma[i], cfg.u_min[i], cfg.u_max[i] = sig[i], lo[i], hi[i]
-        self._handle = C.c_void_p()
-        _cabi.check(self._lib.bnv_mppi_create(C.byref(self._handle), C.byref(cfg)))
+        self._handle = _cabi.SolverHandle(self._lib, cfg)
         record_states = bool(record_states) or self._stochastic
         self._record_states = record_states
         self._local_samples = int(self._lib.bnv_mppi_local_samples(self._handle))
@@ -149,7 +148,7 @@ class MPPI(nn.Module):
 
         # engine-owned state exposed under the reference's attribute names (zero-copy views)
         k, t = self._local_samples, self._horizon
-        view = lambda ptr, shape: torch.as_tensor(_DevView(ptr, shape, self), device=dev)  # noqa: E731
+        view = lambda ptr, shape: torch.as_tensor(_DevView(ptr, shape, self._handle), device=dev)  # noqa: E731
         self._weights = view(self._lib.bnv_mppi_weights(self._handle), (k,))
         self._costs = view(self._lib.bnv_mppi_costs(self._handle), (k,))
         self._previous_action_seq = view(self._lib.bnv_mppi_u_prev(self._handle), (t, 2))
@@ -212,13 +211,10 @@ class MPPI(nn.Module):
                     y_lim[0], y_lim[1], self._goal_host, thr, self._stream()))
         self._risk_key = quick
 
-    def __del__(self):
-        try:
-            if getattr(self, "_handle", None) is not None and self._handle.value:
-                self._lib.bnv_mppi_destroy(self._handle)
-                self._handle = C.c_void_p()
-        except Exception:  # interpreter shutdown
-            pass
+    def close(self) -> None:
+        """Destroy the engine handle now (device buffers, pinned staging, streams).  Without it the handle lives until
+        the solver AND every tensor view of its buffers (``_weights``, ``_state_seq_batch``, ...) are gone."""
+        self._handle.close()
 
     # ------------------------------------------------------------------ reference API
     def forward(self, state: torch.Tensor, noise: Optional[torch.Tensor] = None, xi: Optional[torch.Tensor] = None,
