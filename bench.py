@@ -1,32 +1,43 @@
 #!/usr/bin/env python
 """bench.py -- MPPI control iterations/sec on B200 (BASELINE.json metric), one JSON line on stdout.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--config auto|c1|c2|c3|c4]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
-Workload (BASELINE.json configs[1]): synthetic 256x256 terrain (r = 0.5 m), K = 16384 samples,
-T = 50 steps, sigma = (0.5, 0.5), lambda = 0.5, start (8, 8, pi/4), goal (48, 48), threshold 0.3, full contract
-(noise drawn in-engine and kept, recorded states and weights written).  A "step" is one MPPI.forward().
-At N > 1 GPUs the job is ONE solver whose samples are sharded (K = 16384 per GPU, weak scaling; 512x512 terrain
-as in configs[2]) with one all-gather of the (m, s, U) softmax partial per step.
+Workloads (BASELINE.json `configs`; all: r = 0.5 m, sigma = (0.5, 0.5), lambda = 0.5, start (8, 8, pi/4),
+goal (0.375 G r, 0.375 G r), threshold 0.3, full contract = noise drawn in-engine and kept, recorded states and
+weights written).  A "step" is one control iteration = one MPPI.forward() of the whole job.
+  c1    configs[1]: 256x256 terrain, K = 16384, T = 50, one GPU                       (the headline; `auto` at N = 1)
+  c2w   configs[2] family, weak scaling: 512x512, K = 16384 per GPU, T = 50, samples sharded over the N GPUs with one
+        exchange of the (m, s, U) softmax partial per step; at N = 8 this IS configs[2]     (`auto` at N > 1)
+  c2    configs[2] itself at any N: 512x512, K = 131072 in total, T = 50, samples sharded over N GPUs (strong scaling;
+        N = 1 is the single-GPU datum)
+  c3    configs[3]: 64 environments x K = 4096, T = 30, own 64x64 map each, environments sharded over N GPUs, no
+        exchange at all (strong scaling)
+  c4    configs[4]: stochastic slip, 256x256, K = 32768, T = 50, one GPU
 
 Numbers
-  value        device-timed: per-step CUDA-event pairs around forward() (state resident in HBM), L2 flushed
-               between steps by writing a 256 MiB buffer, max over ranks; unit = iterations of one
-               (16384-sample x 50-step) shard per second summed over ranks (= control iterations/s x N).
-  e2e          forward_host(state, out=...): every step the 12-byte state goes host -> device in the kernel's launch
-               packet, the iteration runs, the kernel stores u* and the optimal state sequence (1012 bytes) device ->
-               host into pinned mapped memory and raises a completion word the host polls; wall clock per step (L2
-               flushed between steps, flush not counted).
-  roofline     rollout kernel alone: SURVEY 8d algorithmic bytes / its CUDA-event duration (second pass with the
-               engine's kernel-event recorder on), against MEASURED_PEAKS.json hbm_gbs.
-  cpu_baseline the oracle port of the reference loop (oracle/mppi_oracle.py, PyTorch CPU ops) on the host cores.
+  value        device-timed: per-step CUDA-event pairs around forward() (inputs resident in HBM), L2 flushed between
+               steps by writing a 256 MiB buffer, max over ranks.  Unit: control iterations/s of the job, except c2w
+               (weak scaling) where it is iterations of one (16384-sample x 50-step) shard per second summed over the
+               ranks = control iterations/s x N, so that N = 1 is exactly BASELINE's metric; the raw control rate is
+               always in detail.control_iters_per_sec.
+  e2e          the same step through the host-buffer call: inputs from pinned host memory, results back in host memory,
+               copies inside the timed region, wall clock per step.
+  roofline     rollout kernel alone: SURVEY 8d algorithmic bytes of one launch / its CUDA-event duration (second pass,
+               engine-side event pairs), against MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline the oracle port of the reference loop (oracle/mppi_oracle.py, PyTorch CPU ops) on the host cores, on a
+               bounded sample of the same workload.
+Multi-GPU lines (c2w / c2 at N > 1) also carry: `parity_check` (every rank holds the bit-identical u*, and it equals the
+unsharded solver's within 5e-6, checked on the first step), and detail.single_gpu_same_total_ms / speedup_vs_1gpu
+(rank 0 alone timed on the SAME total workload with the same method).
 """
 
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import statistics
@@ -38,10 +49,54 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-K_PER_GPU, HORIZON, SIGMAS, LAMBDA, RESOLUTION, SEED = 16384, 50, (0.5, 0.5), 0.5, 0.5, 42
+K_PER_GPU, SIGMAS, LAMBDA, RESOLUTION, SEED = 16384, (0.5, 0.5), 0.5, 0.5, 42
 FLUSH_BYTES = 256 << 20
 METRIC = "mppi_iters_per_sec"
 UNIT = "iters/s"
+
+
+# ------------------------------------------------------------------------------------------ workloads
+def resolve_workload(name: str, world: int) -> dict:
+    """Sizes of the named workload at `world` GPUs.  kind: single (one solver, samples sharded when world > 1),
+    batch (independent environments, sharded by environment) or stoch (stochastic-slip lookups)."""
+    if name == "auto":
+        name = "c1" if world == 1 else "c2w"
+    if name == "c1":
+        w = dict(kind="single", grid=256, k_total=K_PER_GPU, horizon=50, envs=1, scaling="weak",
+                 label="BASELINE configs[1]: 256x256 synthetic terrain, K=16384, T=50, single B200")
+        if world != 1:
+            raise SystemExit("c1 is the single-GPU configuration; use c2w / c2 for sample-sharded runs")
+    elif name == "c2w":
+        w = dict(kind="single", grid=512, k_total=K_PER_GPU * world, horizon=50, envs=1, scaling="weak",
+                 label=f"BASELINE configs[2] family (weak scaling): 512x512 synthetic terrain, K=16384 per GPU "
+                       f"(total {K_PER_GPU * world}), T=50, samples sharded over {world} B200" +
+                       (" -- exactly configs[2]" if world == 8 else ""))
+    elif name == "c2":
+        w = dict(kind="single", grid=512, k_total=131072, horizon=50, envs=1, scaling="strong",
+                 label=f"BASELINE configs[2]: 512x512 synthetic terrain, K=131072, T=50, samples sharded over {world} B200")
+    elif name == "c3":
+        if 64 % world:
+            raise SystemExit("c3 shards 64 environments: --gpus must divide 64")
+        w = dict(kind="batch", grid=64, k_total=4096, horizon=30, envs=64, scaling="strong",
+                 label=f"BASELINE configs[3]: 64 environments x K=4096, T=30, own 64x64 map each, environments sharded "
+                       f"over {world} B200 (no exchange)")
+    elif name == "c4":
+        if world != 1:
+            raise SystemExit("c4 (stochastic slip) is a single-GPU configuration")
+        w = dict(kind="stoch", grid=256, k_total=32768, horizon=50, envs=1, scaling="weak",
+                 label="BASELINE configs[4]: stochastic slip (per-sample, per-lookup Normal draws), 256x256, K=32768, T=50")
+    else:
+        raise SystemExit(f"unknown config {name}")
+    w["name"] = name
+    return w
+
+
+def config_of(w: dict, world: int) -> dict:
+    """The `config` object of the JSON line -- the same in the native and the reference arm."""
+    return {"workload": w["label"], "name": w["name"], "grid": w["grid"], "num_samples_total": w["k_total"],
+            "horizon": w["horizon"], "num_envs": w["envs"], "n_gpus": world,
+            "contract": "full: in-engine noise kept, recorded states + weights written",
+            "l2": "flushed between timed steps (256 MiB write); per-step CUDA-event pairs"}
 
 
 def algorithmic_bytes(k: int, t: int, g: int, channels: int = 1) -> int:
@@ -58,14 +113,30 @@ def hbm_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def kernel_source_hash() -> str:
+    """Identity of the rollout kernel's source: the ncu traffic figure is only quoted for the kernel it was taken on."""
+    h = hashlib.sha256()
+    for name in ("mppi_kernels.cuh", "mppi_math.cuh", "ptx_sm100.cuh"):
+        with open(os.path.join(ROOT, "benchnav_b200", "csrc", name), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
 def ncu_traffic(workload: str):
-    """Per-launch DRAM bytes of the rollout kernel from the committed ncu capture, if any."""
+    """(per-launch DRAM bytes of the rollout kernel from the committed ncu capture, note).  Refused -- null -- when the
+    capture was taken on a different version of the kernel source (profiles/rollout_traffic.json records the hash)."""
     try:
         with open(os.path.join(ROOT, "profiles", "rollout_traffic.json")) as f:
             d = json.load(f)
-        return d.get(workload, {}).get("dram_bytes_per_launch")
     except (OSError, ValueError):
-        return None
+        return None, "no ncu capture committed"
+    entry = d.get(workload)
+    if not entry:
+        return None, f"no ncu capture for {workload}"
+    if entry.get("kernel_source_hash") != kernel_source_hash():
+        return None, (f"stale: capture taken on kernel source {entry.get('kernel_source_hash')}, "
+                      f"current {kernel_source_hash()}")
+    return entry.get("dram_bytes_per_launch"), f"ncu --set full, {entry.get('source', 'profiles/')}"
 
 
 class ClockSampler:
@@ -113,88 +184,275 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def build_problem(grid: int):
+def build_problem(grid: int, seed: int = 0):
     import torch  # noqa: F401
 
     from benchnav_b200.synthetic import benchmark_problem
 
-    return benchmark_problem(grid, RESOLUTION, seed=0)
+    return benchmark_problem(grid, RESOLUTION, seed=seed)
+
+
+def stoch_problem(grid: int):
+    """c4: the synthetic terrain's slip prediction Normal(mean, std); same start / goal / threshold as c1."""
+    from benchnav_b200.synthetic import make_terrain
+
+    terr = make_terrain(grid, RESOLUTION, 0)
+    _, start, goal, thr = build_problem(grid)
+    return terr["slip_mean"], terr["slip_std"], start, goal, thr
 
 
 # ------------------------------------------------------------------------------------------ reference arm
-def cpu_reference_rate(grid: int, k: int, steps: int, warmup: int, budget_s: float = 120.0):
-    """The oracle port of the reference loop on the host cores.  Each step is one forward() of the full workload
-    when `steps + warmup` of them fit the time budget; otherwise each step is a bounded sample -- all K samples
-    over the first T_s < T horizon steps (and, below T_s = 1, fewer samples) -- and the rate is scaled linearly by
-    the sampled fraction of the K x T rollout steps (the reference loop is a Python loop over T of elementwise
-    [K]-wide ATen ops, so its time is proportional to both)."""
+def _bounded(est_s: float, steps: int, warmup: int, budget_s: float, k: int, horizon: int):
+    """Shrink (K, T) of a CPU step so that steps + warmup of them fit the budget; the rate is scaled back linearly by
+    the sampled fraction of the K x T rollout steps (the reference loop is a Python loop over T of [K]-wide ATen ops)."""
+    frac = budget_s / max(est_s * (steps + warmup), 1e-9)
+    k_run, t_run = k, horizon
+    if frac < 1.0:
+        t_run = max(1, int(horizon * frac))
+        if horizon * frac < 1.0:
+            k_run = max(1024, int(k * frac * horizon))
+    return k_run, t_run, (k_run * t_run) / (k * horizon)
+
+
+def cpu_port_rate(w: dict, steps: int, warmup: int, budget_s: float = 100.0):
+    """The oracle port of the reference loop on the host cores for workload `w` (whole job: all samples / all
+    environments of all ranks).  Returns (control iterations/s of the job, ms per job step, cores, sample text)."""
     import torch
 
     from oracle import mppi_oracle as orc
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    risk, start, goal, thr = build_problem(grid)
-    p = orc.make_problem(risk, RESOLUTION, goal.tolist(), thr)
-    probe = orc.OracleSolver(p, HORIZON, k, SIGMAS, LAMBDA, seed=SEED)
-    probe.forward(start)
+    g, k, t_h = w["grid"], w["k_total"], w["horizon"]
+    sig = torch.tensor(SIGMAS)
+    if w["kind"] == "batch":
+        # configs[3]'s reference form: E separate solvers stepped in a Python loop (SURVEY 8c); sample = the first few
+        envs = w["envs"]
+        solvers, starts = [], []
+        for e in range(envs):
+            risk, start, goal, thr = build_problem(g, seed=e)
+            solvers.append(orc.OracleSolver(orc.make_problem(risk, RESOLUTION, goal.tolist(), thr), t_h, k, SIGMAS,
+                                            LAMBDA, seed=SEED + e))
+            starts.append(start)
+        solvers[0].forward(starts[0])
+        t0 = time.perf_counter()
+        solvers[0].forward(starts[0])
+        est = time.perf_counter() - t0
+        e_run = int(max(1, min(envs, budget_s / max(est * (steps + warmup), 1e-9))))
+        for _ in range(warmup):
+            for e in range(e_run):
+                solvers[e].forward(starts[e])
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            for e in range(e_run):
+                solvers[e].forward(starts[e])
+        dt = (time.perf_counter() - t0) / steps * (envs / e_run)
+        sample = (f"{steps} steps of {e_run} of the {envs} environments (K={k}, T={t_h}, G={g} each; one port solver per "
+                  f"environment in a Python loop) after {warmup} warm-up; time scaled by {envs}/{e_run}")
+        return 1.0 / dt, dt * 1e3, cores, sample
+    if w["kind"] == "stoch":
+        mean, std, start, goal, thr = stoch_problem(g)
+        p = orc.make_problem(mean, RESOLUTION, goal.tolist(), thr)
+        p.slip_std = std
+        gen = torch.Generator().manual_seed(SEED)
+
+        def step(k_run, t_run, u_prev):
+            noise = torch.randn(k_run, t_run, 2, generator=gen) * sig
+            xi = torch.randn(k_run, 2 * t_run + 1, generator=gen)
+            xi_opt = torch.randn(t_run, generator=gen)
+            return orc.mppi_iteration(p, start, u_prev, noise, sig, LAMBDA, xi=xi, xi_opt=xi_opt)["u_opt"]
+    else:
+        risk, start, goal, thr = build_problem(g)
+        p = orc.make_problem(risk, RESOLUTION, goal.tolist(), thr)
+        gen = torch.Generator().manual_seed(SEED)
+
+        def step(k_run, t_run, u_prev):
+            noise = torch.randn(k_run, t_run, 2, generator=gen) * sig
+            return orc.mppi_iteration(p, start, u_prev, noise, sig, LAMBDA)["u_opt"]
+
+    # probe on a small slice to size the bounded sample (a full c2 step takes seconds)
+    k_probe = min(k, 16384)
+    step(k_probe, t_h, torch.zeros(t_h, 2))
     t0 = time.perf_counter()
-    probe.forward(start)
-    est = time.perf_counter() - t0
-    frac = budget_s / (est * (steps + warmup))
-    k_run, t_run = k, HORIZON
-    if frac < 1.0:
-        t_run = max(1, int(HORIZON * frac))
-        if HORIZON * frac < 1.0:
-            k_run = max(1024, int(k * frac * HORIZON))
-    scale = (k_run * t_run) / (k * HORIZON)
-    sample = f"{steps} forward() calls of K={k_run}, T={t_run} on G={grid} after {warmup} warm-up"
-    sample += " (full workload)" if scale == 1.0 else f"; rate scaled by {k_run}*{t_run}/({k}*{HORIZON}) to the full workload"
-    solver = orc.OracleSolver(p, t_run, k_run, SIGMAS, LAMBDA, seed=SEED)
+    step(k_probe, t_h, torch.zeros(t_h, 2))
+    est = (time.perf_counter() - t0) * (k / k_probe)
+    k_run, t_run, scale = _bounded(est, steps, warmup, budget_s, k, t_h)
+    u_prev = torch.zeros(t_run, 2)
     for _ in range(warmup):
-        solver.forward(start)
+        u_prev = step(k_run, t_run, u_prev)
     t0 = time.perf_counter()
     for _ in range(steps):
-        solver.forward(start)
-    dt = time.perf_counter() - t0
-    return steps / dt * scale, dt / steps * 1e3 / scale, cores, sample
+        u_prev = step(k_run, t_run, u_prev)
+    dt = (time.perf_counter() - t0) / steps / scale
+    sample = f"{steps} forward() calls of K={k_run}, T={t_run} on G={g} after {warmup} warm-up"
+    sample += " (full workload)" if scale == 1.0 else f"; rate scaled by {k_run}*{t_run}/({k}*{t_h}) to the full workload"
+    return 1.0 / dt, dt * 1e3, cores, sample
+
+
+def reference_class_rate(w: dict, steps: int, warmup: int, budget_s: float = 60.0):
+    """The UNMODIFIED reference `MPPI` class on the host cores, when the reference tree is importable (the build
+    container; it does not travel to the GPU box).  Deterministic single-solver workloads only.  None otherwise."""
+    ref_root = os.environ.get("BENCHNAV_REFERENCE", "/root/reference")
+    if w["kind"] != "single" or not os.path.isdir(os.path.join(ref_root, "src")):
+        return None
+    import types
+
+    import torch
+    from torch.distributions import Normal
+
+    sys.modules.setdefault("opensimplex", types.SimpleNamespace(seed=lambda s: None))
+    for p in (os.path.join(ref_root, "src"), ref_root):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    try:
+        from src.environments.grid_map import GridMap
+        from src.planners.local_planners.mppi import MPPI as RefMPPI
+        from src.simulator.problem_formulation.objectives import Objectives
+        from src.simulator.problem_formulation.robot_model import UnicycleModel
+        from src.simulator.problem_formulation.utils import ModelConfig
+    except Exception:  # noqa: BLE001
+        return None
+    g, k, t_h = w["grid"], w["k_total"], w["horizon"]
+    risk, start, goal, thr = build_problem(g)
+    dists = {"predictions": Normal(risk, torch.full_like(risk, 0.1)), "latent_models": Normal(risk, torch.full_like(risk, 0.1))}
+    gm = GridMap(g, RESOLUTION, tensors={"heights": torch.zeros(g, g)}, distributions=dists, instance_name="bench",
+                 device="cpu")
+    dyn = UnicycleModel(gm, ModelConfig("inference", "expected_value"), device="cpu")
+    obj = Objectives(dyn, goal_pos=goal, stuck_threshold=thr)
+    torch.set_num_threads(os.cpu_count() or 1)
+    k_probe = min(k, 16384)
+    probe = RefMPPI(t_h, k_probe, 3, 2, dyn, obj, torch.tensor(SIGMAS), LAMBDA, device=torch.device("cpu"), seed=SEED)
+    with torch.no_grad():
+        probe.forward(state=start)
+        t0 = time.perf_counter()
+        probe.forward(state=start)
+    est = (time.perf_counter() - t0) * (k / k_probe)
+    k_run, t_run, scale = _bounded(est, steps, warmup, budget_s, k, t_h)
+    solver = RefMPPI(t_run, k_run, 3, 2, dyn, obj, torch.tensor(SIGMAS), LAMBDA, device=torch.device("cpu"), seed=SEED)
+    with torch.no_grad():
+        for _ in range(warmup):
+            solver.forward(state=start)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            solver.forward(state=start)
+    dt = (time.perf_counter() - t0) / steps / scale
+    return {"value": 1.0 / dt, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "reference",
+            "sample": f"{steps} forward() calls of the reference MPPI class, K={k_run}, T={t_run}, G={g}" +
+                      ("" if scale == 1.0 else f"; rate scaled by {scale:.4f} to the full workload")}
+
+
+def unit_factor(w: dict, world: int) -> int:
+    """value = control iterations/s x this factor (weak scaling counts shard iterations, see the module docstring)."""
+    return world if w["name"] == "c2w" else 1
 
 
 def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    grid = 256 if args.gpus == 1 else 512
-    k = K_PER_GPU * args.gpus
-    rate, ms, cores, sample = cpu_reference_rate(grid, k, args.steps, max(args.warmup, 1))
-    value = rate * args.gpus  # same unit as the native arm: 16384-sample shard iterations per second
+    w = resolve_workload(args.config, args.gpus)
+    rate, ms, cores, sample = cpu_port_rate(w, args.steps, max(args.warmup, 1))
+    value = rate * unit_factor(w, args.gpus)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"G={grid} terrain, K={k}, T={HORIZON}, oracle port of the reference PyTorch loop on CPU",
-                   "grid": grid, "num_samples": k, "horizon": HORIZON},
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": w["scaling"], "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": config_of(w, args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "detail": {"arm": "oracle port of the reference PyTorch loop on the host cores (the reference is pure Python and "
+                          "its packaging installs only src/simulator, see DESIGN.md: it cannot travel to the GPU box)",
+                   "control_iters_per_sec": rate},
     }
+    ref_cls = reference_class_rate(w, min(args.steps, 5), 1)
+    if ref_cls is not None:
+        line["detail"]["reference_class"] = ref_cls  # the unmodified class, timed beside the port when importable
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------ native arm
+def make_native(w: dict, dev, group, exchange: str, world: int, rank: int):
+    """Build the solver of workload `w` for this rank.  Returns a dict of closures: step() = device-resident call,
+    e2e_step() = host-buffer call (or None), plus the algorithmic bytes and sample count of ONE launch on this rank."""
+    import torch
+
+    from benchnav_b200 import MPPI, BatchedMPPI
+    from benchnav_b200.problem import GoalObjectives, GridSpec, SlipDistribution, UnicycleProblem
+
+    g, t_h = w["grid"], w["horizon"]
+    sig = torch.tensor(SIGMAS)
+    if w["kind"] == "batch":
+        from benchnav_b200.dist import shard_range
+
+        lo, hi = shard_range(w["envs"], rank, world)
+        dyns, objs, states = [], [], []
+        for e in range(lo, hi):
+            risk, start, goal, thr = build_problem(g, seed=e)
+            d = UnicycleProblem(GridSpec(g, RESOLUTION), risk)
+            dyns.append(d)
+            objs.append(GoalObjectives(d, goal, thr))
+            states.append(start)
+        solver = BatchedMPPI(t_h, w["k_total"], dyns, objs, sig, LAMBDA, device=dev, seed=SEED + lo)
+        e_l = hi - lo
+        st_dev = torch.stack(states).to(dev)
+        st_pin = torch.stack(states).pin_memory()
+        st_in = torch.empty_like(st_dev)
+        u_pin = torch.empty(e_l, t_h, 2).pin_memory()
+        o_pin = torch.empty(e_l, 1, t_h + 1, 3).pin_memory()
+        cur = torch.cuda.current_stream(dev)
+
+        def e2e_step():
+            st_in.copy_(st_pin, non_blocking=True)
+            u, o = solver.forward(st_in)
+            u_pin.copy_(u, non_blocking=True)
+            o_pin.copy_(o, non_blocking=True)
+            cur.synchronize()
+
+        return {"solver": solver, "step": lambda: solver.forward(st_dev), "e2e_step": e2e_step,
+                "h2d": e_l * 12, "d2h": e_l * 4 * (2 * t_h + 3 * (t_h + 1)),
+                "e2e_how": "pinned states [E,3] -> device copy, BatchedMPPI.forward, u* [E,T,2] and optimal states "
+                           "[E,1,T+1,3] copied to pinned host tensors, stream synchronised; wall clock per step",
+                "alg_bytes": e_l * algorithmic_bytes(w["k_total"], t_h, g), "units": e_l, "local_samples": w["k_total"],
+                "parallelism": f"environment-shard x{world}: {e_l} environments per GPU, one launch, no exchange"}
+    if w["kind"] == "stoch":
+        mean, std, start, goal, thr = stoch_problem(g)
+        dyn = UnicycleProblem(GridSpec(g, RESOLUTION, distributions={"predictions": SlipDistribution(mean, std)}), mean)
+        solver = MPPI(t_h, w["k_total"], 3, 2, dyn, GoalObjectives(dyn, goal, thr), sig, LAMBDA, device=dev, seed=SEED,
+                      stochastic_slip=True)
+        channels = 2
+    else:
+        risk, start, goal, thr = build_problem(g)
+        dyn = UnicycleProblem(GridSpec(g, RESOLUTION), risk)
+        solver = MPPI(t_h, w["k_total"], 3, 2, dyn, GoalObjectives(dyn, goal, thr), sig, LAMBDA, device=dev, seed=SEED,
+                      process_group=group, exchange=exchange)
+        channels = 1
+    st_dev = start.to(dev)
+    st_pin = start.clone().pin_memory()
+    outs = (torch.empty(t_h, 2).pin_memory(), torch.empty(1, t_h + 1, 3).pin_memory())
+    k_l = solver._local_samples
+    par = f"sample-shard x{world}" + ("" if world == 1 else (", fused exchange of the softmax partial inside the rollout "
+                                                             "kernel over NVLink peer memory" if solver._fused_exchange
+                                                             else ", NCCL all-gather + finalize kernel"))
+    return {"solver": solver, "step": lambda: solver.forward(st_dev),
+            "e2e_step": (lambda: solver.forward_host(st_pin, out=outs)) if world == 1 else None,
+            "h2d": 12, "d2h": 4 * (2 * t_h + 3 * (t_h + 1)),
+            "e2e_how": "forward_host(state, out=caller buffers): the 12-byte state rides in the launch packet (or a "
+                       "pinned, device-mapped mailbox when pre-launched), the kernel stores u* and the optimal state "
+                       "sequence into pinned mapped host memory and raises a completion word the host polls; wall clock",
+            "alg_bytes": algorithmic_bytes(k_l, t_h, g, channels), "units": 1, "local_samples": k_l,
+            "parallelism": par, "start": start, "state_dev": st_dev}
+
+
 def run_native(args) -> None:
     import torch
     import torch.distributed as dist
-
-    from benchnav_b200 import MPPI
-    from benchnav_b200.problem import GoalObjectives, GridSpec, UnicycleProblem
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.gpus != world:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run "
+                         f"--nproc-per-node {args.gpus}")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     group = None
@@ -202,16 +460,10 @@ def run_native(args) -> None:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
-
-    grid = 256 if world == 1 else 512
-    k_total = K_PER_GPU * world
-    risk, start, goal, thr = build_problem(grid)
-    dyn = UnicycleProblem(GridSpec(grid, RESOLUTION), risk)
-    obj = GoalObjectives(dyn, goal, thr)
-    solver = MPPI(HORIZON, k_total, 3, 2, dyn, obj, torch.tensor(SIGMAS), LAMBDA, device=dev, seed=SEED,
-                  process_group=group, exchange=args.exchange)
-    state_dev = start.to(dev)
-    state_pinned = start.clone().pin_memory()
+    w = resolve_workload(args.config, world)
+    sharded = w["kind"] == "single" and world > 1
+    nat = make_native(w, dev, group if w["kind"] == "single" else None, args.exchange, world, rank)
+    solver, step = nat["solver"], nat["step"]
     flush = torch.empty(FLUSH_BYTES, dtype=torch.uint8, device=dev)
     steps, warmup = args.steps, max(args.warmup, 3)
 
@@ -221,105 +473,153 @@ def run_native(args) -> None:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def timed_pass(n: int):
-        """n forward() calls, each preceded by an L2 flush, each bracketed by its own CUDA-event pair."""
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed_pass(fn, n: int, sync=barrier) -> float:
+        """n calls, each preceded by an L2 flush, each bracketed by its own CUDA-event pair; returns milliseconds."""
         ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(n)]
         ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(n)]
-        barrier()
+        sync()
         for i in range(n):
             flush.fill_(i & 0xFF)
             ev0[i].record()
-            solver.forward(state_dev)
+            fn()
             ev1[i].record()
-        barrier()
-        return sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))  # milliseconds
+        sync()
+        return sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))
+
+    # ---- parity of the sharded solver, on its very first step (driver-run evidence in every multi-GPU line)
+    parity = None
+    single_ref = None
+    if sharded:
+        from benchnav_b200 import MPPI
+        from benchnav_b200.problem import GoalObjectives, GridSpec, UnicycleProblem
+
+        u0, _ = step()  # iteration 0 of the sharded solver
+        torch.cuda.synchronize(dev)
+        gathered = [torch.empty_like(u0) for _ in range(world)]
+        dist.all_gather(gathered, u0)
+        same = all(torch.equal(gathered[0], g_) for g_ in gathered[1:])
+        if rank == 0:
+            risk, start, goal, thr = build_problem(w["grid"])
+            dyn = UnicycleProblem(GridSpec(w["grid"], RESOLUTION), risk)
+            single_ref = MPPI(w["horizon"], w["k_total"], 3, 2, dyn, GoalObjectives(dyn, goal, thr),
+                              torch.tensor(SIGMAS), LAMBDA, device=dev, seed=SEED)
+            u_ref, _ = single_ref.forward(nat["state_dev"])  # iteration 0 of the unsharded solver: same Philox stream
+            torch.cuda.synchronize(dev)
+            diff = float((u_ref - u0).abs().max())
+            ok = same and diff <= 5e-6
+            parity = {"parity_check": "ok" if ok else "FAILED", "ranks_bit_equal": bool(same),
+                      "max_abs_du_vs_unsharded": diff, "tolerance": 5e-6,
+                      "what": "first step: u* all-gathered over ranks is bit-identical, and equals the unsharded "
+                              "single-GPU solver's u* (same seed, same Philox stream by global sample index)"}
 
     for _ in range(warmup):
         flush.fill_(1)
-        solver.forward(state_dev)
+        step()
     barrier()
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = solver.launch_count
-    total_ms = timed_pass(steps)
+    total_ms = max_over_ranks(timed_pass(step, steps))
     launches = solver.launch_count - launches0
     clocks = sampler.stop() if sampler else None
-    if world > 1:
-        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
 
-    # second pass: rollout kernel alone (engine-side event pairs) -> roofline
+    # ---- second pass: rollout kernel alone (engine-side event pairs) -> roofline
     n_k = min(steps, 4096)
     solver.kernel_timing(n_k)
-    timed_pass(n_k)
+    timed_pass(step, n_k)
     kern_ms, kern_n = solver.kernel_time()
     solver.kernel_timing(0)
     kern_s = kern_ms / max(kern_n, 1) * 1e-3
 
-    # back-to-back (no flush): explains how far launch gaps / cold L2 matter
+    # ---- back-to-back (no flush): how far launch gaps / cold L2 matter
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
-        solver.forward(state_dev)
+        step()
     e1.record()
     barrier()
-    hot_ms = e0.elapsed_time(e1) / steps
+    hot_ms = max_over_ranks(e0.elapsed_time(e1) / steps)
 
-    # end to end through the host-buffer call (single GPU): pinned state in, results out, sync, every step
+    # ---- end to end through the host-buffer call
     e2e = None
-    if world == 1:
+    if nat["e2e_step"] is not None:
         n_e = min(steps, 2000)
-        out_bufs = (torch.empty(HORIZON, 2).pin_memory(), torch.empty(1, HORIZON + 1, 3).pin_memory())
         cur = torch.cuda.current_stream(dev)
+        e2e_step = nat["e2e_step"]
 
         def e2e_pass(n: int) -> float:
             """n steps: L2 flush (not timed; only the flush's own stream is synchronised -- a pre-launched kernel is
             meant to be waiting on the device at that point), then the timed host-buffer call."""
             for _ in range(3):
-                solver.forward_host(state_pinned, out=out_bufs)
+                e2e_step()
             total = 0.0
             for i in range(n):
                 flush.fill_(i & 0xFF)
                 cur.synchronize()
                 t0 = time.perf_counter()
-                solver.forward_host(state_pinned, out=out_bufs)
+                e2e_step()
                 total += time.perf_counter() - t0
             return total
 
-        acc_plain = e2e_pass(n_e)
-        # pre-launched iterations: the next kernel is already resident when the state arrives (bnv_mppi_prelaunch)
-        e2e_mode = "pre-launched iterations"
-        try:
-            solver.prelaunch(True)
-            acc = e2e_pass(n_e)
-        except Exception as exc:  # keep the bench line: report the plain-launch path as the end-to-end number
-            acc, e2e_mode = acc_plain, f"plain launches (pre-launching failed: {exc})"
-        finally:
+        barrier()
+        acc_plain = max_over_ranks(e2e_pass(n_e))
+        factor = unit_factor(w, world)
+        e2e = {"value": n_e / acc_plain * factor, "unit": UNIT, "h2d_bytes_per_step": nat["h2d"],
+               "d2h_bytes_per_step": nat["d2h"], "steps": n_e, "mode": "plain launches", "timing": nat["e2e_how"]}
+        if w["kind"] != "batch":
+            # the same call with the next iteration's kernel pre-launched (opt-in, solver.prelaunch()): the kernel is
+            # resident and polling a host-mapped mailbox when the state arrives.  Reported beside the plain number; the
+            # headline `value` of e2e is the better of the two and `mode` says which.
             try:
-                solver.prelaunch(False)
-            except Exception:
-                pass
-        # the reference-style call that allocates fresh result tensors every step, for comparison
-        acc_alloc = 0.0
-        for i in range(min(n_e, 500)):
-            flush.fill_(i & 0xFF)
-            torch.cuda.synchronize(dev)
-            t0 = time.perf_counter()
-            solver.forward_host(state_pinned)
-            acc_alloc += time.perf_counter() - t0
-        e2e = {"value": n_e / acc, "unit": UNIT, "h2d_bytes_per_step": 12,
-               "d2h_bytes_per_step": 4 * (2 * HORIZON + 3 * (HORIZON + 1)), "steps": n_e,
-               "mode": e2e_mode, "value_plain_launch": n_e / acc_plain,
-               "value_allocating_outputs": min(n_e, 500) / acc_alloc,
-               "timing": "wall clock around forward_host(state, out=caller buffers) per step with pre-launched "
-                         "iterations (solver.prelaunch(): the 12-byte state is posted to a pinned, device-mapped mailbox "
-                         "that the already-resident kernel polls; results D2H by zero-copy stores to pinned host memory, "
-                         "host polls the kernel's completion word; the launch of the next iteration is issued inside the "
-                         "timed call), L2 flushed before each step; value_plain_launch = the same call launching the "
-                         "kernel when the state arrives (state in the launch packet); value_allocating_outputs = plain "
-                         "launch, allocating fresh result tensors every step"}
+                solver.prelaunch(True)
+                acc_pre = e2e_pass(n_e)
+                e2e["value_prelaunched"] = n_e / acc_pre
+                e2e["value_plain_launch"] = n_e / acc_plain
+                if acc_pre < acc_plain:
+                    e2e["value"], e2e["mode"] = n_e / acc_pre, "pre-launched iterations (solver.prelaunch())"
+            except Exception as exc:  # noqa: BLE001 -- keep the bench line
+                e2e["prelaunch_error"] = str(exc)
+            finally:
+                try:
+                    solver.prelaunch(False)
+                except Exception:  # noqa: BLE001
+                    pass
+            # the reference-style call: forward(host state) returning CUDA tensors, then .cpu() on both results --
+            # what Tutorial 3.3's loop does (test/test_mppi.py:176-181)
+            n_r = min(n_e, 500)
+            acc_ref_style = 0.0
+            start_host = nat["start"]
+            for i in range(n_r + 3):
+                flush.fill_(i & 0xFF)
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                u_, o_ = solver.forward(start_host)
+                u_.cpu()
+                o_.cpu()
+                if i >= 3:
+                    acc_ref_style += time.perf_counter() - t0
+            e2e["value_forward_then_cpu"] = n_r / acc_ref_style
+
+    # ---- strong-scaling datum: ONE GPU on the same total workload, same method (rank 0 only; the others wait)
+    single_same = None
+    if sharded:
+        barrier()
+        if rank == 0:
+            n_s = min(steps, 500)
+            st = nat["state_dev"]
+            for _ in range(3):
+                single_ref.forward(st)
+            ms_1 = timed_pass(lambda: single_ref.forward(st), n_s, sync=lambda: torch.cuda.synchronize(dev)) / n_s
+            single_same = {"single_gpu_same_total_ms": ms_1, "steps": n_s, "launch": single_ref.launch_geometry}
+        barrier()
 
     if rank != 0:
         if world > 1:
@@ -328,38 +628,44 @@ def run_native(args) -> None:
 
     ms_per_step = total_ms / steps
     control_rate = 1e3 / ms_per_step
+    factor = unit_factor(w, world)
     peak, peak_src = hbm_peak()
-    alg_bytes = algorithmic_bytes(K_PER_GPU, HORIZON, grid)
-    achieved = alg_bytes / kern_s / 1e9 if kern_s > 0 else 0.0
-    workload = f"G{grid}_K{K_PER_GPU}_T{HORIZON}"
+    achieved = nat["alg_bytes"] / kern_s / 1e9 if kern_s > 0 else 0.0
+    traffic, traffic_note = ncu_traffic(f"{w['name']}_G{w['grid']}_K{nat['local_samples']}_T{w['horizon']}")
+    detail = {"parallelism": nat["parallelism"], "control_iters_per_sec": control_rate,
+              "back_to_back_ms_per_step": hot_ms,
+              "rollout_steps_per_sec": control_rate * w["k_total"] * w["horizon"] * w["envs"],
+              "value_is": "control iterations/s" + (f" x {world} (16384-sample shard iterations/s, weak scaling)" if factor > 1 else "")}
+    if hasattr(solver, "launch_geometry"):
+        detail["launch"] = solver.launch_geometry
+    if w["kind"] == "batch":
+        detail["env_iters_per_sec"] = control_rate * w["envs"]
+    if single_same is not None:
+        detail.update(single_same)
+        detail["speedup_vs_1gpu"] = single_same["single_gpu_same_total_ms"] / ms_per_step
     line = {
-        "metric": METRIC, "value": control_rate * world, "unit": UNIT, "n_gpus": world, "steps": steps,
-        "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"BASELINE configs[1]: {grid}x{grid} synthetic terrain, K={K_PER_GPU} samples/GPU "
-                               f"(total {k_total}), T={HORIZON}, full contract (in-engine Philox noise kept, recorded "
-                               f"states + weights written)",
-                   "grid": grid, "num_samples_total": k_total, "horizon": HORIZON, "parallelism": f"sample-shard x{world}" + ("" if world == 1 else
-                                   (", fused P2P mailbox exchange in-kernel" if solver._fused_exchange else
-                                    ", NCCL all-gather + finalize kernel")),
-                   "l2": "flushed between timed steps (256 MiB write); per-step CUDA-event pairs",
-                   "launch": solver.launch_geometry,
-                   "control_iters_per_sec": control_rate, "back_to_back_ms_per_step": hot_ms,
-                   "rollout_steps_per_sec": control_rate * k_total * HORIZON},
+        "metric": METRIC, "value": control_rate * factor, "unit": UNIT, "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": w["scaling"],
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_of(w, world),
         "roofline": {"bound": "hbm", "kernel": "bnv::rollout_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": ncu_traffic(workload), "algorithmic_bytes": alg_bytes,
-                     "kernel_us": kern_s * 1e6, "launches_timed": kern_n, "peak_source": peak_src,
-                     "note": "latency-bound by the T-step dependency chain at ~1 warp per SM sub-partition (DESIGN.md)"},
+                     "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
+                     "algorithmic_bytes": nat["alg_bytes"], "kernel_us": kern_s * 1e6, "launches_timed": kern_n,
+                     "peak_source": peak_src, "kernel_source_hash": kernel_source_hash()},
         "gpu_launches": int(launches),
         "clocks": clocks,
+        "detail": detail,
     }
+    if parity is not None:
+        line.update({"parity_check": parity["parity_check"]})
+        detail["parity"] = parity
     if e2e is not None:
         line["e2e"] = e2e
-        rate, ms, cores, sample = cpu_reference_rate(grid, K_PER_GPU, 5, 2)
-        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
     else:
-        line["e2e"] = {"value": control_rate * world, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                       "note": "multi-GPU: device-resident state; host-buffer path is single-GPU"}
+        line["e2e"] = {"value": control_rate * factor, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                       "note": "sample-sharded multi-GPU: device-resident state; no host-buffer number claimed"}
+    if world == 1:
+        rate, ms, cores, sample = cpu_port_rate(w, 5, 2, budget_s=25.0)
+        line["cpu_baseline"] = {"value": rate * factor, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -371,6 +677,8 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=20000)
     ap.add_argument("--warmup", type=int, default=100)
     ap.add_argument("--impl", choices=("native", "reference"), default="native")
+    ap.add_argument("--config", choices=("auto", "c1", "c2w", "c2", "c3", "c4"), default="auto",
+                    help="workload (see the module docstring); auto = c1 on one GPU, c2w on several")
     ap.add_argument("--exchange", choices=("p2p", "nccl"), default="p2p",
                     help="multi-GPU softmax exchange: fused over NVLink peer memory (default) or NCCL all-gather")
     args = ap.parse_args()

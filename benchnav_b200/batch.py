@@ -133,3 +133,21 @@ class BatchedMPPI(nn.Module):
     @property
     def launch_count(self) -> int:
         return int(self._lib.bnv_mppi_launch_count(self._handle))
+
+    @property
+    def launch_geometry(self) -> dict:
+        """Rollout-kernel launch shape: CTAs per environment, warps per CTA, slab split step, cooperative."""
+        out = (C.c_int32 * 4)()
+        _cabi.check(self._lib.bnv_mppi_launch_geometry(self._handle, out))
+        return {"ctas": out[0], "envs": self._num_envs, "warps_per_cta": out[1], "rec_split": out[2],
+                "cooperative": bool(out[3])}
+
+    def kernel_timing(self, max_launches: int) -> None:
+        """Record CUDA-event pairs around the rollout kernel of the next ``max_launches`` iterations."""
+        _cabi.check(self._lib.bnv_mppi_kernel_timing(self._handle, int(max_launches)))
+
+    def kernel_time(self) -> Tuple[float, int]:
+        """(summed rollout-kernel milliseconds, launches measured) since kernel_timing(); synchronises."""
+        ms, n = C.c_double(), C.c_uint64()
+        _cabi.check(self._lib.bnv_mppi_kernel_time(self._handle, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)

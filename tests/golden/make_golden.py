@@ -73,6 +73,65 @@ CASES = {
 }
 
 
+# Every attribute the engine's host mirror reads through the reference's own objects (benchnav_b200/mppi.py
+# _introspect_problem, _slip_distribution and the constructor), as dotted paths from (dynamics, objectives).
+SNAPSHOT_PATHS = {
+    "dynamics": ["min_action", "max_action", "_grid_map.grid_size", "_grid_map.resolution", "_grid_map.x_limits",
+                 "_grid_map.y_limits", "_model_config.mode", "_model_config.inference_metric",
+                 "_model_config.confidence_value", "_traversability_model._risks",
+                 "_grid_map.distributions[predictions].mean", "_grid_map.distributions[predictions].stddev"],
+    "objectives": ["_goal_pos", "_stuck_threshold"],
+}
+
+
+def _walk(obj, path: str):
+    for part in path.split("."):
+        if part.endswith("]"):
+            name, key = part[:-1].split("[")
+            obj = getattr(obj, name)[key]
+        else:
+            obj = getattr(obj, part)  # AttributeError here = the reference no longer has what the engine reads
+    return obj
+
+
+def snapshot_objects(name: str, dyn, obj) -> dict:
+    """Attribute snapshot of the REAL reference objects of one case: values (and tensor dtypes) under the exact
+    attribute names the reference uses, plus the default ``delta_t`` of ``UnicycleModel.transit``
+    (robot_model.py:60).  tests/test_dropin_objects.py rebuilds bare attribute trees from it on the GPU box."""
+    import inspect
+
+    out = {}
+    for root, paths in SNAPSHOT_PATHS.items():
+        for path in paths:
+            v = _walk(dyn if root == "dynamics" else obj, path)
+            if torch.is_tensor(v):
+                v = v.detach().cpu().numpy()  # dtype preserved (the goal may be int64, test/test_mppi.py:133)
+            elif v is None:
+                v = np.asarray("__none__")
+            else:
+                v = np.asarray(v)
+            out[f"{name}|{root}|{path}"] = v
+    out[f"{name}|dynamics|transit.delta_t"] = np.asarray(
+        inspect.signature(dyn.transit).parameters["delta_t"].default, dtype=np.float64)
+    return out
+
+
+def build_objects(name: str, c: dict, ref):
+    """The reference's own GridMap / UnicycleModel / Objectives of one case (shared by run_case and the drop-in test)."""
+    GridMap, ModelConfig, UnicycleModel, Objectives, _ = ref
+    g = torch.Generator().manual_seed(c["map_seed"])
+    mean = torch.rand(c["G"], c["G"], generator=g) * c["map_scale"] + c.get("map_offset", 0.0)
+    std = torch.full((c["G"], c["G"]), c["std"])
+    dists = {"predictions": Normal(mean, std), "latent_models": Normal(mean, std)}
+    gm = GridMap(c["G"], c["res"], tensors={"heights": torch.zeros(c["G"], c["G"])}, distributions=dists,
+                 instance_name=name, device="cpu")
+    torch.manual_seed(c["map_seed"] + 1000)  # the VaR/CVaR risk map consumes the global generator
+    dyn = UnicycleModel(gm, ModelConfig("inference", c["metric"], c["conf"]), device="cpu")
+    goal = torch.tensor(c["goal"]) if c["goal_int"] else torch.tensor(c["goal"], dtype=torch.float32)
+    obj = Objectives(dyn, goal_pos=goal, stuck_threshold=c["thr"])
+    return gm, dyn, obj
+
+
 def run_case(name: str, c: dict, ref):
     GridMap, ModelConfig, UnicycleModel, Objectives, MPPI = ref
     g = torch.Generator().manual_seed(c["map_seed"])
@@ -124,9 +183,19 @@ def run_case(name: str, c: dict, ref):
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
+    ap.add_argument("--snapshots-only", action="store_true",
+                    help="only (re)write ref_object_snapshots.npz: attribute snapshots of the reference objects")
     args = ap.parse_args()
     torch.set_num_threads(1)  # results are thread-count invariant; 1 keeps the run reproducible anyway
     ref = import_reference(args.ref)
+    snaps = {}
+    for name, c in CASES.items():
+        _, dyn, obj = build_objects(name, c, ref)
+        snaps.update(snapshot_objects(name, dyn, obj))
+    np.savez_compressed(os.path.join(HERE, "ref_object_snapshots.npz"), **snaps)
+    print(f"ref_object_snapshots.npz: {len(snaps)} attributes of {len(CASES)} cases")
+    if args.snapshots_only:
+        return
     for name, c in CASES.items():
         o = run_case(name, c, ref)
         print(f"{name}: u_opt[0]={o['u_opt_0'][0]}, sum|u|={np.abs(o['u_opt_0']).sum():.6f}, "

@@ -319,7 +319,10 @@ def test_dwa_golden_calls(golden_cases):
             np.testing.assert_array_equal(solver._sub_goal.cpu().numpy(), c[f"sub_goal_{i}"])
         rec = solver._state_seq_batch.cpu().numpy()
         bad = np.abs(rec - c[f"rec_{i}"]).reshape(rec.shape[0], -1).max(axis=1) > TOL_REC
-        assert bad.mean() <= 0.02, f"dwa[{i}]: {bad.sum()} rollouts off"
+        # K = 100 constant-action rollouts: at most ONE may differ -- a rollout whose position lands within an ulp of
+        # a cell border can take the neighbouring cell's traversability (the engine's sin/cos is <= 2 ulp, not
+        # bit-equal to ATen's Sleef kernel), after which its remaining states follow the other cell's value
+        assert bad.sum() <= 1, f"dwa[{i}]: {bad.sum()} of {bad.size} rollouts off by > {TOL_REC}"
         np.testing.assert_allclose(solver._weights.cpu().numpy(), c[f"weights_{i}"], rtol=0, atol=2e-4)
         assert a.shape == (1, 2) and s.shape == (1, T + 1, 3)
         np.testing.assert_allclose(a.cpu().numpy(), c[f"opt_action_{i}"], rtol=0, atol=1e-6)
@@ -371,6 +374,10 @@ def test_closed_loop_planner_and_environment_follow_the_oracle():
             want_coll = eo.collision_check(ps, ref["opt_rec"], 0.1, xi_c[e].view(1, -1))
             nxt, r_rew, r_term = eo.env_step(ps, ref_state[e].view(1, 3), ref["u_opt"][0].view(1, 2), goals[e].view(1, 2),
                                              0.1, 1.0, xi[e].view(1))
+            # two free-running closed loops (engine state / oracle state): step s starts from states and mean sequences
+            # that already differ by the accumulated deviation of steps 0..s-1, so the bounds grow linearly -- 2e-3 per
+            # step on u* (the single-call tolerance) and 2e-3 * v_max * dt * 5 = 1e-3 per step on the state (the applied
+            # control moves the robot by at most dt per step; the factor 5 covers the heading's lever arm)
             np.testing.assert_allclose(u[e].cpu().numpy(), ref["u_opt"].numpy(), rtol=0, atol=2e-3 * (step + 1))
             np.testing.assert_allclose(st[e].cpu().numpy(), nxt[0].numpy(), rtol=0, atol=1e-3 * (step + 1))
             np.testing.assert_allclose(rew[e].item(), r_rew[0].item(), rtol=0, atol=1e-6)

@@ -97,3 +97,33 @@ def test_python_restatement_of_philox_matches_the_published_known_answers():
 
     for counter, key, want in PHILOX_KAT:
         assert philox4x32_10(counter, key) == want
+
+
+# ------------------------------------------------------------------------------------------ bench.py host logic
+def test_bench_workloads_bytes_and_config_agree_between_arms():
+    """bench.py: the SURVEY 8d byte formula reproduces the survey's per-unit figures, every workload resolves, the
+    `config` object is identical in the native and the reference arm (built by one function), and a stale ncu traffic
+    figure is refused."""
+    import json
+
+    import bench
+
+    assert bench.algorithmic_bytes(16384, 50, 256) == 16_909_300      # C1
+    assert bench.algorithmic_bytes(1000, 25, 64) == 532_896           # C0a
+    assert bench.algorithmic_bytes(5000, 50, 64) == 5_097_396         # C0b
+    assert bench.algorithmic_bytes(16384, 50, 512) == 17_695_732      # C2 per GPU
+    assert bench.algorithmic_bytes(4096, 30, 64) == 2_540_132         # C3 per environment
+    for name, world in (("auto", 1), ("auto", 8), ("c2", 1), ("c2", 4), ("c3", 8), ("c4", 1)):
+        w = bench.resolve_workload(name, world)
+        cfg = bench.config_of(w, world)
+        assert json.dumps(cfg) == json.dumps(bench.config_of(bench.resolve_workload(name, world), world))
+        assert cfg["num_samples_total"] == w["k_total"] and cfg["n_gpus"] == world
+    assert bench.resolve_workload("auto", 8)["k_total"] == 131072 and bench.resolve_workload("auto", 8)["grid"] == 512
+    assert bench.unit_factor(bench.resolve_workload("auto", 4), 4) == 4
+    assert bench.unit_factor(bench.resolve_workload("c2", 4), 4) == 1
+    with pytest.raises(SystemExit):
+        bench.resolve_workload("c1", 2)
+    with pytest.raises(SystemExit):
+        bench.resolve_workload("c3", 3)
+    traffic, note = bench.ncu_traffic("no_such_workload")
+    assert traffic is None and "no ncu capture" in note

@@ -51,6 +51,10 @@ def test_golden_chained_calls(golden_cases, name):
         u, opt = solver.forward(torch.from_numpy(case[f"state_{i}"]), noise=torch.from_numpy(case[f"noise_{i}"]))
         eng = engine_outputs(solver, u, opt)
         du = np.abs(eng["u_opt"] - case[f"u_opt_{i}"]).max()
+        # Why the bound grows with the call index: call i starts from the engine's OWN u* of call i-1 as the mean
+        # sequence, so the per-call deviation (<= TOL_U: a peaked softmax -- effective sample size 1-4 on these maps --
+        # amplifies fp32 cost rounding) is carried into the next call's inputs and a new one is added on top.  The
+        # single-call tests above (reference inputs injected every call) hold the flat TOL_U.
         assert du <= (i + 1) * TOL_U, f"{name}[{i}] chained |du*| = {du}"
 
 
