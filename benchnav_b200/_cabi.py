@@ -102,6 +102,7 @@ _SIGNATURES = {
     "bnv_mppi_argmin": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP]),
     "bnv_mppi_dwa_subgoal": (C.c_int, [_VP, _VP, C.c_int32, _VP, _VP, C.c_float, _VP, _VP]),
     "bnv_mppi_launch_count": (C.c_uint64, [_VP]),
+    "bnv_mppi_check": (C.c_int, [_VP, _VP]),
     "bnv_mppi_launch_geometry": (C.c_int, [_VP, C.POINTER(C.c_int32)]),
     "bnv_mppi_kernel_timing": (C.c_int, [_VP, C.c_int32]),
     "bnv_mppi_kernel_time": (C.c_int, [_VP, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),

@@ -30,7 +30,7 @@ COMPILE_FLAGS = [
 LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-cudart", "static"]
 
 
-SOURCES = ("bnv_mppi.cu", "rollout_ext.cu", "bnv_aux.cu")
+SOURCES = ("bnv_mppi.cu", "rollout_ext.cu", "rollout_wide.cu", "rollout_wide_ext.cu", "bnv_aux.cu")
 
 
 def _sources():

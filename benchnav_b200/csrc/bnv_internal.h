@@ -26,6 +26,10 @@ using BnvRolloutFn = void (*)(bnv::EngineParams);
 // (instantiated in rollout_ext.cu so that the two halves of the template space compile in parallel).
 BnvRolloutFn bnv_pick_rollout_ext(bool patch, bool pow2, bool philox, bool stoch, bool batch);
 
+// the wide (throughput) variant, rollout_kernel<..., kWide = true> (rollout_wide.cu / rollout_wide_ext.cu)
+BnvRolloutFn bnv_pick_rollout_wide(bool patch, bool pow2, bool record, bool philox);
+BnvRolloutFn bnv_pick_rollout_wide_ext(bool patch, bool pow2, bool philox, bool stoch, bool batch);
+
 // argmin_gather_kernel (aux_kernels.cuh) launcher, defined in bnv_aux.cu.
 int bnv_launch_argmin(const float* costs, int K, const float* actions, const float* rec, int row_len, float* action_out,
                       float* states_out, int* idx_out, cudaStream_t s);

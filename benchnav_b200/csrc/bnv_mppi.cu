@@ -95,6 +95,16 @@ struct bnv_mppi {
   float* shard_partial = nullptr;
   float* io_dev = nullptr;  // [3] state + [2T] u_out + [3(T+1)] opt states, staging for forward_host
   unsigned int* ticket = nullptr;
+  uint2* part_ll_u = nullptr;            // [E][max_grid][2T] per-CTA partials as LL words (distributed epilogue)
+  uint2* part_ll_ms = nullptr;           // [E][max_grid][2]
+  size_t part_ll_words = 0;              // uint2 words in part_ll_u + part_ll_ms (for the clears)
+  unsigned long long* arrive = nullptr;  // (reserved)
+  uint2* ustar_ll = nullptr;             // [E][2T] LL words of u*
+  unsigned int* ticket_grp = nullptr;    // [E][max_groups]
+  float* part2_ms = nullptr;             // [E][max_groups][2]
+  float* part2_u = nullptr;              // [E][max_groups][2T]
+  int max_groups = 1;
+  unsigned int* err_flag = nullptr;      // device word raised by a timed-out in-kernel wait
   float* stats = nullptr;
   unsigned int epoch = 0;
   int num_sms = 0;
@@ -125,6 +135,7 @@ struct bnv_mppi {
   bool user_work = false;                   // work was queued on a caller's stream since the last pre-launched step
   cudaStream_t user_stream = nullptr;
   int grid = 0, warps = 0;
+  bool wide = false;            // the wide (throughput) variant of the rollout kernel is selected (configure_launch)
   long long resident_ctas = 0;  // how many rollout CTAs the device can hold at once (cooperative-launch bound)
   bool fast_angles = false;
   size_t rollout_smem = 0, finalize_smem = 0;
@@ -153,6 +164,14 @@ void free_all(bnv_mppi* h) {
   cudaFree(h->shard_partial);
   cudaFree(h->io_dev);
   cudaFree(h->ticket);
+  cudaFree(h->arrive);
+  cudaFree(h->part_ll_u);
+  cudaFree(h->part_ll_ms);
+  cudaFree(h->ustar_ll);
+  cudaFree(h->ticket_grp);
+  cudaFree(h->part2_ms);
+  cudaFree(h->part2_u);
+  cudaFree(h->err_flag);
   cudaFree(h->stats);
   cudaFree(h->dbg_ts);
   for (size_t r = 0; r < h->peer_ptrs.size(); ++r)
@@ -187,6 +206,10 @@ RolloutFn pick_rollout1(bool b, bool c, bool d, bool e) {
 }
 RolloutFn pick_rollout(const bnv_mppi* h, bool philox) {
   const bool a = h->P.use_patch, b = h->P.geom.fast_grid, c = h->P.record, d = h->fast_angles;
+  if (h->wide) {
+    if (h->stoch || h->E > 1) return bnv_pick_rollout_wide_ext(a, b, philox, h->stoch, h->E > 1);
+    return bnv_pick_rollout_wide(a, b, c, philox);
+  }
   if (h->stoch || h->E > 1) return bnv_pick_rollout_ext(a, b, philox, h->stoch, h->E > 1);  // record + fast angles
   return a ? pick_rollout1<true>(b, c, d, philox) : pick_rollout1<false>(b, c, d, philox);
 }
@@ -204,7 +227,8 @@ FinalizeFn pick_finalize(const bnv_mppi* h) {
 // how many CTAs the device holds at once (min over the Philox / injected-noise instantiations), 0 if it does not fit.
 int layout_capacity(bnv_mppi* h, int w, int rec_split, size_t* smem_out, long long* cap_out) {
   bnv::EngineParams& P = h->P;
-  bnv::RolloutSmem L = bnv::rollout_smem_layout(P.T, w, P.patch_w, P.patch_h, P.use_patch, P.record, h->stoch ? 2 : 1, rec_split);
+  bnv::RolloutSmem L = bnv::rollout_smem_layout(P.T, w, P.patch_w, P.patch_h, P.use_patch, P.record, h->stoch ? 2 : 1, rec_split,
+                                                h->wide ? 1 : 0);
   *smem_out = L.total;
   *cap_out = 0;
   if (static_cast<size_t>(L.total) > kMaxDynSmem) return BNV_OK;
@@ -229,6 +253,12 @@ int layout_capacity(bnv_mppi* h, int w, int rec_split, size_t* smem_out, long lo
 int configure_launch(bnv_mppi* h) {
   bnv::EngineParams& P = h->P;
   P.rec_split = 0;
+  h->wide = false;
+  // Latency variant first (4 warps per CTA, whole-horizon slabs, one CTA per SM at long horizons): it is the fastest
+  // shape whenever its grid fits the device in one co-resident wave.  A single solver that does not fit runs the wide
+  // variant (8 warps per CTA, two CTAs per SM, chunked staging): 4x the resident warps, bound by the FP32 pipe instead
+  // of by the per-step dependency chain.  BNV_DEBUG_DISABLE bit 2048 = never wide, bit 4096 = always wide
+  // (measurement aids; 4096 is also how the test suite drives every golden case through the wide variant).
   for (int w = bnv::kMaxWarps; w >= 1; w >>= 1) {
     size_t smem = 0;
     long long cap = 0;
@@ -255,12 +285,43 @@ int configure_launch(bnv_mppi* h) {
     }
     h->rollout_smem = smem;
     h->resident_ctas = cap;
+    // A single solver whose grid does not fit the device in one wave even so runs the wide variant (measured: K = 131072
+    // at T = 50, 145 -> 100 us).  Batched solvers stay on the latency variant (64 environments x K = 4096: 88 vs 120 us --
+    // their per-CTA fixed costs are paid once per wave, and the wide variant's waves are longer, not fewer).
+    const bool want_wide = (debug_disable() & 4096u) || (h->E == 1 && total > cap);
+    if (want_wide && h->fast_angles && !(debug_disable() & 2048u)) {
+      h->wide = true;
+      size_t smem_w = 0;
+      long long cap_w = 0;
+      rc = layout_capacity(h, bnv::kWideWarps, 0, &smem_w, &cap_w);
+      if (rc != BNV_OK) return rc;
+      if (smem_w <= kMaxDynSmem && cap_w > 0) {
+        P.rec_split = 0;
+        h->warps = bnv::kWideWarps;
+        h->grid = (h->Kl + bnv::kWideWarps * 32 - 1) / (bnv::kWideWarps * 32);
+        h->rollout_smem = smem_w;
+        h->resident_ctas = 0;  // never launched cooperatively: the last CTA's epilogue serves every grid size
+      } else {
+        h->wide = false;  // (a reach window close to 64 KB leaves no room for two wide CTAs per SM)
+      }
+    }
     return BNV_OK;
   }
   return fail(BNV_ERR_UNSUPPORTED, "horizon %d does not fit the rollout kernel's shared-memory staging", P.T);
 }
 
 }  // namespace
+
+// LL words carry the launch epoch as their tag; when the epoch's source changes (by value <-> device counter) stale
+// tags could collide with new ones: wipe them.
+static cudaError_t clear_ll_words(bnv_mppi* h, cudaStream_t s) {
+  const size_t nE = static_cast<size_t>(h->E), T = static_cast<size_t>(h->P.T);
+  const size_t max_grid = (static_cast<size_t>(h->Kl) + 31) / 32;
+  cudaError_t e = cudaMemsetAsync(h->part_ll_u, 0, nE * max_grid * 2 * T * sizeof(uint2), s);
+  if (e == cudaSuccess) e = cudaMemsetAsync(h->part_ll_ms, 0, nE * max_grid * 2 * sizeof(uint2), s);
+  if (e == cudaSuccess) e = cudaMemsetAsync(h->ustar_ll, 0, nE * 2 * T * sizeof(uint2), s);
+  return e;
+}
 
 struct PreStats {
   double t_sync = 0, t_post = 0, t_launch = 0, t_wait = 0;
@@ -348,10 +409,20 @@ int bnv_mppi_create(bnv_mppi** out, const bnv_mppi_cfg* cfg) {
   alloc(reinterpret_cast<void**>(&h->shard_partial), sizeof(float) * (2 + 2 * T));
   alloc(reinterpret_cast<void**>(&h->io_dev), sizeof(float) * io_floats);
   alloc(reinterpret_cast<void**>(&h->ticket), 2 * nE * sizeof(unsigned int));
+  h->max_groups = (max_grid + bnv::kMergeGroup - 1) / bnv::kMergeGroup;
+  const size_t nG = static_cast<size_t>(h->max_groups);
+  alloc(reinterpret_cast<void**>(&h->arrive), nE * sizeof(unsigned long long));
+  alloc(reinterpret_cast<void**>(&h->part_ll_u), nE * max_grid * 2 * T * sizeof(uint2));
+  alloc(reinterpret_cast<void**>(&h->part_ll_ms), nE * max_grid * 2 * sizeof(uint2));
+  alloc(reinterpret_cast<void**>(&h->ustar_ll), nE * 2 * T * sizeof(uint2));
+  alloc(reinterpret_cast<void**>(&h->ticket_grp), nE * nG * sizeof(unsigned int));
+  alloc(reinterpret_cast<void**>(&h->part2_ms), sizeof(float) * nE * nG * 2);
+  alloc(reinterpret_cast<void**>(&h->part2_u), sizeof(float) * nE * nG * 2 * T);
+  alloc(reinterpret_cast<void**>(&h->err_flag), sizeof(unsigned int));
   alloc(reinterpret_cast<void**>(&h->stats), 4 * nE * sizeof(float));
   alloc(reinterpret_cast<void**>(&h->goals_dev), 2 * nE * sizeof(float));
-  if (cfg->world_size > 1) {  // mailbox: 2 parities x world slots x (m, s, U[2T], flag, pad)
-    h->mbox_floats = 2 * static_cast<size_t>(cfg->world_size) * (2 + 2 * static_cast<size_t>(T) + 2);
+  if (cfg->world_size > 1) {  // mailbox: [2 parities][world ranks][2T columns] cells of three LL words {U[c] | M | S, tag}
+    h->mbox_floats = 2 * static_cast<size_t>(cfg->world_size) * 2 * static_cast<size_t>(T) * 3 * 2;
     alloc(reinterpret_cast<void**>(&h->mbox), sizeof(float) * h->mbox_floats);
     alloc(reinterpret_cast<void**>(&h->peer_mbox_dev), sizeof(float*) * cfg->world_size);
     if (e == cudaSuccess) e = cudaMemset(h->mbox, 0, sizeof(float) * h->mbox_floats);
@@ -360,6 +431,12 @@ int bnv_mppi_create(bnv_mppi** out, const bnv_mppi_cfg* cfg) {
   if (e == cudaSuccess) std::memset(h->io_host, 0, sizeof(float) * io_floats);
   if (e == cudaSuccess) e = cudaMemset(h->u_prev, 0, sizeof(float) * nE * T * 2);  // mppi.py:116
   if (e == cudaSuccess) e = cudaMemset(h->ticket, 0, 2 * nE * sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMemset(h->arrive, 0, nE * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemset(h->part_ll_u, 0, nE * max_grid * 2 * T * sizeof(uint2));  // tag 0 = never written
+  if (e == cudaSuccess) e = cudaMemset(h->part_ll_ms, 0, nE * max_grid * 2 * sizeof(uint2));
+  if (e == cudaSuccess) e = cudaMemset(h->ustar_ll, 0, nE * 2 * T * sizeof(uint2));
+  if (e == cudaSuccess) e = cudaMemset(h->ticket_grp, 0, nE * nG * sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMemset(h->err_flag, 0, sizeof(unsigned int));
   if (e == cudaSuccess) e = cudaMemset(h->weights, 0, sizeof(float) * nE * Kl);    // mppi.py:126-128
   if (e == cudaSuccess && record) e = cudaMemset(h->rec, 0, sizeof(float) * nE * Kl * (T + 1) * 3);  // mppi.py:119-125
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -406,6 +483,15 @@ int bnv_mppi_create(bnv_mppi** out, const bnv_mppi_cfg* cfg) {
   P.part_u = h->part_u;
   P.shard_partial = h->shard_partial;
   P.ticket = h->ticket;
+  P.arrive = h->arrive;
+  P.part_ll_u = h->part_ll_u;
+  P.part_ll_ms = h->part_ll_ms;
+  P.ustar_ll = h->ustar_ll;
+  P.ticket_grp = h->ticket_grp;
+  P.part2_ms = h->part2_ms;
+  P.part2_u = h->part2_u;
+  P.max_groups = h->max_groups;
+  P.err_flag = h->err_flag;
   P.stats = h->stats;
   cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, cfg->device);
   int coop_attr = 0;
@@ -519,6 +605,10 @@ int bnv_mppi_set_problem_ex(bnv_mppi* h, const float* mean_dev, const float* std
   }
   int rc = configure_launch(h);
   if (rc != BNV_OK) return rc;
+  // the launch geometry may have changed: restart the arrival counters (the stream was synchronised above)
+  BNV_CUDA(cudaMemsetAsync(h->arrive, 0, static_cast<size_t>(E) * sizeof(unsigned long long), s));
+  BNV_CUDA(cudaMemsetAsync(h->ticket, 0, 2 * static_cast<size_t>(E) * sizeof(unsigned int), s));
+  BNV_CUDA(cudaMemsetAsync(h->ticket_grp, 0, static_cast<size_t>(E) * h->max_groups * sizeof(unsigned int), s));
   h->finalize_smem = 128 + (P.use_patch ? ((P.patch_w * P.patch_h + 31) / 32) * 32 * 4 : 0) + 2 * (2 * P.T + 4) * 4 + 16;
   if (!h->stoch && E == 1)
     BNV_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(pick_finalize(h)),
@@ -566,7 +656,7 @@ static int launch_forward(bnv_mppi* h, const float* state_dev, const float* stat
   const bool coop = h->coop_ok && static_cast<long long>(h->grid) * h->E <= h->resident_ctas;
   h->epoch = (h->epoch == 0xFFFFFFFFu) ? 1u : h->epoch + 1u;
   P.epoch = h->epoch;
-  P.coop = coop ? 1 : 0;
+  P.coop = coop ? ((debug_disable() & 8192u) ? 1 : 2) : 0;  // bit 8192: round-1 schedule (last CTA merges), for A/B runs
   if (h->peers_attached) {
     h->xchg_seq = (h->xchg_seq == 0xFFFFFFFFu) ? 1u : h->xchg_seq + 1u;  // advances in lock-step on every rank
     P.xchg_seq = h->xchg_seq;
@@ -585,11 +675,19 @@ static int launch_forward(bnv_mppi* h, const float* state_dev, const float* stat
   cfg.attrs = attr;
   cfg.numAttrs = (coop && !(debug_disable() & 128u)) ? 1 : 0;  // bit 128: measurement aid, plain launch of the coop path
   BNV_CUDA(cudaLaunchKernelEx(&cfg, pick_rollout(h, philox), P));
+  h->launches++;
+  if (!coop) {  // the grid was not co-resident: its weights are normalised by a second, fully parallel kernel
+    int spb_shift = 0;
+    while ((1 << spb_shift) < h->warps * 32) ++spb_shift;
+    bnv::normalize_weights_kernel<<<dim3((h->Kl + 255) / 256, h->E), 256, 0, s>>>(
+        h->weights, h->part_ms, h->stats, h->Kl, spb_shift, h->grid, mailbox_seq != 0u ? h->pre_decision : nullptr);
+    BNV_CUDA(cudaGetLastError());
+  }
   if (timed) {
     BNV_CUDA(cudaEventRecord(h->ev[h->ev_used + 1], s));
     h->ev_used += 2;
   }
-  h->launches++;
+  if (!coop) h->launches++;
   if (h->iter_dev) {  // the counter advances on the device, in stream order (and on every replay of a captured graph)
     bnv::bump_iteration_kernel<<<1, 1, 0, s>>>(h->iter_dev);
     BNV_CUDA(cudaGetLastError());
@@ -997,12 +1095,15 @@ int bnv_mppi_device_counter(bnv_mppi* h, int32_t enable, void* stream) {
     if (!h->iter_dev) BNV_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->iter_dev), sizeof(unsigned long long)));
     const unsigned long long it = h->iteration;
     BNV_CUDA(cudaMemcpyAsync(h->iter_dev, &it, sizeof(it), cudaMemcpyHostToDevice, s));
-    // the "merge done" flags hold by-value epochs of earlier launches: clear them (0 is never a valid epoch)
+    // the "merge done" flags and the LL words hold by-value epochs of earlier launches: clear them (0 is never a
+    // valid epoch)
     BNV_CUDA(cudaMemsetAsync(h->ticket, 0, 2 * static_cast<size_t>(h->E) * sizeof(unsigned int), s));
+    BNV_CUDA(clear_ll_words(h, s));
     BNV_CUDA(cudaStreamSynchronize(s));
     h->P.iter_dev = h->iter_dev;
   } else if (h->iter_dev && h->P.iter_dev) {
     BNV_CUDA(cudaMemsetAsync(h->ticket, 0, 2 * static_cast<size_t>(h->E) * sizeof(unsigned int), s));
+    BNV_CUDA(clear_ll_words(h, s));
     unsigned long long it = 0;
     BNV_CUDA(cudaMemcpyAsync(&it, h->iter_dev, sizeof(it), cudaMemcpyDeviceToHost, s));
     BNV_CUDA(cudaStreamSynchronize(s));
@@ -1069,6 +1170,21 @@ int bnv_mppi_dwa_subgoal(bnv_mppi* h, const float* path_dev, int32_t n, const fl
 }
 
 uint64_t bnv_mppi_launch_count(const bnv_mppi* h) { return h ? h->launches : 0; }
+
+int bnv_mppi_check(bnv_mppi* h, void* stream) {
+  if (!h) return fail(BNV_ERR_INVALID, "null argument");
+  BNV_CUDA(cudaSetDevice(h->cfg.device));
+  BNV_DRAIN(h);
+  unsigned int flag = 0;
+  BNV_CUDA(cudaMemcpyAsync(&flag, h->err_flag, sizeof(flag), cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
+  BNV_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  if (flag != 0u) {
+    BNV_CUDA(cudaMemsetAsync(h->err_flag, 0, sizeof(flag), static_cast<cudaStream_t>(stream)));
+    return fail(BNV_ERR_CUDA, "an in-kernel wait timed out (a peer rank did not deliver its softmax partial within 2 s): "
+                              "the results of that iteration are invalid");
+  }
+  return BNV_OK;
+}
 
 int bnv_mppi_launch_geometry(const bnv_mppi* h, int32_t out[4]) {
   if (!h || !out) return fail(BNV_ERR_INVALID, "null argument");

@@ -34,6 +34,17 @@ namespace bnv {
 
 constexpr int kMaxWarps = 4;        // warps (x32 samples) per rollout CTA
 constexpr int kFinalizeThreads = 128;
+// Wide (throughput) variant of the rollout kernel, for grids that do not fit the device in one wave of the latency
+// variant: 8 warps per CTA, two CTAs per SM, and instead of whole-horizon slabs each warp stages kChunkSteps steps of
+// recorded states / drawn noise in shared memory and flushes them with coalesced stores.
+constexpr int kWideWarps = 8;
+constexpr int kChunkPairs = 8;
+constexpr int kChunkSteps = 2 * kChunkPairs;
+constexpr int kWideNzStride = 4 * kChunkPairs + 4;   // floats per sample row of the noise chunk: rows 16-byte aligned,
+                                                     // per-lane 16-byte stores conflict-free (9 quad-banks apart)
+constexpr int kWideRecStride = 3 * kChunkSteps + 1;  // floats per sample row of the recorded-state chunk (odd: conflict-free)
+constexpr int kTwoLevelMin = 64;  // non-cooperative grids above this many CTAs merge their partials in two levels ...
+constexpr int kMergeGroup = 32;   // ... in groups of this many consecutive CTAs
 
 struct alignas(64) EngineParams {
   CUtensorMap tau_map;  // 2-D tiled descriptor over the padded tau map, box = patch_w x patch_h
@@ -73,6 +84,15 @@ struct alignas(64) EngineParams {
   float* part_ms;       // [nCTA][2]   per-CTA (max score, sum exp)
   float* part_u;        // [nCTA][2T]  per-CTA sum exp * v
   float* shard_partial; // [2+2T]      (m, s, U) of this shard
+  uint2* part_ll_u;            // [E][nCTA][2T] per-CTA column sums as LL words {value, launch epoch} (coop == 2)
+  uint2* part_ll_ms;           // [E][nCTA][2]  per-CTA (max score, sum exp) as LL words
+  unsigned long long* arrive;  // (unused by the current schedules; reserved)
+  uint2* ustar_ll;             // [E][2T] {u*[c] bits, tag}: columns of u* handed to the CTA that runs the optimal rollout
+  unsigned int* ticket_grp;    // [E][max_groups] arrival counters of the level-1 groups of a two-level merge
+  float* part2_ms;             // [E][max_groups][2]   (max score, sum exp) per merged group
+  float* part2_u;              // [E][max_groups][2T]  sum exp * v per merged group
+  int max_groups;
+  unsigned int* err_flag;      // device word: set when a peer exchange / hand-over wait timed out (result then invalid)
   unsigned int* ticket;  // [0] arrival counter of the last-CTA election, [1] "merge done" epoch flag (coop)
   float* stats;          // [2] (M, S) of the last merge, published to the waiting CTAs (coop)
   unsigned int epoch;    // unique per launch
@@ -89,7 +109,9 @@ struct alignas(64) EngineParams {
   unsigned int* prelaunch_decision;    // device word, zeroed before the launch: 0 undecided, 1 go, 2 abort
   unsigned int* abort_flag;            // mapped host word: set to `epoch` when the launch aborted
   int keep_mean;         // write u* back as the next call's mean sequence (mppi.py:217); 0 for DWA's constant actions
-  int coop;              // grid is co-resident (cooperative launch): deferred slab stores, in-register weights
+  int coop;              // grid is co-resident (cooperative launch): deferred slab stores, in-register weights.
+                         // 2 = distributed merge (every CTA merges its own columns after a grid barrier),
+                         // 1 = the last CTA merges while the others wait (round-1 schedule, kept for A/B runs)
   float* const* peer_mbox;  // [world] device pointers to every rank's mailbox (peer memory over NVLink), or null
   unsigned int xchg_seq;    // exchange sequence number (same on every rank), selects the mailbox parity
   int rank;
@@ -117,16 +139,17 @@ __host__ __device__ inline int rec_slab_slots(int T, int rec_split) {
   return rec_split > 0 ? (rec_split > T + 1 - rec_split ? rec_split : T + 1 - rec_split) : T + 1;
 }
 __host__ __device__ inline RolloutSmem rollout_smem_layout(int T, int warps, int patch_w, int patch_h, int use_patch,
-                                                           int record, int cell_floats = 1, int rec_split = 0) {
+                                                           int record, int cell_floats = 1, int rec_split = 0,
+                                                           int wide = 0) {
   RolloutSmem s;
   int spb = warps * 32;
   int off = 128;  // [0,128): mbarriers (1 patch + kMaxWarps noise) and the last-CTA flag
   s.off_patch = off;
   off += use_patch ? ((patch_w * patch_h * cell_floats * 4 + 127) / 128) * 128 : 0;
   s.off_noise = off;
-  off += ((spb * 2 * T * 4 + 127) / 128) * 128;
+  off += (((wide ? spb * kWideNzStride : spb * 2 * T) * 4 + 127) / 128) * 128;
   s.off_rec = off;
-  off += record ? ((spb * 3 * rec_slab_slots(T, rec_split) * 4 + 127) / 128) * 128 : 0;
+  off += record ? (((wide ? spb * kWideRecStride : spb * 3 * rec_slab_slots(T, rec_split)) * 4 + 127) / 128) * 128 : 0;
   s.off_uprev = off;
   off += ((2 * T * 4 + 15) / 16) * 16;
   s.off_coef = off;
@@ -134,7 +157,7 @@ __host__ __device__ inline RolloutSmem rollout_smem_layout(int T, int warps, int
   s.off_e = off;
   off += spb * 4;
   s.off_warpu = off;
-  off += ((kMaxWarps * 2 * T * 4 + 15) / 16) * 16;
+  off += (((warps > kMaxWarps ? warps : kMaxWarps) * 2 * T * 4 + 15) / 16) * 16;
   s.off_red = off;
   off += 64 * 4;
   s.off_merge = off;  // last CTA only: a_g [kMergeACap], group column sums [max(kMergeGrpCap, 2T)]
@@ -191,6 +214,23 @@ __global__ void __launch_bounds__(256) noise_kernel(float* __restrict__ noise, i
   float* dst = noise + ((static_cast<size_t>(env) * Kl + k) * T + 2 * p) * 2;
   *reinterpret_cast<float2*>(dst) = make_float2(n.x, n.y);
   if (2 * p + 1 < T) *reinterpret_cast<float2*>(dst + 2) = make_float2(n.z, n.w);
+}
+
+// Softmax weights of a grid that was not co-resident (launched right behind rollout_kernel): the rollout left
+// exp(score_k - m_cta) in weights[k], the per-CTA maxima in part_ms and the merged (M, S) in stats (S = 1 when the 1/S
+// is deferred to finalize_kernel).  weights[k] *= exp(m_cta - M) / S (mppi.py:193).  blockIdx.y = environment.
+__global__ void __launch_bounds__(256) normalize_weights_kernel(float* __restrict__ weights,
+                                                                const float* __restrict__ part_ms,
+                                                                const float* __restrict__ stats, int Kl, int spb_shift,
+                                                                int nblk, const unsigned int* __restrict__ decision) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= Kl) return;
+  if (decision != nullptr && *decision != 1u) return;  // the pre-launched rollout in front of this kernel aborted
+  const size_t env = blockIdx.y;
+  const float M = stats[2 * env], S = stats[2 * env + 1];
+  const float m_cta = part_ms[(env * nblk + (k >> spb_shift)) * 2];
+  float* w = weights + env * Kl + k;
+  *w = *w * (__expf(m_cta - M) * __fdiv_rn(1.0f, S));
 }
 
 // Graph-capturable launches: advance the device-resident iteration counter after the rollout kernel.
@@ -417,6 +457,34 @@ __device__ __forceinline__ void copy_rec_slots(float* rec_g, const float* rec_w,
   }
 }
 
+// Wide variant: copy a block of 32 rows x n words from a shared-memory chunk slab (row stride `src_stride` words) to
+// global rows (row stride `dst_stride` words), all 32 lanes on consecutive words of the flat (row, word) index space,
+// so that every store instruction covers whole 128-byte runs except where it crosses a row boundary.  kN = n when it is
+// known at compile time (the full chunk: division by a constant, fully unrolled), 0 = runtime n (last, partial chunk).
+template <int kN>
+__device__ __forceinline__ void copy_rows_flat(float* __restrict__ dst, int dst_stride, const float* __restrict__ src,
+                                               int src_stride, int n_rt, int lane) {
+  const int n = kN > 0 ? kN : n_rt;
+  const uint32_t magic = 0xFFFFFFFFu / static_cast<uint32_t>(n) + 1u;  // ceil(2^32 / n): row = umulhi(idx, magic), idx < 2^16
+  const int total = 32 * n;
+#pragma unroll 1
+  for (int base = 0; base < total; base += 256) {  // eight 128-byte passes in flight
+    float v[8];
+    int off[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int idx = base + 32 * j + lane;
+      const int row = kN > 0 ? idx / kN : static_cast<int>(__umulhi(static_cast<uint32_t>(idx), magic));
+      const int col = idx - row * n;
+      off[j] = idx < total ? row * dst_stride + col : -1;
+      v[j] = idx < total ? src[row * src_stride + col] : 0.0f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (off[j] >= 0) dst[off[j]] = v[j];
+  }
+}
+
 template <bool kRecord, bool kPhilox>
 __device__ __forceinline__ void store_slabs(const EngineParams& P, float* rec_env, float* noise_env, float* rec_s,
                                             float* nz_w, int warp, int lane, int warp_first, int warp_rows,
@@ -467,6 +535,140 @@ __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) 
 }
 __device__ __forceinline__ void st_release_gpu(unsigned int* p, unsigned int v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ unsigned long long atom_add_acq_rel_gpu_u64(unsigned long long* p, unsigned long long v) {
+  unsigned long long old;
+  asm volatile("atom.add.acq_rel.gpu.global.u64 %0, [%1], %2;" : "=l"(old) : "l"(p), "l"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// Self-validating 8-byte words {value, tag} ("LL" protocol): one aligned 8-byte store is a single memory transaction,
+// so a reader that sees the expected tag also sees the value -- no fence, no separate flag.  volatile = relaxed at
+// system scope: the same two functions serve hand-overs inside the GPU and stores into a peer GPU's memory over NVLink.
+__device__ __forceinline__ void st_ll(uint2* p, float v, uint32_t tag) {
+  asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag) : "memory");
+}
+__device__ __forceinline__ uint2 ld_ll(const uint2* p) {
+  uint2 w;
+  asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(w.x), "=r"(w.y) : "l"(p) : "memory");
+  return w;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+constexpr unsigned long long kSpinLimitNs = 2000000000ull;  // 2 s: a peer that never answers must not hang the device
+
+// Wait for the LL word at `p` to carry `tag`; returns its value.  On a time-out the solver's error word is raised and
+// 0 is returned (the iteration's result is then invalid; bnv_mppi_check reports it).
+__device__ __forceinline__ float wait_ll(const uint2* p, uint32_t tag, unsigned int* err_flag) {
+  uint2 w = ld_ll(p);
+  if (w.y == tag) return __uint_as_float(w.x);
+  const unsigned long long t0 = globaltimer_ns();
+  for (unsigned int spins = 1;; ++spins) {
+    w = ld_ll(p);
+    if (w.y == tag) return __uint_as_float(w.x);
+    if ((spins & 1023u) == 0u && globaltimer_ns() - t0 > kSpinLimitNs) {
+      if (err_flag != nullptr) atomicExch(err_flag, 1u);
+      return 0.0f;
+    }
+  }
+}
+
+// Sharded softmax, one column of the exchange, executed by ONE thread: this rank's un-normalised column
+// sum U[c] (relative to its shard maximum M, with the shard's sum S) goes into the cell (rank, c) of every rank's
+// mailbox as three LL words over NVLink peer memory; then the thread collects the W cells of column c from its own
+// mailbox and merges them in rank order -- identical arithmetic on every rank, so every rank holds the same u*.
+// Mailboxes are double-buffered by the parity of the exchange sequence number (= the tag): a rank can be at most one
+// iteration ahead of the slowest peer.  Mailbox layout: [2 parities][W ranks][2T columns][3] uint2.
+struct ColumnMerge {
+  float U, M, S;
+};
+__device__ __forceinline__ const uint2* mailbox_cell(const EngineParams& P, int holder, int src_rank, int c, int ncol) {
+  const size_t idx = ((static_cast<size_t>(P.xchg_seq & 1u) * P.world + src_rank) * ncol + c) * 3;
+  return reinterpret_cast<const uint2*>(P.peer_mbox[holder]) + idx;
+}
+// Collect the cells (src ranks r0 .. r0 + n - 1, n <= 8) of column c from this rank's own mailbox: all outstanding
+// words are requested before the first is examined, so a round costs one L2 round trip; rounds repeat until every word
+// carries the tag (or the time-out raises the error word).
+__device__ __forceinline__ void poll_cells(const EngineParams& P, int c, int ncol, int r0, int n, float (&U)[8],
+                                           float (&M)[8], float (&S)[8]) {
+  const uint32_t tag = P.xchg_seq;
+  unsigned pend = 0u;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    U[j] = 0.0f;
+    M[j] = -FLT_MAX;
+    S[j] = 0.0f;
+    if (j < n) pend |= 7u << (3 * j);
+  }
+  const uint2* cell0 = mailbox_cell(P, P.rank, r0, c, ncol);
+  const size_t rank_stride = static_cast<size_t>(ncol) * 3;
+  const unsigned long long t0 = globaltimer_ns();
+  for (unsigned int spins = 1; pend != 0u; ++spins) {
+    uint2 w[8][3];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        w[j][q] = make_uint2(0u, 0u);
+        if (pend & (1u << (3 * j + q))) w[j][q] = ld_ll(cell0 + j * rank_stride + q);
+      }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int q = 0; q < 3; ++q)
+        if ((pend & (1u << (3 * j + q))) && w[j][q].y == tag) {
+          const float v = __uint_as_float(w[j][q].x);
+          if (q == 0) U[j] = v;
+          if (q == 1) M[j] = v;
+          if (q == 2) S[j] = v;
+          pend &= ~(1u << (3 * j + q));
+        }
+    if ((spins & 1023u) == 0u && globaltimer_ns() - t0 > kSpinLimitNs) {
+      if (P.err_flag != nullptr) atomicExch(P.err_flag, 1u);
+      pend = 0u;
+    }
+  }
+}
+__device__ __forceinline__ ColumnMerge merge_column_cells(const EngineParams& P, int c, int ncol) {
+  const int W = P.world;
+  float U[8], M[8], S[8];
+  float Mg = -FLT_MAX;
+  for (int r0 = 0; r0 < W; r0 += 8) {  // (one group on a single node: W <= 8)
+    poll_cells(P, c, ncol, r0, min(8, W - r0), U, M, S);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) Mg = fmaxf(Mg, M[j]);
+  }
+  ColumnMerge out{0.0f, Mg, 0.0f};
+  for (int r0 = 0; r0 < W; r0 += 8) {  // rank order: the same sums on every rank
+    if (W > 8) poll_cells(P, c, ncol, r0, min(8, W - r0), U, M, S);  // (all valid by now: one round)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (r0 + j < W) {
+        const float a = __expf(M[j] - Mg);
+        out.S = fmaf(a, S[j], out.S);
+        out.U = fmaf(a, U[j], out.U);
+      }
+    }
+  }
+  return out;
+}
+__device__ __forceinline__ ColumnMerge exchange_column(const EngineParams& P, int c, int ncol, float U, float M, float S) {
+  const uint32_t tag = P.xchg_seq;
+  for (int r = 0; r < P.world; ++r) {
+    uint2* cell = const_cast<uint2*>(mailbox_cell(P, r, P.rank, c, ncol));
+    st_ll(cell, U, tag);
+    st_ll(cell + 1, M, tag);
+    st_ll(cell + 2, S, tag);
+  }
+  return merge_column_cells(P, c, ncol);
 }
 
 // Results complete (u_out and opt_rec written by this CTA, ordered before this thread by the CTA barrier): publish
@@ -522,9 +724,13 @@ __device__ __forceinline__ void sample_step(SampleState& s, const StepConsts& C,
 // kPow2: resolution is a power of two (multiply instead of divide in the cell index);
 // kRecord: keep every sample's recorded states; kFastAngles: dt * max|omega| < pi (branch-free steps 1..T-1);
 // kPhilox: draw the noise in the loop (else it is injected and bulk-loaded from HBM);
-// kStoch: stochastic-slip lookups; kBatch: blockIdx.y = environment.
-template <bool kPatch, bool kPow2, bool kRecord, bool kFastAngles, bool kPhilox, bool kStoch, bool kBatch>
-__global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid_constant__ EngineParams P) {
+// kStoch: stochastic-slip lookups; kBatch: blockIdx.y = environment;
+// kWide: throughput variant -- 8 warps per CTA, 2 CTAs per SM (<= 128 registers), chunked staging of the recorded
+// states and the drawn noise, weighted sum re-reads the noise from L2/HBM; never launched cooperatively.
+template <bool kPatch, bool kPow2, bool kRecord, bool kFastAngles, bool kPhilox, bool kStoch, bool kBatch,
+          bool kWide = false>
+__global__ void __launch_bounds__((kWide ? kWideWarps : kMaxWarps) * 32, kWide ? 2 : 1)
+    rollout_kernel(const __grid_constant__ EngineParams P) {
   extern __shared__ __align__(128) unsigned char smem[];
   const long long t_start = clock64();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -532,7 +738,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
   const int nwarps = blockDim.x >> 5;
   const int spb = nwarps * 32;
   constexpr int kCell = kStoch ? 2 : 1;
-  const RolloutSmem L = rollout_smem_layout(T, nwarps, P.patch_w, P.patch_h, kPatch, kRecord, kCell, P.rec_split);
+  const RolloutSmem L = rollout_smem_layout(T, nwarps, P.patch_w, P.patch_h, kPatch, kRecord, kCell, P.rec_split, kWide);
   const int rec_slots = rec_slab_slots(T, P.rec_split);  // slots per sample in the recorded-state slab
   uint64_t* bar_patch = reinterpret_cast<uint64_t*>(smem);
   uint64_t* bar_noise = reinterpret_cast<uint64_t*>(smem) + 1;  // [kMaxWarps]
@@ -651,10 +857,10 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
   __syncthreads();
 
   // ---- injected noise: stage this warp's slab, rows [warp_first, warp_first+warp_rows) x 2T floats, contiguous in HBM
-  float* nz_w = noise_s + warp * 32 * 2 * T;
+  float* nz_w = noise_s + warp * 32 * (kWide ? kWideNzStride : 2 * T);
   const uint32_t nz_bytes = static_cast<uint32_t>(warp_rows) * 2u * T * 4u;
   bool nz_bulk = false;
-  if (!kPhilox) {
+  if (!kPhilox && !kWide) {  // (wide: every thread reads its own injected row from global memory in the loop)
     const float* nz_g = P.noise_in + (eK + warp_first) * 2 * T;
     nz_bulk = P.noise_bulk_ok && ((nz_bytes & 15u) == 0u) && warp_rows > 0 &&
               (reinterpret_cast<uintptr_t>(nz_g) & 15u) == 0u;
@@ -669,7 +875,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
   }
   // noise rows of a ragged warp that carry no sample: keep them finite (the weighted-sum pass multiplies the
   // controls rebuilt from them by 0)
-  for (int i = warp_rows * 2 * T + lane; i < 32 * 2 * T; i += 32) nz_w[i] = 0.0f;
+  if (!kWide)
+    for (int i = warp_rows * 2 * T + lane; i < 32 * 2 * T; i += 32) nz_w[i] = 0.0f;
 
   // ---- window geometry, traversability window via TMA
   const WindowGeom wg = window_for_state(P, sx, sy);
@@ -708,19 +915,67 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
   const float4* ucf_s = reinterpret_cast<const float4*>(coef_s);
   __syncthreads();
   if (kPatch) mbar_wait(bar_patch, 0);
-  if (!kPhilox) {
+  if (!kPhilox && !kWide) {
     if (nz_bulk) mbar_wait(bar_noise + warp, 0);
     else __syncwarp();
   }
-  C.pin_all();
-  pin(sig0);
-  pin(sig1);
+  if (!kWide) {  // the latency variant keeps every loop invariant in a register; the wide one must fit 128 registers
+    C.pin_all();
+    pin(sig0);
+    pin(sig1);
+  }
   const long long t_loop0 = clock64();
 
   // ---- T-step rollout, one sample per thread
   float cost = FLT_MAX;
-  float* nrow = nz_w + lane * 2 * T;
-  float* rrow = rec_s + (warp * 32 + lane) * 3 * rec_slots;
+  float* nrow = nz_w + lane * (kWide ? kWideNzStride : 2 * T);
+  float* rrow = rec_s + (warp * 32 + lane) * (kWide ? kWideRecStride : 3 * rec_slots);
+  // wide variant: flush recorded-state slots [t0, t0 + nt_rec) and noise steps [t0, t0 + nt_nz) of this warp's chunk
+  // slabs to HBM (row segments of nt * 12 / nt * 8 bytes: whole sectors except at the segment ends), then rebase the
+  // slab pointers so that step t0 + nt lands at the start of the slab.  A full warp copies cooperatively (one row
+  // segment per pass, consecutive lanes on consecutive words); the one ragged warp of a launch copies lane by lane.
+  const bool nz_vec_ok = kWide && (T & 1) == 0 && (reinterpret_cast<uintptr_t>(noise_out_e) & 15u) == 0u;
+  auto flush_chunk = [&](int t0, int nt_rec, int nt_nz) {
+    if (!kWide) return;
+    float* rec_g = kRecord ? rec_e + static_cast<size_t>(warp_first) * 3 * (T + 1) + 3 * t0 : nullptr;
+    float* nz_g = noise_out_e + static_cast<size_t>(warp_first) * 2 * T + 2 * t0;
+    if (warp_rows == 32) {
+      __syncwarp();
+      if (kRecord) {
+        const float* src = rec_s + warp * 32 * kWideRecStride;
+        if (nt_rec == kChunkSteps) copy_rows_flat<3 * kChunkSteps>(rec_g, 3 * (T + 1), src, kWideRecStride, 0, lane);
+        else copy_rows_flat<0>(rec_g, 3 * (T + 1), src, kWideRecStride, 3 * nt_rec, lane);
+      }
+      if (kPhilox && nt_nz > 0) {
+        if (nz_vec_ok && nt_nz == kChunkSteps) {  // 16-byte words: 8 lanes per row, 4 rows per pass
+          const int u = lane & 7;
+#pragma unroll
+          for (int r0 = 0; r0 < 32; r0 += 4) {
+            const int r = r0 + (lane >> 3);
+            const float4 v = *reinterpret_cast<const float4*>(nz_w + r * kWideNzStride + 4 * u);
+            *reinterpret_cast<float4*>(nz_g + static_cast<size_t>(r) * 2 * T + 4 * u) = v;
+          }
+        } else {
+          copy_rows_flat<0>(nz_g, 2 * T, nz_w, kWideNzStride, 2 * nt_nz, lane);
+        }
+      }
+      __syncwarp();
+    } else if (valid) {
+      if (kRecord) {
+        float* dst = rec_g + static_cast<size_t>(lane) * 3 * (T + 1);
+        const float* src = rec_s + (warp * 32 + lane) * kWideRecStride;
+        for (int i = 0; i < 3 * nt_rec; ++i) dst[i] = src[i];
+      }
+      if (kPhilox) {
+        float* dst = nz_g + static_cast<size_t>(lane) * 2 * T;
+        const float* src = nz_w + lane * kWideNzStride;
+        for (int i = 0; i < 2 * nt_nz; ++i) dst[i] = src[i];
+      }
+    }
+    rrow -= 3 * nt_nz;
+    nrow -= 2 * nt_nz;
+  };
+  const float* nz_in_row = (kWide && !kPhilox) ? P.noise_in + (eK + k) * 2 * T : nullptr;  // injected noise, wide
   // mid-loop flush of the slab's first half (rec_split): coalesced by the whole warp when it is full, else (the one
   // ragged warp of a launch) every lane writes its own row; afterwards slot t lives at rrow[3 (t - Tc)]
   auto flush_first_half = [&]() {
@@ -758,6 +1013,9 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
       if (kPhilox) {
         nz = nz_cur;
         nz_cur = noise_pair(kg, static_cast<uint32_t>(p + 1), iter_lo, iter_hi_e, key, sig0, sig1);
+      } else if (kWide) {
+        const float* g = nz_in_row + 4 * p;
+        nz = make_float4(__ldg(g), __ldg(g + 1), __ldg(g + 2), __ldg(g + 3));
       } else {
         const float2 a = *reinterpret_cast<const float2*>(nrow + 4 * p);
         const float2 b = *reinterpret_cast<const float2*>(nrow + 4 * p + 2);
@@ -793,14 +1051,24 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
           const float4 nq = fetch_pair(p);
           const float4 xp = fetch_xi(p);
           if (kPhilox) {
-            *reinterpret_cast<float2*>(nrow + 4 * p) = make_float2(nq.x, nq.y);
-            *reinterpret_cast<float2*>(nrow + 4 * p + 2) = make_float2(nq.z, nq.w);
+            if (kWide) {
+              *reinterpret_cast<float4*>(nrow + 4 * p) = nq;
+            } else {
+              *reinterpret_cast<float2*>(nrow + 4 * p) = make_float2(nq.x, nq.y);
+              *reinterpret_cast<float2*>(nrow + 4 * p + 2) = make_float2(nq.z, nq.w);
+            }
           }
           sample_step<kPatch, kPow2, kRecord, kFastAngles, kStoch>(s, C, 2 * p, nq.x, nq.y, xp.x, xp.y, ucf_s, rrow);
           sample_step<kPatch, kPow2, kRecord, kFastAngles, kStoch>(s, C, 2 * p + 1, nq.z, nq.w, xp.z, xp.w, ucf_s, rrow);
         }
       };
-      if (split_pair < 0) {
+      if (kWide) {  // chunks of kChunkPairs step pairs, each flushed as soon as it is complete
+        for (int pc = 0; pc < nfull; pc += kChunkPairs) {
+          const int pe = min(pc + kChunkPairs, nfull);
+          run_pairs(max(pc, 1), pe);
+          flush_chunk(2 * pc, 2 * (pe - pc), 2 * (pe - pc));
+        }
+      } else if (split_pair < 0) {
         run_pairs(1, nfull);
       } else {
         run_pairs(1, split_pair);
@@ -817,7 +1085,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
         xl_tr = xi_cur.x;
         xl_st = xi_cur.y;
       } else {
-        nl = *reinterpret_cast<const float2*>(nrow + 4 * nfull);
+        nl = kWide ? make_float2(__ldg(nz_in_row + 4 * nfull), __ldg(nz_in_row + 4 * nfull + 1))
+                   : *reinterpret_cast<const float2*>(nrow + 4 * nfull);
         if (kStoch) {
           xl_tr = __ldg(xrow + 4 * nfull);
           xl_st = __ldg(xrow + 4 * nfull + 1);
@@ -827,6 +1096,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
       else sample_step<kPatch, kPow2, kRecord, kFastAngles, kStoch>(s, C, T - 1, nl.x, nl.y, xl_tr, xl_st, ucf_s, rrow);
     }
     if (kRecord) { rrow[3 * T + 0] = s.x; rrow[3 * T + 1] = s.y; rrow[3 * T + 2] = s.th; }
+    // wide: what is left in the slabs -- an odd horizon's last step and the final (clamped, wrapped) state
+    flush_chunk(2 * nfull, T + 1 - 2 * nfull, T - 2 * nfull);
     // terminal cost (mppi.py:184; objectives.py:65): same cell as the last stage cost, its own draw when stochastic
     float tau_term = s.tau;
     if (kStoch) {
@@ -852,8 +1123,50 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
   if (lane == 0) red_s[8 + warp] = ws;
   __syncwarp();
   // each warp: columns over lanes, its own 32 samples; the clamped controls v = clamp(u_prev + noise) are rebuilt from
-  // the noise slab (the same two ops as in sample_step), e_s holds the un-normalised weights
-  {
+  // the noise (the same two ops as in sample_step), e_s holds the un-normalised weights.  Row r always goes to
+  // accumulator r mod 4, in ascending order, in both variants.
+  if (kWide) {
+    // the noise left shared memory chunk by chunk: re-read this warp's rows from L2 / HBM, lanes on consecutive columns
+    // (coalesced), 16 rows x 4 column groups = 64 loads in flight per lane.  A batch of rows whose un-normalised weights
+    // all underflowed to exactly 0 is skipped (its exact zeros would not change a bit of the sums; a NaN weight counts
+    // as non-zero and propagates).
+    const unsigned nzmask = __ballot_sync(0xffffffffu, e != 0.0f);
+    const float* ew = e_s + warp * 32;
+    const int ncol2 = 2 * T;
+    const float* nz_rows = (kPhilox ? noise_out_e : P.noise_in + eK * 2 * T) + static_cast<size_t>(warp_first) * 2 * T;
+    const float lo = (lane & 1) ? C.u_min1 : C.u_min0, hi = (lane & 1) ? C.u_max1 : C.u_max0;  // column parity = lane parity
+    for (int c0 = 0; c0 < ncol2; c0 += 128) {
+      float acc[4][4];
+      float um[4];
+      int cc[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        cc[i] = c0 + 32 * i + lane;
+        um[i] = cc[i] < ncol2 ? uprev_s[cc[i]] : 0.0f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[q][i] = 0.0f;
+      }
+#pragma unroll 1
+      for (int r0 = 0; r0 < 32; r0 += 16) {
+        if (((nzmask >> r0) & 0xFFFFu) == 0u) continue;
+        float v[16][4];
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            v[j][i] = (r0 + j < warp_rows && cc[i] < ncol2) ? __ldcg(nz_rows + (r0 + j) * ncol2 + cc[i]) : 0.0f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float ej = ew[r0 + j];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[j & 3][i] = fmaf(ej, clampf(__fadd_rn(um[i], v[j][i]), lo, hi), acc[j & 3][i]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (cc[i] < ncol2) warpu_s[warp * ncol2 + cc[i]] = (acc[0][i] + acc[1][i]) + (acc[2][i] + acc[3][i]);
+    }
+  } else {
     const float4* e4 = reinterpret_cast<const float4*>(e_s + warp * 32);
     for (int c = lane; c < 2 * T; c += 32) {
       const float* col = nz_w + c;
@@ -874,15 +1187,209 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
   __syncthreads();
   float s_cta = 0.0f;
   for (int w = 0; w < nwarps; ++w) s_cta += red_s[8 + w];
+  // Distributed schedule (P.coop == 2): the partial leaves as self-validating {value, launch epoch} words, so the
+  // CTAs that consume it need neither a fence nor a grid barrier -- seeing the epoch IS the synchronisation.
+  uint2* const pll_u_e = P.part_ll_u + (eB + blockIdx.x) * 2 * T;   // this CTA's [2T] column sums
+  uint2* const pll_ms_e = P.part_ll_ms + (eB + blockIdx.x) * 2;     // this CTA's (max score, sum exp)
   for (int c = tid; c < 2 * T; c += blockDim.x) {
     float acc = 0.0f;
     for (int w = 0; w < nwarps; ++w) acc += warpu_s[w * 2 * T + c];
-    part_u_e[static_cast<size_t>(blockIdx.x) * 2 * T + c] = acc;
+    if (P.coop == 2) st_ll(pll_u_e + c, acc, epoch);
+    else part_u_e[static_cast<size_t>(blockIdx.x) * 2 * T + c] = acc;
   }
   if (tid == 0) {
-    part_ms_e[2 * blockIdx.x + 0] = m_cta;
-    part_ms_e[2 * blockIdx.x + 1] = s_cta;
+    if (P.coop == 2) {
+      st_ll(pll_ms_e, m_cta, epoch);
+      st_ll(pll_ms_e + 1, s_cta, epoch);
+    } else {
+      part_ms_e[2 * blockIdx.x + 0] = m_cta;
+      part_ms_e[2 * blockIdx.x + 1] = s_cta;
+    }
   }
+  const long long t_part = clock64();
+  // ---- Epilogue, distributed schedule (P.coop == 2; the whole grid is co-resident: cooperative launch).
+  // EVERY CTA merges for itself: one warp collects all (m_g, s_g) words -- 2 KB -- and the CTA's own column(s) of the
+  // U_g words -- 1 KB per column -- polling until each carries this launch's epoch, which gives the CTA (M, S) for its
+  // weights and u*[c] for its columns.  The columns travel, again as LL words, to CTA 0 of the environment, which runs
+  // the serial optimal rollout.  After the last CTA's partial is computed the critical path is: its LL stores reach
+  // L2, the column owners' next poll sees them, a warp reduction, one more LL hop -- no fence, no atomic, no barrier
+  // (the round-1 schedule: fence + atomic ticket, 52 KB of partials into ONE SM, four CTA barriers, a release that
+  // the other CTAs wait for).  Fixed lanes and fixed-order sums: bit-reproducible, every CTA computes bit-identical
+  // (M, S).  With peers attached (sharded solver) the column owners also do the exchange over NVLink.
+  if (P.coop == 2) {
+    const int nblk = gridDim.x, ncol = 2 * T;
+    const bool fused = !kBatch && P.world > 1 && P.peer_mbox != nullptr;
+    const bool complete = P.world == 1 || fused;  // (M, S, U) cover every sample of the solver
+    const bool is_final = blockIdx.x == 0;        // runs the optimal rollout of this environment
+    const bool stamp = P.dbg_ts != nullptr && env == 0 && is_final;
+    const uint32_t tag = epoch;
+    const uint2* const all_ms = P.part_ll_ms + eB * 2;
+    const uint2* const all_u = P.part_ll_u + eB * ncol;
+    uint2* ull_e = P.ustar_ll + static_cast<size_t>(env) * ncol;
+    if (stamp && tid == 0) {
+      P.dbg_ts[0] = t_start; P.dbg_ts[1] = t_loop0; P.dbg_ts[2] = t_loop1; P.dbg_ts[3] = t_part;
+    }
+    if (warp == 0) {
+      constexpr int kKeep = 8;  // (m_g, s_g) and one column of up to 256 CTAs stay in registers
+      float2 msr[kKeep];
+      float ucol[kKeep];
+      const int c_first = blockIdx.x;
+      // poll until every word carries the epoch: lanes over CTAs g = lane, lane + 32, ...
+      unsigned pend = 0u;
+#pragma unroll
+      for (int j = 0; j < kKeep; ++j) {
+        msr[j] = make_float2(-FLT_MAX, 0.0f);
+        ucol[j] = 0.0f;
+        if (lane + 32 * j < nblk) pend |= (c_first < ncol ? 3u : 1u) << (2 * j);  // bit 2j: (m, s); bit 2j + 1: column word
+      }
+      const unsigned long long t0 = globaltimer_ns();
+      for (unsigned int spins = 1; __any_sync(0xffffffffu, pend != 0u); ++spins) {
+        // one round: every outstanding word is requested before the first is examined (a round costs one L2 round
+        // trip, not one per word)
+        uint4 wm[kKeep];
+        uint2 wu[kKeep];
+#pragma unroll
+        for (int j = 0; j < kKeep; ++j) {
+          const int g = lane + 32 * j;
+          wm[j] = make_uint4(0u, 0u, 0u, 0u);
+          wu[j] = make_uint2(0u, 0u);
+          if (pend & (1u << (2 * j)))  // {m, tag, s, tag}: two LL words, each validated on its own
+            asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(wm[j].x), "=r"(wm[j].y), "=r"(wm[j].z), "=r"(wm[j].w) : "l"(all_ms + 2 * g) : "memory");
+          if (pend & (2u << (2 * j))) wu[j] = ld_ll(all_u + static_cast<size_t>(g) * ncol + c_first);
+        }
+#pragma unroll
+        for (int j = 0; j < kKeep; ++j) {
+          if ((pend & (1u << (2 * j))) && wm[j].y == tag && wm[j].w == tag) {
+            msr[j] = make_float2(__uint_as_float(wm[j].x), __uint_as_float(wm[j].z));
+            pend &= ~(1u << (2 * j));
+          }
+          if ((pend & (2u << (2 * j))) && wu[j].y == tag) {
+            ucol[j] = __uint_as_float(wu[j].x);
+            pend &= ~(2u << (2 * j));
+          }
+        }
+        if ((spins & 1023u) == 0u && globaltimer_ns() - t0 > kSpinLimitNs) {
+          if (P.err_flag != nullptr) atomicExch(P.err_flag, 1u);
+          pend = 0u;
+        }
+      }
+      if (stamp && lane == 0) P.dbg_ts[4] = clock64();
+      float lm = -FLT_MAX;
+#pragma unroll
+      for (int j = 0; j < kKeep; ++j) lm = fmaxf(lm, msr[j].x);
+      for (int g = lane + 32 * kKeep; g < nblk; g += 32) {  // (grids beyond 256 CTAs: short horizons, several CTAs per SM)
+        lm = fmaxf(lm, wait_ll(all_ms + 2 * g, tag, P.err_flag));
+      }
+      const float Ml = warp_max(lm);
+      float ls = 0.0f;
+#pragma unroll
+      for (int j = 0; j < kKeep; ++j) {
+        msr[j].x = __expf(msr[j].x - Ml);  // a_g (0 for the padding entries: exp(-FLT_MAX - Ml) = 0)
+        ls = fmaf(msr[j].x, msr[j].y, ls);
+      }
+      for (int g = lane + 32 * kKeep; g < nblk; g += 32)
+        ls = fmaf(__expf(wait_ll(all_ms + 2 * g, tag, P.err_flag) - Ml), wait_ll(all_ms + 2 * g + 1, tag, P.err_flag), ls);
+      const float Sl = warp_sum(ls);
+      float Mg = Ml, Sg = Sl;  // after the exchange: over all shards
+      if (stamp && lane == 0) P.dbg_ts[12] = clock64();
+      for (int c = c_first; c < ncol; c += nblk) {
+        float acc = 0.0f;
+#pragma unroll
+        for (int j = 0; j < kKeep; ++j) {
+          const int g = lane + 32 * j;
+          float uv = ucol[j];
+          if (c != c_first) uv = (g < nblk) ? wait_ll(all_u + static_cast<size_t>(g) * ncol + c, tag, P.err_flag) : 0.0f;
+          acc = fmaf(msr[j].x, uv, acc);
+        }
+        for (int g = lane + 32 * kKeep; g < nblk; g += 32)
+          acc = fmaf(__expf(wait_ll(all_ms + 2 * g, tag, P.err_flag) - Ml),
+                     wait_ll(all_u + static_cast<size_t>(g) * ncol + c, tag, P.err_flag), acc);
+        float Uc = warp_sum(acc);
+        if (fused) {
+          ColumnMerge cm{0.0f, 0.0f, 0.0f};
+          if (lane == 0) cm = exchange_column(P, c, ncol, Uc, Ml, Sl);
+          Uc = __shfl_sync(0xffffffffu, cm.U, 0);
+          Mg = __shfl_sync(0xffffffffu, cm.M, 0);
+          Sg = __shfl_sync(0xffffffffu, cm.S, 0);
+        }
+        if (lane == 0) {
+          if (complete) st_ll(ull_e + c, __fdiv_rn(Uc, Sg), tag);  // u*[c] = U[c] / S (mppi.py:196-199)
+          else P.shard_partial[2 + c] = Uc;  // unfused sharding: the host-side exchange + finalize_kernel take over
+        }
+      }
+      if (fused && c_first >= ncol) {  // a CTA without a column still needs the merged (M, S): column 0's cells carry them
+        ColumnMerge cm{0.0f, 0.0f, 0.0f};
+        if (lane == 0) cm = merge_column_cells(P, 0, ncol);
+        Mg = __shfl_sync(0xffffffffu, cm.M, 0);
+        Sg = __shfl_sync(0xffffffffu, cm.S, 0);
+      }
+      if (lane == 0) {
+        red_s[32] = Mg;
+        red_s[33] = complete ? Sg : 1.0f;  // 1/S is deferred to finalize_kernel when unfused-sharded
+        if (!complete && blockIdx.x == 0) {
+          P.shard_partial[0] = Ml;
+          P.shard_partial[1] = Sl;
+        }
+      }
+    }
+    __syncthreads();
+    {
+      // softmax weight of this thread's sample straight from registers (mppi.py:193)
+      const float Mw = red_s[32], Sw = red_s[33];
+      if (valid) weights_e[k] = e * __expf(m_cta - Mw) * __fdiv_rn(1.0f, Sw);
+    }
+    // the slab stores (17 MB over the grid) leave last: issued before the merge's traffic they were measured to stretch
+    // its L2 round trips from ~0.8k to ~3k cycles each
+    if (!kWide)
+      store_slabs<kRecord, kPhilox>(P, rec_e, noise_out_e, rec_s, nz_w, warp, lane, warp_first, warp_rows, nz_bytes);
+    if (is_final && complete && warp == 0) {
+      // collect u* from the column owners, publish it, run the batch-1 optimal rollout (mppi.py:202-214)
+      float* u_out_e = P.u_out + static_cast<size_t>(env) * ncol;
+      for (int c0 = 0; c0 < ncol; c0 += 128) {  // four words per lane requested per round
+        uint2 wv[4];
+        unsigned need = 0u;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (c0 + 32 * i + lane < ncol) need |= 1u << i;
+        const unsigned long long t0 = globaltimer_ns();
+        for (unsigned int spins = 1; need != 0u; ++spins) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (need & (1u << i)) wv[i] = ld_ll(ull_e + c0 + 32 * i + lane);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if ((need & (1u << i)) && wv[i].y == tag) {
+              const int c = c0 + 32 * i + lane;
+              const float u = __uint_as_float(wv[i].x);
+              warpu_s[c] = clampf(u, (c & 1) ? C.u_min1 : C.u_min0, (c & 1) ? C.u_max1 : C.u_max0);
+              u_out_e[c] = u;
+              if (P.keep_mean) u_prev_e[c] = u;  // next call's mean sequence, unshifted (mppi.py:217)
+              need &= ~(1u << i);
+            }
+          }
+          if ((spins & 1023u) == 0u && globaltimer_ns() - t0 > kSpinLimitNs) {
+            if (P.err_flag != nullptr) atomicExch(P.err_flag, 1u);
+            need = 0u;
+          }
+        }
+      }
+      __syncwarp();
+      if (stamp) BNV_STAMP(6);
+      if (lane == 0) {
+        const XiSource xs{(kStoch && !kPhilox) ? P.xi_opt_in + static_cast<size_t>(env) * T : nullptr, kOptimalSample,
+                          iter_lo, iter_hi_e, key};
+        optimal_rollout<kPatch, kPow2, kFastAngles, kStoch>(T, C, warpu_s, sx, sy, sth,
+                                                            P.opt_rec + static_cast<size_t>(env) * 3 * (T + 1), xs);
+        signal_done(P);
+      }
+      if (stamp) BNV_STAMP(7);
+    }
+    if (!kWide && (kRecord || kPhilox)) bulk_wait_read_all();
+    if (stamp) BNV_STAMP_ANY(10, 32);
+    return;
+  }
+
   // Two epilogue schedules.  coop (the whole grid is co-resident; cooperative launch): the slab stores (17 MB over
   // the grid) are held back until the last CTA has merged the partials -- issued earlier, their burst through
   // L2 was measured to stretch the merge's loads from ~0.8k to ~3k cycles each -- and every CTA normalises its own
@@ -891,36 +1398,51 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
   const bool coop = P.coop != 0;
   if (!coop) {
     if (valid) weights_e[k] = e;  // exp(score - m_cta); rescaled by the last CTA
-    store_slabs<kRecord, kPhilox>(P, rec_e, noise_out_e, rec_s, nz_w, warp, lane, warp_first, warp_rows, nz_bytes);
+    if (!kWide)
+      store_slabs<kRecord, kPhilox>(P, rec_e, noise_out_e, rec_s, nz_w, warp, lane, warp_first, warp_rows, nz_bytes);
   }
-  const long long t_part = clock64();
 
   // ---- grid-wide merge (per environment) by the last CTA to finish (atomic ticket).  The CTA barrier orders every
   // thread's writes before thread 0's acq_rel atomic (cumulativity): the release half publishes this CTA's partial,
   // the acquire half (in the CTA that draws the last ticket) makes every other CTA's partial visible to the loads below.
+  // Grids of more than kTwoLevelMin CTAs (several waves: the wide variant at K >= 32768) merge in two levels: the
+  // last CTA of every group of kMergeGroup consecutive CTAs merges its group's partials into one group partial, the
+  // last group to finish merges those -- each merge reads a few KB instead of the whole array (512 CTAs: 209 KB into
+  // one SM, measured 12 us), and the group merges overlap the rollouts still running.
+  const int nblk_all = gridDim.x;
+  const int ncol = 2 * T;
+  const bool two_level = !coop && nblk_all > kTwoLevelMin;
+  const int ngroups = (nblk_all + kMergeGroup - 1) / kMergeGroup;
+  const int my_group = blockIdx.x / kMergeGroup;
+  const int group_cnt = min(kMergeGroup, nblk_all - my_group * kMergeGroup);
+  unsigned int* const ticket_grp_e = P.ticket_grp + static_cast<size_t>(env) * P.max_groups;
+  float* const part2_ms_e = P.part2_ms + static_cast<size_t>(env) * P.max_groups * 2;
+  float* const part2_u_e = P.part2_u + static_cast<size_t>(env) * P.max_groups * ncol;
   __syncthreads();
   if (tid == 0) {
-    unsigned int prev = atom_add_acq_rel_gpu(ticket_e, 1u);
-    *last_flag = (prev == gridDim.x - 1) ? 1 : 0;
+    if (two_level) {
+      const unsigned int prev = atom_add_acq_rel_gpu(ticket_grp_e + my_group, 1u);
+      *last_flag = (prev == static_cast<unsigned int>(group_cnt) - 1u) ? 2 : 0;
+      if (*last_flag) ticket_grp_e[my_group] = 0u;  // every member has arrived: re-arm for the next launch
+    } else {
+      const unsigned int prev = atom_add_acq_rel_gpu(ticket_e, 1u);
+      *last_flag = (prev == gridDim.x - 1) ? 1 : 0;
+    }
   }
   __syncthreads();
-  const bool is_last = *last_flag != 0;
+  int role = *last_flag;  // 0 = done after the partial, 1 = merges the grid (or the groups), 2 = merges its group
   float M = 0.0f, S = 1.0f;
-  if (is_last) {
-    const bool stamp = P.dbg_ts != nullptr && env == 0;
-    if (stamp && tid == 0) {
-      P.dbg_ts[0] = t_start; P.dbg_ts[1] = t_loop0; P.dbg_ts[2] = t_loop1; P.dbg_ts[3] = t_part;
-    }
-    if (stamp) BNV_STAMP(4);
-    const int nblk = gridDim.x;
-    const int ncol = 2 * T;
-    float* a_s = reinterpret_cast<float*>(smem + L.off_merge);  // per-CTA rescale factors exp(m_g - M)
-    float* grp_s = a_s + kMergeACap;                             // [ngrp][ncol] partial column sums
+  const bool stamp = P.dbg_ts != nullptr && env == 0;
+  float* a_s = reinterpret_cast<float*>(smem + L.off_merge);  // per-CTA rescale factors exp(m_g - M)
+  float* grp_s = a_s + kMergeACap;                             // [ngrp][ncol] partial column sums
+  // LSE merge of `nblk` partials (ms_src [nblk][2], u_src [nblk][2T]) by this CTA: leaves M, S and the un-normalised
+  // column sums U in uprev_s.  Called by every thread of the CTA.
+  auto merge_partials = [&](const float* part_ms_e, const float* part_u_e, const int nblk) {
     // Fast path (2T a multiple of 4, one float4 column unit per thread, every a_g in shared memory): everything the
     // merge needs from other SMs -- (m_g, s_g) and this thread's share of the U_g rows -- is requested up front and
     // consumed from registers, so the merge costs one L2 round trip.  Fixed assignment and fixed-order sums keep
     // the result bit-reproducible.
-    constexpr int kMsCache = 8, kMergeBatch = 32;
+    constexpr int kMsCache = 8, kMergeBatch = kWide ? 8 : 32;  // (the wide variant lives within 128 registers)
     const int nunit = ncol >> 2;
     const bool fast_merge = (ncol & 3) == 0 && nunit <= static_cast<int>(blockDim.x) && nblk <= kMergeACap &&
                             ncol <= kMergeGrpCap && nblk <= kMsCache * static_cast<int>(blockDim.x);
@@ -981,13 +1503,23 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
             acc.w = fmaf(a, pv[j].w, acc.w);
           }
         }
-        for (int j = kMergeBatch; j < cnt; ++j) {  // more CTAs than one batch covers (K beyond ~500k samples)
-          const float a = ap[j * ngrp];
-          const float4 v4 = __ldcg(src + j * stride4);
-          acc.x = fmaf(a, v4.x, acc.x);
-          acc.y = fmaf(a, v4.y, acc.y);
-          acc.z = fmaf(a, v4.z, acc.z);
-          acc.w = fmaf(a, v4.w, acc.w);
+        for (int j0 = kMergeBatch; j0 < cnt; j0 += 8) {  // more CTAs than the first batch covers: eight loads at a time
+          float4 q[8];
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            q[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j0 + jj < cnt) q[jj] = __ldcg(src + (j0 + jj) * stride4);
+          }
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            if (j0 + jj < cnt) {
+              const float a = ap[(j0 + jj) * ngrp];
+              acc.x = fmaf(a, q[jj].x, acc.x);
+              acc.y = fmaf(a, q[jj].y, acc.y);
+              acc.z = fmaf(a, q[jj].z, acc.z);
+              acc.w = fmaf(a, q[jj].w, acc.w);
+            }
+          }
         }
         *reinterpret_cast<float4*>(grp_s + grp * ncol + unit * 4) = acc;
       }
@@ -1019,48 +1551,48 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
     for (int c = tid; c < ncol; c += blockDim.x) {
       float acc = 0.0f;
       for (int gq = 0; gq < ngrp; ++gq) acc += grp_s[gq * ncol + c];
-      uprev_s[c] = acc;  // U of this shard, un-normalised
+      uprev_s[c] = acc;  // U of these partials, un-normalised
     }
     __syncthreads();
-    // ---- sharded softmax, fused exchange over NVLink peer memory: every rank's last CTA writes its shard partial
-    // (M, S, U) into its slot of every peer's mailbox, raises the slot's flag (release.sys), waits for the W flags of
-    // its own mailbox and merges the W partials in rank order -- identical arithmetic on every rank, so every rank
-    // holds the same u*.  Mailboxes are double-buffered by the parity of the exchange sequence number: a rank can
-    // be at most one iteration ahead of the slowest peer.
+  };
+  if (role != 0 && stamp && tid == 0) {
+    P.dbg_ts[0] = t_start; P.dbg_ts[1] = t_loop0; P.dbg_ts[2] = t_loop1; P.dbg_ts[3] = t_part; P.dbg_ts[4] = clock64();
+  }
+  if (role == 2) {
+    merge_partials(part_ms_e + 2 * my_group * kMergeGroup, part_u_e + static_cast<size_t>(my_group) * kMergeGroup * ncol,
+                   group_cnt);
+    if (tid == 0) {
+      part2_ms_e[2 * my_group + 0] = M;
+      part2_ms_e[2 * my_group + 1] = S;
+    }
+    for (int c = tid; c < ncol; c += blockDim.x) part2_u_e[static_cast<size_t>(my_group) * ncol + c] = uprev_s[c];
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned int prev = atom_add_acq_rel_gpu(ticket_e, 1u);
+      *last_flag = (prev == static_cast<unsigned int>(ngroups) - 1u) ? 1 : 0;
+    }
+    __syncthreads();
+    role = *last_flag;
+    if (role == 1) merge_partials(part2_ms_e, part2_u_e, ngroups);
+  } else if (role == 1) {
+    merge_partials(part_ms_e, part_u_e, nblk_all);
+  }
+  const bool is_last = role == 1;
+  if (is_last) {
+    // ---- sharded softmax, fused exchange over NVLink peer memory (exchange_column): one thread per column
     const bool fused = !kBatch && P.world > 1 && P.peer_mbox != nullptr;
-    float m_shard = M;  // reference of the per-sample exponentials already computed on this shard
     if (fused) {
-      const int W = P.world, plen = 2 + ncol, slot = plen + 2;
-      const size_t my_slot = (static_cast<size_t>(P.xchg_seq & 1u) * W + P.rank) * slot;
-      for (int r = 0; r < W; ++r) {
-        float* dst = P.peer_mbox[r] + my_slot;
-        for (int c = tid; c < ncol; c += blockDim.x) dst[2 + c] = uprev_s[c];
-        if (tid == 0) {
-          dst[0] = M;
-          dst[1] = S;
+      for (int c = tid; c < ncol; c += blockDim.x) {
+        const ColumnMerge cm = exchange_column(P, c, ncol, uprev_s[c], M, S);
+        uprev_s[c] = cm.U;
+        if (c == 0) {
+          red_s[34] = cm.M;
+          red_s[35] = cm.S;
         }
       }
       __syncthreads();
-      if (tid < W) {
-        unsigned int* flag = reinterpret_cast<unsigned int*>(P.peer_mbox[tid] + my_slot + plen);
-        st_release_sys(flag, P.xchg_seq);
-        const float* mine = P.peer_mbox[P.rank] + (static_cast<size_t>(P.xchg_seq & 1u) * W + tid) * slot;
-        while (ld_acquire_sys(reinterpret_cast<const unsigned int*>(mine + plen)) != P.xchg_seq) __nanosleep(64);
-      }
-      __syncthreads();
-      const float* box = P.peer_mbox[P.rank] + static_cast<size_t>(P.xchg_seq & 1u) * W * slot;
-      float Mg = -FLT_MAX;
-      for (int r = 0; r < W; ++r) Mg = fmaxf(Mg, __ldcg(box + r * slot));
-      float Sg = 0.0f;
-      for (int r = 0; r < W; ++r) Sg = fmaf(__expf(__ldcg(box + r * slot) - Mg), __ldcg(box + r * slot + 1), Sg);
-      for (int c = tid; c < ncol; c += blockDim.x) {
-        float acc = 0.0f;
-        for (int r = 0; r < W; ++r) acc = fmaf(__expf(__ldcg(box + r * slot) - Mg), __ldcg(box + r * slot + 2 + c), acc);
-        uprev_s[c] = acc;
-      }
-      M = Mg;
-      S = Sg;
-      __syncthreads();
+      M = red_s[34];
+      S = red_s[35];
     }
     const bool complete = P.world == 1 || fused;  // (M, S, U) now cover every sample of the solver
     // publish (M, S) and release the waiting CTAs as early as possible -- from the LAST thread: the release is a
@@ -1098,15 +1630,18 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
       __syncthreads();
     }
     if (stamp) BNV_STAMP(5);
-    if (tid == 0) *ticket_e = 0u;  // re-arm for the next launch
+    if (tid == 0) *ticket_e = 0u;  // re-arm for the next launch (all arrivals of this one have happened)
     if (stamp) BNV_STAMP(6);
     if (!coop) {
-      // the other warps rescale every sample's weight underneath warp 0's serial optimal rollout:
-      // weights[k] = exp(score_k - m_cta) * exp(m_cta - M) / S (softmax, mppi.py:193; 1/S deferred when unfused-sharded)
-      const float inv_s = complete ? __fdiv_rn(__expf(m_shard - M), S) : 1.0f;
-      const bool own_thread = complete && blockDim.x > 32;
-      auto scale_of = [&](int g) { return fast_merge ? a_s[g] : __expf(__ldcg(part_ms_e + 2 * g) - m_shard); };
+      // (M, S) for normalize_weights_kernel, launched right behind this kernel: weights[k] = exp(score_k - m_cta) *
+      // exp(m_cta - M) / S (softmax, mppi.py:193; 1/S deferred to finalize_kernel when unfused-sharded).  Rescaling
+      // all K weights here, by one CTA, was the longest serial piece of a large launch (1 MB through one SM).
+      if (tid == 32 % blockDim.x) {
+        stats_e[0] = M;
+        stats_e[1] = complete ? S : 1.0f;
+      }
       if (complete && tid == 0) {
+        if (kWide) C.pin_all();  // the serial rollout is a pure latency chain: its invariants belong in registers
         const XiSource xs{(kStoch && !kPhilox) ? P.xi_opt_in + static_cast<size_t>(env) * T : nullptr, kOptimalSample,
                           iter_lo, iter_hi_e, key};
         optimal_rollout<kPatch, kPow2, kFastAngles, kStoch>(T, C, warpu_s, sx, sy, sth,
@@ -1114,12 +1649,6 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
         signal_done(P);
       }
       if (stamp) BNV_STAMP(7);
-      if (!(own_thread && tid < 32)) {
-        if (!own_thread) __syncwarp();
-        rescale_weights(weights_e, P.Kl, 31 - __clz(spb), own_thread ? tid - 32 : tid,
-                        own_thread ? static_cast<int>(blockDim.x) - 32 : static_cast<int>(blockDim.x),
-                        [&](int g) { return scale_of(g) * inv_s; });
-      }
     }
   } else if (coop) {
     // wait for the last CTA's merge (all CTAs are co-resident: cooperative launch), then pick up (M, S)
@@ -1134,7 +1663,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
     // softmax weight of this thread's sample straight from registers (mppi.py:193; 1/S deferred when unfused-sharded)
     const bool complete = P.world == 1 || (!kBatch && P.peer_mbox != nullptr);
     if (valid) weights_e[k] = e * __expf(m_cta - M) * (complete ? __fdiv_rn(1.0f, S) : 1.0f);
-    store_slabs<kRecord, kPhilox>(P, rec_e, noise_out_e, rec_s, nz_w, warp, lane, warp_first, warp_rows, nz_bytes);
+    if (!kWide)
+      store_slabs<kRecord, kPhilox>(P, rec_e, noise_out_e, rec_s, nz_w, warp, lane, warp_first, warp_rows, nz_bytes);
     if (is_last && complete && tid == 0) {
       const XiSource xs{(kStoch && !kPhilox) ? P.xi_opt_in + static_cast<size_t>(env) * T : nullptr, kOptimalSample,
                         iter_lo, iter_hi_e, key};
@@ -1145,7 +1675,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) rollout_kernel(const __grid
     if (is_last && P.dbg_ts != nullptr && env == 0) BNV_STAMP(7);
   }
   // shared memory must stay allocated until the bulk stores have read it
-  if (kRecord || kPhilox) bulk_wait_read_all();
+  if (!kWide && (kRecord || kPhilox)) bulk_wait_read_all();
   if (is_last && P.dbg_ts != nullptr && env == 0) BNV_STAMP_ANY(10, 32);
 }
 

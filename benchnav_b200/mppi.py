@@ -375,6 +375,12 @@ class MPPI(nn.Module):
     def launch_count(self) -> int:
         return int(self._lib.bnv_mppi_launch_count(self._handle))
 
+    def check(self) -> None:
+        """Synchronise and raise if an in-kernel wait of an earlier iteration timed out (a peer rank of a sharded
+        solver never delivered its softmax partial)."""
+        with torch.cuda.device(self._device):
+            _cabi.check(self._lib.bnv_mppi_check(self._handle, self._stream()))
+
     @property
     def launch_geometry(self) -> dict:
         """Rollout-kernel launch shape: CTAs, warps per CTA, recorded-state slab split step (0 = one flush), cooperative."""

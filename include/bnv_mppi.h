@@ -150,8 +150,11 @@ int bnv_mppi_finalize(bnv_mppi* h, const float* gathered_partials_dev, float* u_
 /* Fused exchange over NVLink peer memory (replaces the host-side all-gather + bnv_mppi_finalize pair): every rank
  * exports the CUDA IPC handle of its mailbox (64 bytes), the handles are gathered by the caller (any transport,
  * rank-major) and attached once.  Afterwards bnv_mppi_forward on a sharded handle exchanges the shard partials
- * inside the rollout kernel (P2P stores + release/acquire flags, double-buffered) and writes u_out/opt_states
- * itself; all ranks must call forward the same number of times (as with any collective). */
+ * inside the rollout kernel -- every column of the partial travels as self-validating 8-byte {value, sequence} words
+ * stored straight into the peers' mailboxes, double-buffered by the parity of the sequence number; no fence, no flag,
+ * no NCCL call -- and writes u_out/opt_states itself; all ranks must call forward the same number of times (as with
+ * any collective).  A peer that does not deliver within 2 s makes the waiting kernel give up instead of hanging the
+ * device; bnv_mppi_check() then reports the failure. */
 int bnv_mppi_mailbox_handle(bnv_mppi* h, unsigned char out[64]);
 int bnv_mppi_attach_peers(bnv_mppi* h, const unsigned char* handles /* [world_size][64] */);
 
@@ -234,6 +237,11 @@ int bnv_mppi_dwa_subgoal(bnv_mppi* h, const float* path_dev, int32_t n, const fl
 
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 uint64_t bnv_mppi_launch_count(const bnv_mppi* h);
+
+/* Synchronises `stream` and reports whether an in-kernel wait of an earlier iteration timed out (sharded solvers: a
+ * peer rank never delivered its partial).  BNV_OK, or BNV_ERR_CUDA with the reason in bnv_last_error(); the error
+ * state is cleared by the call. */
+int bnv_mppi_check(bnv_mppi* h, void* stream);
 
 /* Launch geometry chosen for the rollout kernel by the last bnv_mppi_set_problem*: out = {CTAs per environment,
  * warps per CTA, the step at which the recorded-state slab is flushed mid-loop (0 = one flush at the end),

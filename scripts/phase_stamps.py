@@ -17,8 +17,11 @@ dyn = UnicycleProblem(GridSpec(G, 0.5), risk)
 s = MPPI(T, K, 3, 2, dyn, GoalObjectives(dyn, goal, thr), torch.tensor([0.5, 0.5]), 0.5, device=torch.device("cuda"))
 st = start.cuda()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-names = ["start", "loop0", "loop1", "partial", "last:enter", "last:merged", "last:u_out", "last:opt_done", "last:w_begin",
-         "last:w_done", "last:exit", "m:fence", "m:ms_loaded", "m:M_sync", "m:S_sync", "m:fma_done"]
+# distributed schedule (default): 4 = barrier passed, 12 = (M, S) known, 5 = weights' (M, S) in smem, 6 = u* gathered,
+# 7 = optimal rollout done, 10 = exit; round-1 schedule / wave schedule: 4 = merge entered, 12..15 merge internals,
+# 5 = merged, 7 = optimal rollout done
+names = ["start", "loop0", "loop1", "partial", "barrier|enter", "ms_smem|merged", "u*_gathered|u_out", "opt_done", "-",
+         "-", "exit", "-", "MS_known|ms_loaded", "M_sync", "S_sync", "fma_done"]
 INJECT = os.environ.get("BNV_STAMPS_INJECT") == "1"  # injected noise: the T-loop without the in-loop Philox draw
 nz = (torch.randn(K, T, 2, device="cuda") * 0.5) if INJECT else None
 for it in range(6):

@@ -43,15 +43,21 @@ def test_sm100a_only_sass_with_tma_and_bulk_copies():
     assert "sm_100a" in sass
     funcs = sass.split("Function : ")[1:]
     rollouts = [f for f in funcs if "rollout_kernel" in f.splitlines()[0]]
-    # single solver: kPatch x kPow2 x kRecord x kFastAngles x kPhilox = 32; stochastic and/or batched modes
-    # (record + fast angles only): 3 x kPatch x kPow2 x kPhilox = 24
-    assert len(rollouts) == 56
+    # latency variant -- single solver: kPatch x kPow2 x kRecord x kFastAngles x kPhilox = 32; stochastic and/or batched
+    # modes (record + fast angles only): 3 x kPatch x kPow2 x kPhilox = 24; wide variant (fast angles only) -- single
+    # solver: kPatch x kPow2 x kRecord x kPhilox = 16; stochastic and/or batched: 24
+    assert len(rollouts) == 96
+    n_wide = 0
     for f in rollouts:
         name = f.splitlines()[0]
         patch = "rollout_kernelILb1E" in name
+        wide = name.split("EEEv")[0].endswith("Lb1")  # last template flag
+        n_wide += wide
         assert ("UTMALDG.2D" in f) == patch, name  # the TMA window load exists exactly in the kPatch variants
-        assert "UBLKCP" in f, name                 # bulk slab copies
+        # bulk slab copies in the latency variant; the wide variant flushes its chunks with coalesced vector stores
+        assert ("UBLKCP" in f) == (not wide), name
         assert "HMMA" not in f and "UTCHMMA" not in f  # no tensor cores on this path
+    assert n_wide == 40
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-box behaviour")
