@@ -434,11 +434,15 @@ def make_native(w: dict, dev, group, exchange: str, world: int, rank: int):
                                                              "kernel over NVLink peer memory" if solver._fused_exchange
                                                              else ", NCCL all-gather + finalize kernel"))
     return {"solver": solver, "step": lambda: solver.forward(st_dev),
-            "e2e_step": (lambda: solver.forward_host(st_pin, out=outs)) if world == 1 else None,
+            "e2e_step": (lambda: solver.forward_host(st_pin, out=outs)) if (world == 1 or rank == 0) else
+                        ((lambda: solver.forward_follow()) if solver._fused_exchange else None),
             "h2d": 12, "d2h": 4 * (2 * t_h + 3 * (t_h + 1)),
             "e2e_how": "forward_host(state, out=caller buffers): the 12-byte state rides in the launch packet (or a "
                        "pinned, device-mapped mailbox when pre-launched), the kernel stores u* and the optimal state "
-                       "sequence into pinned mapped host memory and raises a completion word the host polls; wall clock",
+                       "sequence into pinned mapped host memory and raises a completion word the host polls; wall clock" +
+                       ("" if world == 1 else "; sharded: the control loop runs on rank 0 (its kernel broadcasts the state "
+                        "to the other ranks over NVLink), every other rank calls forward_follow(), whose kernel waits on "
+                        "the device for that state; rank 0's wall clock per step, its host buffers receive the results"),
             "alg_bytes": algorithmic_bytes(k_l, t_h, g, channels), "units": 1, "local_samples": k_l,
             "parallelism": par, "start": start, "state_dev": st_dev}
 
@@ -550,6 +554,11 @@ def run_native(args) -> None:
 
     # ---- end to end through the host-buffer call
     e2e = None
+    if world > 1 and w["kind"] == "single":  # every rank must take part (or none): agree on it
+        ok = torch.tensor([1 if nat["e2e_step"] is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            nat["e2e_step"] = None
     if nat["e2e_step"] is not None:
         n_e = min(steps, 2000)
         cur = torch.cuda.current_stream(dev)
@@ -561,20 +570,28 @@ def run_native(args) -> None:
             for _ in range(3):
                 e2e_step()
             total = 0.0
+            follower = sharded and rank != 0  # enqueues only: its kernels wait on the device for the leader's state
             for i in range(n):
                 flush.fill_(i & 0xFF)
-                cur.synchronize()
+                if not follower:
+                    cur.synchronize()
                 t0 = time.perf_counter()
                 e2e_step()
                 total += time.perf_counter() - t0
             return total
 
         barrier()
-        acc_plain = max_over_ranks(e2e_pass(n_e))
+        acc_plain = e2e_pass(n_e)
+        if sharded:  # followers only enqueue (they run ahead of the leader on purpose): the leader's clock counts
+            barrier()
+            solver.check()
+            acc_plain = max_over_ranks(acc_plain if rank == 0 else 0.0)
+        else:
+            acc_plain = max_over_ranks(acc_plain)
         factor = unit_factor(w, world)
         e2e = {"value": n_e / acc_plain * factor, "unit": UNIT, "h2d_bytes_per_step": nat["h2d"],
                "d2h_bytes_per_step": nat["d2h"], "steps": n_e, "mode": "plain launches", "timing": nat["e2e_how"]}
-        if w["kind"] != "batch":
+        if w["kind"] != "batch" and world == 1:
             # the same call with the next iteration's kernel pre-launched (opt-in, solver.prelaunch()): the kernel is
             # resident and polling a host-mapped mailbox when the state arrives.  Reported beside the plain number; the
             # headline `value` of e2e is the better of the two and `mode` says which.
@@ -618,7 +635,8 @@ def run_native(args) -> None:
             for _ in range(3):
                 single_ref.forward(st)
             ms_1 = timed_pass(lambda: single_ref.forward(st), n_s, sync=lambda: torch.cuda.synchronize(dev)) / n_s
-            single_same = {"single_gpu_same_total_ms": ms_1, "steps": n_s, "launch": single_ref.launch_geometry}
+            single_same = {"single_gpu_same_total_ms": ms_1, "single_gpu_steps": n_s,
+                           "single_gpu_launch": single_ref.launch_geometry}
         barrier()
 
     if rank != 0:

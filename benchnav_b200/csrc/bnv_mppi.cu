@@ -95,11 +95,6 @@ struct bnv_mppi {
   float* shard_partial = nullptr;
   float* io_dev = nullptr;  // [3] state + [2T] u_out + [3(T+1)] opt states, staging for forward_host
   unsigned int* ticket = nullptr;
-  uint2* part_ll_u = nullptr;            // [E][max_grid][2T] per-CTA partials as LL words (distributed epilogue)
-  uint2* part_ll_ms = nullptr;           // [E][max_grid][2]
-  size_t part_ll_words = 0;              // uint2 words in part_ll_u + part_ll_ms (for the clears)
-  unsigned long long* arrive = nullptr;  // (reserved)
-  uint2* ustar_ll = nullptr;             // [E][2T] LL words of u*
   unsigned int* ticket_grp = nullptr;    // [E][max_groups]
   float* part2_ms = nullptr;             // [E][max_groups][2]
   float* part2_u = nullptr;              // [E][max_groups][2T]
@@ -164,10 +159,6 @@ void free_all(bnv_mppi* h) {
   cudaFree(h->shard_partial);
   cudaFree(h->io_dev);
   cudaFree(h->ticket);
-  cudaFree(h->arrive);
-  cudaFree(h->part_ll_u);
-  cudaFree(h->part_ll_ms);
-  cudaFree(h->ustar_ll);
   cudaFree(h->ticket_grp);
   cudaFree(h->part2_ms);
   cudaFree(h->part2_u);
@@ -312,17 +303,6 @@ int configure_launch(bnv_mppi* h) {
 
 }  // namespace
 
-// LL words carry the launch epoch as their tag; when the epoch's source changes (by value <-> device counter) stale
-// tags could collide with new ones: wipe them.
-static cudaError_t clear_ll_words(bnv_mppi* h, cudaStream_t s) {
-  const size_t nE = static_cast<size_t>(h->E), T = static_cast<size_t>(h->P.T);
-  const size_t max_grid = (static_cast<size_t>(h->Kl) + 31) / 32;
-  cudaError_t e = cudaMemsetAsync(h->part_ll_u, 0, nE * max_grid * 2 * T * sizeof(uint2), s);
-  if (e == cudaSuccess) e = cudaMemsetAsync(h->part_ll_ms, 0, nE * max_grid * 2 * sizeof(uint2), s);
-  if (e == cudaSuccess) e = cudaMemsetAsync(h->ustar_ll, 0, nE * 2 * T * sizeof(uint2), s);
-  return e;
-}
-
 struct PreStats {
   double t_sync = 0, t_post = 0, t_launch = 0, t_wait = 0;
   long calls = 0, posted = 0, fallbacks = 0, retries = 0;
@@ -411,10 +391,6 @@ int bnv_mppi_create(bnv_mppi** out, const bnv_mppi_cfg* cfg) {
   alloc(reinterpret_cast<void**>(&h->ticket), 2 * nE * sizeof(unsigned int));
   h->max_groups = (max_grid + bnv::kMergeGroup - 1) / bnv::kMergeGroup;
   const size_t nG = static_cast<size_t>(h->max_groups);
-  alloc(reinterpret_cast<void**>(&h->arrive), nE * sizeof(unsigned long long));
-  alloc(reinterpret_cast<void**>(&h->part_ll_u), nE * max_grid * 2 * T * sizeof(uint2));
-  alloc(reinterpret_cast<void**>(&h->part_ll_ms), nE * max_grid * 2 * sizeof(uint2));
-  alloc(reinterpret_cast<void**>(&h->ustar_ll), nE * 2 * T * sizeof(uint2));
   alloc(reinterpret_cast<void**>(&h->ticket_grp), nE * nG * sizeof(unsigned int));
   alloc(reinterpret_cast<void**>(&h->part2_ms), sizeof(float) * nE * nG * 2);
   alloc(reinterpret_cast<void**>(&h->part2_u), sizeof(float) * nE * nG * 2 * T);
@@ -422,7 +398,8 @@ int bnv_mppi_create(bnv_mppi** out, const bnv_mppi_cfg* cfg) {
   alloc(reinterpret_cast<void**>(&h->stats), 4 * nE * sizeof(float));
   alloc(reinterpret_cast<void**>(&h->goals_dev), 2 * nE * sizeof(float));
   if (cfg->world_size > 1) {  // mailbox: [2 parities][world ranks][2T columns] cells of three LL words {U[c] | M | S, tag}
-    h->mbox_floats = 2 * static_cast<size_t>(cfg->world_size) * 2 * static_cast<size_t>(T) * 3 * 2;
+    // + [2 parities] state cells of three LL words {x | y | theta, tag} (host-driven sharded solver)
+    h->mbox_floats = 2 * static_cast<size_t>(cfg->world_size) * 2 * static_cast<size_t>(T) * 3 * 2 + 2 * 3 * 2;
     alloc(reinterpret_cast<void**>(&h->mbox), sizeof(float) * h->mbox_floats);
     alloc(reinterpret_cast<void**>(&h->peer_mbox_dev), sizeof(float*) * cfg->world_size);
     if (e == cudaSuccess) e = cudaMemset(h->mbox, 0, sizeof(float) * h->mbox_floats);
@@ -431,10 +408,6 @@ int bnv_mppi_create(bnv_mppi** out, const bnv_mppi_cfg* cfg) {
   if (e == cudaSuccess) std::memset(h->io_host, 0, sizeof(float) * io_floats);
   if (e == cudaSuccess) e = cudaMemset(h->u_prev, 0, sizeof(float) * nE * T * 2);  // mppi.py:116
   if (e == cudaSuccess) e = cudaMemset(h->ticket, 0, 2 * nE * sizeof(unsigned int));
-  if (e == cudaSuccess) e = cudaMemset(h->arrive, 0, nE * sizeof(unsigned long long));
-  if (e == cudaSuccess) e = cudaMemset(h->part_ll_u, 0, nE * max_grid * 2 * T * sizeof(uint2));  // tag 0 = never written
-  if (e == cudaSuccess) e = cudaMemset(h->part_ll_ms, 0, nE * max_grid * 2 * sizeof(uint2));
-  if (e == cudaSuccess) e = cudaMemset(h->ustar_ll, 0, nE * 2 * T * sizeof(uint2));
   if (e == cudaSuccess) e = cudaMemset(h->ticket_grp, 0, nE * nG * sizeof(unsigned int));
   if (e == cudaSuccess) e = cudaMemset(h->err_flag, 0, sizeof(unsigned int));
   if (e == cudaSuccess) e = cudaMemset(h->weights, 0, sizeof(float) * nE * Kl);    // mppi.py:126-128
@@ -483,10 +456,6 @@ int bnv_mppi_create(bnv_mppi** out, const bnv_mppi_cfg* cfg) {
   P.part_u = h->part_u;
   P.shard_partial = h->shard_partial;
   P.ticket = h->ticket;
-  P.arrive = h->arrive;
-  P.part_ll_u = h->part_ll_u;
-  P.part_ll_ms = h->part_ll_ms;
-  P.ustar_ll = h->ustar_ll;
   P.ticket_grp = h->ticket_grp;
   P.part2_ms = h->part2_ms;
   P.part2_u = h->part2_u;
@@ -606,7 +575,6 @@ int bnv_mppi_set_problem_ex(bnv_mppi* h, const float* mean_dev, const float* std
   int rc = configure_launch(h);
   if (rc != BNV_OK) return rc;
   // the launch geometry may have changed: restart the arrival counters (the stream was synchronised above)
-  BNV_CUDA(cudaMemsetAsync(h->arrive, 0, static_cast<size_t>(E) * sizeof(unsigned long long), s));
   BNV_CUDA(cudaMemsetAsync(h->ticket, 0, 2 * static_cast<size_t>(E) * sizeof(unsigned int), s));
   BNV_CUDA(cudaMemsetAsync(h->ticket_grp, 0, static_cast<size_t>(E) * h->max_groups * sizeof(unsigned int), s));
   h->finalize_smem = 128 + (P.use_patch ? ((P.patch_w * P.patch_h + 31) / 32) * 32 * 4 : 0) + 2 * (2 * P.T + 4) * 4 + 16;
@@ -619,7 +587,7 @@ int bnv_mppi_set_problem_ex(bnv_mppi* h, const float* mean_dev, const float* std
 
 static int launch_forward(bnv_mppi* h, const float* state_dev, const float* state_host, const float* noise_dev,
                           float* u_out_dev, float* opt_states_dev, cudaStream_t s, const float* xi_dev = nullptr,
-                          const float* xi_opt_dev = nullptr, unsigned int mailbox_seq = 0) {
+                          const float* xi_opt_dev = nullptr, unsigned int mailbox_seq = 0, int state_role = 0) {
   if (state_host && h->E > 1) return fail(BNV_ERR_INVALID, "batched solver: states must be device-resident [E,3]");
   if (state_host) {  // state travels by value in the launch packet; remembered for finalize (world_size > 1)
     for (int i = 0; i < 3; ++i) h->P.state_val[i] = state_host[i];
@@ -628,6 +596,7 @@ static int launch_forward(bnv_mppi* h, const float* state_dev, const float* stat
     h->P.state_inline = 0;
   }
   bnv::EngineParams P = h->P;
+  P.state_role = state_role;
   const bool philox = noise_dev == nullptr;
   P.noise_in = noise_dev;
   P.noise_out = h->noise;
@@ -656,11 +625,12 @@ static int launch_forward(bnv_mppi* h, const float* state_dev, const float* stat
   const bool coop = h->coop_ok && static_cast<long long>(h->grid) * h->E <= h->resident_ctas;
   h->epoch = (h->epoch == 0xFFFFFFFFu) ? 1u : h->epoch + 1u;
   P.epoch = h->epoch;
-  P.coop = coop ? ((debug_disable() & 8192u) ? 1 : 2) : 0;  // bit 8192: round-1 schedule (last CTA merges), for A/B runs
+  P.coop = coop ? 1 : 0;
   if (h->peers_attached) {
     h->xchg_seq = (h->xchg_seq == 0xFFFFFFFFu) ? 1u : h->xchg_seq + 1u;  // advances in lock-step on every rank
     P.xchg_seq = h->xchg_seq;
     P.peer_mbox = h->peer_mbox_dev;
+    for (size_t r = 0; r < 8; ++r) P.peer_mbox_val[r] = r < h->peer_ptrs.size() ? static_cast<float*>(h->peer_ptrs[r]) : nullptr;
   }
   const bool timed = h->timing && h->ev_used + 2 <= h->ev.size();
   if (timed) BNV_CUDA(cudaEventRecord(h->ev[h->ev_used], s));
@@ -768,6 +738,19 @@ int bnv_mppi_forward_ex(bnv_mppi* h, const float* state_dev, const float* noise_
   BNV_USER_WORK(h, stream);
   return launch_forward(h, state_dev, nullptr, noise_dev, u_out_dev, opt_states_dev, static_cast<cudaStream_t>(stream),
                         xi_dev, xi_opt_dev);
+}
+
+int bnv_mppi_forward_follow(bnv_mppi* h, const float* noise_dev, float* u_out_dev, float* opt_states_dev, void* stream) {
+  if (!h || !u_out_dev || !opt_states_dev) return fail(BNV_ERR_INVALID, "null argument");
+  if (!h->problem_set) return fail(BNV_ERR_STATE, "bnv_mppi_set_problem must be called before forward");
+  if (h->cfg.world_size < 2 || !h->peers_attached)
+    return fail(BNV_ERR_INVALID, "forward_follow needs a sharded solver with attached peers");
+  BNV_CUDA(cudaSetDevice(h->cfg.device));
+  BNV_DRAIN(h);
+  BNV_USER_WORK(h, stream);
+  h->P.state = nullptr;
+  return launch_forward(h, nullptr, nullptr, noise_dev, u_out_dev, opt_states_dev, static_cast<cudaStream_t>(stream),
+                        nullptr, nullptr, 0u, 2);
 }
 
 int bnv_mppi_forward_state(bnv_mppi* h, const float state_host[3], const float* noise_dev, float* u_out_dev,
@@ -900,7 +883,10 @@ int bnv_mppi_forward_host(bnv_mppi* h, const float state_host[3], const float* n
                           float* opt_states_host, void* stream) {
   if (!h || !state_host || !u_out_host || !opt_states_host) return fail(BNV_ERR_INVALID, "null argument");
   if (!h->problem_set) return fail(BNV_ERR_STATE, "bnv_mppi_set_problem must be called before forward");
-  if (h->cfg.world_size != 1 || h->E != 1) return fail(BNV_ERR_INVALID, "forward_host needs world_size == 1 and a single environment");
+  if (h->E != 1) return fail(BNV_ERR_INVALID, "forward_host needs a single environment");
+  if (h->cfg.world_size != 1 && !h->peers_attached)
+    return fail(BNV_ERR_INVALID, "forward_host on a sharded solver needs attached peers (bnv_mppi_attach_peers); the "
+                                 "other ranks call bnv_mppi_forward_follow");
   if (h->stoch && noise_dev) return fail(BNV_ERR_INVALID, "stochastic-slip solver: inject noise through bnv_mppi_forward_ex");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   BNV_CUDA(cudaSetDevice(h->cfg.device));
@@ -916,7 +902,8 @@ int bnv_mppi_forward_host(bnv_mppi* h, const float state_host[3], const float* n
   float* out_dev = h->io_host_dev;
   const size_t flag_off = 3 + 2 * static_cast<size_t>(T) + 3 * static_cast<size_t>(T + 1);
   h->P.done_flag = reinterpret_cast<unsigned int*>(out_dev + flag_off);
-  int rc = launch_forward(h, nullptr, state_host, noise_dev, out_dev + 3, out_dev + 3 + 2 * T, s);
+  int rc = launch_forward(h, nullptr, state_host, noise_dev, out_dev + 3, out_dev + 3 + 2 * T, s, nullptr, nullptr, 0u,
+                          h->cfg.world_size > 1 ? 1 : 0);  // sharded: this rank leads, its kernel broadcasts the state
   h->P.done_flag = nullptr;
   if (rc != BNV_OK) return rc;
   h->user_work = true;
@@ -1095,15 +1082,12 @@ int bnv_mppi_device_counter(bnv_mppi* h, int32_t enable, void* stream) {
     if (!h->iter_dev) BNV_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->iter_dev), sizeof(unsigned long long)));
     const unsigned long long it = h->iteration;
     BNV_CUDA(cudaMemcpyAsync(h->iter_dev, &it, sizeof(it), cudaMemcpyHostToDevice, s));
-    // the "merge done" flags and the LL words hold by-value epochs of earlier launches: clear them (0 is never a
-    // valid epoch)
+    // the "merge done" flags hold by-value epochs of earlier launches: clear them (0 is never a valid epoch)
     BNV_CUDA(cudaMemsetAsync(h->ticket, 0, 2 * static_cast<size_t>(h->E) * sizeof(unsigned int), s));
-    BNV_CUDA(clear_ll_words(h, s));
     BNV_CUDA(cudaStreamSynchronize(s));
     h->P.iter_dev = h->iter_dev;
   } else if (h->iter_dev && h->P.iter_dev) {
     BNV_CUDA(cudaMemsetAsync(h->ticket, 0, 2 * static_cast<size_t>(h->E) * sizeof(unsigned int), s));
-    BNV_CUDA(clear_ll_words(h, s));
     unsigned long long it = 0;
     BNV_CUDA(cudaMemcpyAsync(&it, h->iter_dev, sizeof(it), cudaMemcpyDeviceToHost, s));
     BNV_CUDA(cudaStreamSynchronize(s));

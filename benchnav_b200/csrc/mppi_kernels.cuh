@@ -75,6 +75,9 @@ struct alignas(64) EngineParams {
   const float* state;   // [3] device-resident current state, or
   float state_val[3];   // ... the same three floats passed by value in the launch packet (state_inline != 0)
   int state_inline;
+  int state_role;       // sharded solver driven from ONE rank's host (bnv_mppi_forward_host on the leader,
+                        // bnv_mppi_forward_follow on the others): 1 = leader: broadcast state_val to every peer's state
+                        // cell over NVLink at kernel start; 2 = follower: take the state from this rank's own cell
   const float* noise_in;  // injected noise [Kl][T][2] (kPhilox == false)
   float* noise_out;     // engine noise buffer [Kl][T][2], written when kPhilox
   float* u_prev;        // [T][2]   mean sequence (read at start, replaced by u* at the end)
@@ -84,10 +87,6 @@ struct alignas(64) EngineParams {
   float* part_ms;       // [nCTA][2]   per-CTA (max score, sum exp)
   float* part_u;        // [nCTA][2T]  per-CTA sum exp * v
   float* shard_partial; // [2+2T]      (m, s, U) of this shard
-  uint2* part_ll_u;            // [E][nCTA][2T] per-CTA column sums as LL words {value, launch epoch} (coop == 2)
-  uint2* part_ll_ms;           // [E][nCTA][2]  per-CTA (max score, sum exp) as LL words
-  unsigned long long* arrive;  // (unused by the current schedules; reserved)
-  uint2* ustar_ll;             // [E][2T] {u*[c] bits, tag}: columns of u* handed to the CTA that runs the optimal rollout
   unsigned int* ticket_grp;    // [E][max_groups] arrival counters of the level-1 groups of a two-level merge
   float* part2_ms;             // [E][max_groups][2]   (max score, sum exp) per merged group
   float* part2_u;              // [E][max_groups][2T]  sum exp * v per merged group
@@ -109,10 +108,9 @@ struct alignas(64) EngineParams {
   unsigned int* prelaunch_decision;    // device word, zeroed before the launch: 0 undecided, 1 go, 2 abort
   unsigned int* abort_flag;            // mapped host word: set to `epoch` when the launch aborted
   int keep_mean;         // write u* back as the next call's mean sequence (mppi.py:217); 0 for DWA's constant actions
-  int coop;              // grid is co-resident (cooperative launch): deferred slab stores, in-register weights.
-                         // 2 = distributed merge (every CTA merges its own columns after a grid barrier),
-                         // 1 = the last CTA merges while the others wait (round-1 schedule, kept for A/B runs)
+  int coop;              // grid is co-resident (cooperative launch): deferred slab stores, in-register weights
   float* const* peer_mbox;  // [world] device pointers to every rank's mailbox (peer memory over NVLink), or null
+  float* peer_mbox_val[8];  // the same pointers by value for world <= 8 (one node): no table load on the exchange's path
   unsigned int xchg_seq;    // exchange sequence number (same on every rank), selects the mailbox parity
   int rank;
   float* u_out;         // [T][2]
@@ -537,16 +535,6 @@ __device__ __forceinline__ void st_release_gpu(unsigned int* p, unsigned int v) 
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-__device__ __forceinline__ unsigned long long atom_add_acq_rel_gpu_u64(unsigned long long* p, unsigned long long v) {
-  unsigned long long old;
-  asm volatile("atom.add.acq_rel.gpu.global.u64 %0, [%1], %2;" : "=l"(old) : "l"(p), "l"(v) : "memory");
-  return old;
-}
-__device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
 // Self-validating 8-byte words {value, tag} ("LL" protocol): one aligned 8-byte store is a single memory transaction,
 // so a reader that sees the expected tag also sees the value -- no fence, no separate flag.  volatile = relaxed at
 // system scope: the same two functions serve hand-overs inside the GPU and stores into a peer GPU's memory over NVLink.
@@ -564,17 +552,26 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 constexpr unsigned long long kSpinLimitNs = 2000000000ull;  // 2 s: a peer that never answers must not hang the device
+// Called every 1024 polls of a wait loop: starts the clock on the first call, true once the limit has passed.
+__device__ __forceinline__ bool spin_expired(unsigned long long& t0) {
+  const unsigned long long now = globaltimer_ns();
+  if (t0 == 0ull) {
+    t0 = now;
+    return false;
+  }
+  return now - t0 > kSpinLimitNs;
+}
 
 // Wait for the LL word at `p` to carry `tag`; returns its value.  On a time-out the solver's error word is raised and
 // 0 is returned (the iteration's result is then invalid; bnv_mppi_check reports it).
 __device__ __forceinline__ float wait_ll(const uint2* p, uint32_t tag, unsigned int* err_flag) {
   uint2 w = ld_ll(p);
   if (w.y == tag) return __uint_as_float(w.x);
-  const unsigned long long t0 = globaltimer_ns();
+  unsigned long long t0 = 0ull;  // (read lazily: %globaltimer is slow, and normally nobody waits long enough to need it)
   for (unsigned int spins = 1;; ++spins) {
     w = ld_ll(p);
     if (w.y == tag) return __uint_as_float(w.x);
-    if ((spins & 1023u) == 0u && globaltimer_ns() - t0 > kSpinLimitNs) {
+    if ((spins & 1023u) == 0u && spin_expired(t0)) {
       if (err_flag != nullptr) atomicExch(err_flag, 1u);
       return 0.0f;
     }
@@ -592,7 +589,8 @@ struct ColumnMerge {
 };
 __device__ __forceinline__ const uint2* mailbox_cell(const EngineParams& P, int holder, int src_rank, int c, int ncol) {
   const size_t idx = ((static_cast<size_t>(P.xchg_seq & 1u) * P.world + src_rank) * ncol + c) * 3;
-  return reinterpret_cast<const uint2*>(P.peer_mbox[holder]) + idx;
+  const float* base = P.world <= 8 ? P.peer_mbox_val[holder] : P.peer_mbox[holder];
+  return reinterpret_cast<const uint2*>(base) + idx;
 }
 // Collect the cells (src ranks r0 .. r0 + n - 1, n <= 8) of column c from this rank's own mailbox: all outstanding
 // words are requested before the first is examined, so a round costs one L2 round trip; rounds repeat until every word
@@ -610,7 +608,7 @@ __device__ __forceinline__ void poll_cells(const EngineParams& P, int c, int nco
   }
   const uint2* cell0 = mailbox_cell(P, P.rank, r0, c, ncol);
   const size_t rank_stride = static_cast<size_t>(ncol) * 3;
-  const unsigned long long t0 = globaltimer_ns();
+  unsigned long long t0 = 0ull;  // (read lazily: %globaltimer is slow, and normally nobody waits long enough to need it)
   for (unsigned int spins = 1; pend != 0u; ++spins) {
     uint2 w[8][3];
 #pragma unroll
@@ -631,11 +629,17 @@ __device__ __forceinline__ void poll_cells(const EngineParams& P, int c, int nco
           if (q == 2) S[j] = v;
           pend &= ~(1u << (3 * j + q));
         }
-    if ((spins & 1023u) == 0u && globaltimer_ns() - t0 > kSpinLimitNs) {
+    if ((spins & 1023u) == 0u && spin_expired(t0)) {
       if (P.err_flag != nullptr) atomicExch(P.err_flag, 1u);
       pend = 0u;
     }
   }
+}
+// The leader's state for followers: three LL words {x | y | theta, tag} behind the column cells of the mailbox,
+// double-buffered by the same parity.
+__device__ __forceinline__ const uint2* mailbox_state_cell(const EngineParams& P, int holder, int ncol) {
+  const float* base = P.world <= 8 ? P.peer_mbox_val[holder] : P.peer_mbox[holder];
+  return reinterpret_cast<const uint2*>(base) + static_cast<size_t>(2) * P.world * ncol * 3 + (P.xchg_seq & 1u) * 3;
 }
 __device__ __forceinline__ ColumnMerge merge_column_cells(const EngineParams& P, int c, int ncol) {
   const int W = P.world;
@@ -662,13 +666,18 @@ __device__ __forceinline__ ColumnMerge merge_column_cells(const EngineParams& P,
 }
 __device__ __forceinline__ ColumnMerge exchange_column(const EngineParams& P, int c, int ncol, float U, float M, float S) {
   const uint32_t tag = P.xchg_seq;
+  const bool stamp = P.dbg_ts != nullptr && c == 0;  // BNV_DEBUG_TS: wall-clock (ns) stamps of column 0's exchange
+  if (stamp) P.dbg_ts[8] = static_cast<long long>(globaltimer_ns());
   for (int r = 0; r < P.world; ++r) {
     uint2* cell = const_cast<uint2*>(mailbox_cell(P, r, P.rank, c, ncol));
     st_ll(cell, U, tag);
     st_ll(cell + 1, M, tag);
     st_ll(cell + 2, S, tag);
   }
-  return merge_column_cells(P, c, ncol);
+  if (stamp) P.dbg_ts[9] = static_cast<long long>(globaltimer_ns());
+  const ColumnMerge out = merge_column_cells(P, c, ncol);
+  if (stamp) P.dbg_ts[11] = static_cast<long long>(globaltimer_ns());
+  return out;
 }
 
 // Results complete (u_out and opt_rec written by this CTA, ordered before this thread by the CTA barrier): publish
@@ -733,6 +742,8 @@ __global__ void __launch_bounds__((kWide ? kWideWarps : kMaxWarps) * 32, kWide ?
     rollout_kernel(const __grid_constant__ EngineParams P) {
   extern __shared__ __align__(128) unsigned char smem[];
   const long long t_start = clock64();
+  if (P.dbg_ts != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0)
+    P.dbg_ts[13] = static_cast<long long>(globaltimer_ns());  // BNV_DEBUG_TS: wall clock (ns) at the start of CTA 0
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int T = P.T;
   const int nwarps = blockDim.x >> 5;
@@ -843,10 +854,32 @@ __global__ void __launch_bounds__((kWide ? kWideWarps : kMaxWarps) * 32, kWide ?
     sy = __uint_as_float(box_s[1]);
     sth = __uint_as_float(box_s[2]);
   } else {
-    const float* state_e = P.state + 3 * env;
-    sx = P.state_inline ? P.state_val[0] : __ldg(state_e);
-    sy = P.state_inline ? P.state_val[1] : __ldg(state_e + 1);
-    sth = P.state_inline ? P.state_val[2] : __ldg(state_e + 2);
+    if (!kBatch && P.state_role == 2) {
+      // follower of a host-driven sharded solver: the leader's kernel stores the state into this rank's mailbox over
+      // NVLink (three LL words); thread 0 of every CTA polls the (local) cell
+      float* box_f = reinterpret_cast<float*>(smem + 96);
+      if (tid == 0) {
+        const uint2* cell = mailbox_state_cell(P, P.rank, 2 * T);
+        box_f[0] = wait_ll(cell, P.xchg_seq, P.err_flag);
+        box_f[1] = wait_ll(cell + 1, P.xchg_seq, P.err_flag);
+        box_f[2] = wait_ll(cell + 2, P.xchg_seq, P.err_flag);
+      }
+      __syncthreads();
+      sx = box_f[0];
+      sy = box_f[1];
+      sth = box_f[2];
+    } else {
+      const float* state_e = P.state + 3 * env;
+      sx = P.state_inline ? P.state_val[0] : __ldg(state_e);
+      sy = P.state_inline ? P.state_val[1] : __ldg(state_e + 1);
+      sth = P.state_inline ? P.state_val[2] : __ldg(state_e + 2);
+      if (!kBatch && P.state_role == 1 && blockIdx.x == 0 && tid < P.world && tid != P.rank) {
+        uint2* cell = const_cast<uint2*>(mailbox_state_cell(P, tid, 2 * T));  // leader: one thread per peer
+        st_ll(cell, sx, P.xchg_seq);
+        st_ll(cell + 1, sy, P.xchg_seq);
+        st_ll(cell + 2, sth, P.xchg_seq);
+      }
+    }
   }
   if (tid == 0) {
     mbar_init(bar_patch, 1);
@@ -1187,209 +1220,16 @@ __global__ void __launch_bounds__((kWide ? kWideWarps : kMaxWarps) * 32, kWide ?
   __syncthreads();
   float s_cta = 0.0f;
   for (int w = 0; w < nwarps; ++w) s_cta += red_s[8 + w];
-  // Distributed schedule (P.coop == 2): the partial leaves as self-validating {value, launch epoch} words, so the
-  // CTAs that consume it need neither a fence nor a grid barrier -- seeing the epoch IS the synchronisation.
-  uint2* const pll_u_e = P.part_ll_u + (eB + blockIdx.x) * 2 * T;   // this CTA's [2T] column sums
-  uint2* const pll_ms_e = P.part_ll_ms + (eB + blockIdx.x) * 2;     // this CTA's (max score, sum exp)
   for (int c = tid; c < 2 * T; c += blockDim.x) {
     float acc = 0.0f;
     for (int w = 0; w < nwarps; ++w) acc += warpu_s[w * 2 * T + c];
-    if (P.coop == 2) st_ll(pll_u_e + c, acc, epoch);
-    else part_u_e[static_cast<size_t>(blockIdx.x) * 2 * T + c] = acc;
+    part_u_e[static_cast<size_t>(blockIdx.x) * 2 * T + c] = acc;
   }
   if (tid == 0) {
-    if (P.coop == 2) {
-      st_ll(pll_ms_e, m_cta, epoch);
-      st_ll(pll_ms_e + 1, s_cta, epoch);
-    } else {
-      part_ms_e[2 * blockIdx.x + 0] = m_cta;
-      part_ms_e[2 * blockIdx.x + 1] = s_cta;
-    }
+    part_ms_e[2 * blockIdx.x + 0] = m_cta;
+    part_ms_e[2 * blockIdx.x + 1] = s_cta;
   }
   const long long t_part = clock64();
-  // ---- Epilogue, distributed schedule (P.coop == 2; the whole grid is co-resident: cooperative launch).
-  // EVERY CTA merges for itself: one warp collects all (m_g, s_g) words -- 2 KB -- and the CTA's own column(s) of the
-  // U_g words -- 1 KB per column -- polling until each carries this launch's epoch, which gives the CTA (M, S) for its
-  // weights and u*[c] for its columns.  The columns travel, again as LL words, to CTA 0 of the environment, which runs
-  // the serial optimal rollout.  After the last CTA's partial is computed the critical path is: its LL stores reach
-  // L2, the column owners' next poll sees them, a warp reduction, one more LL hop -- no fence, no atomic, no barrier
-  // (the round-1 schedule: fence + atomic ticket, 52 KB of partials into ONE SM, four CTA barriers, a release that
-  // the other CTAs wait for).  Fixed lanes and fixed-order sums: bit-reproducible, every CTA computes bit-identical
-  // (M, S).  With peers attached (sharded solver) the column owners also do the exchange over NVLink.
-  if (P.coop == 2) {
-    const int nblk = gridDim.x, ncol = 2 * T;
-    const bool fused = !kBatch && P.world > 1 && P.peer_mbox != nullptr;
-    const bool complete = P.world == 1 || fused;  // (M, S, U) cover every sample of the solver
-    const bool is_final = blockIdx.x == 0;        // runs the optimal rollout of this environment
-    const bool stamp = P.dbg_ts != nullptr && env == 0 && is_final;
-    const uint32_t tag = epoch;
-    const uint2* const all_ms = P.part_ll_ms + eB * 2;
-    const uint2* const all_u = P.part_ll_u + eB * ncol;
-    uint2* ull_e = P.ustar_ll + static_cast<size_t>(env) * ncol;
-    if (stamp && tid == 0) {
-      P.dbg_ts[0] = t_start; P.dbg_ts[1] = t_loop0; P.dbg_ts[2] = t_loop1; P.dbg_ts[3] = t_part;
-    }
-    if (warp == 0) {
-      constexpr int kKeep = 8;  // (m_g, s_g) and one column of up to 256 CTAs stay in registers
-      float2 msr[kKeep];
-      float ucol[kKeep];
-      const int c_first = blockIdx.x;
-      // poll until every word carries the epoch: lanes over CTAs g = lane, lane + 32, ...
-      unsigned pend = 0u;
-#pragma unroll
-      for (int j = 0; j < kKeep; ++j) {
-        msr[j] = make_float2(-FLT_MAX, 0.0f);
-        ucol[j] = 0.0f;
-        if (lane + 32 * j < nblk) pend |= (c_first < ncol ? 3u : 1u) << (2 * j);  // bit 2j: (m, s); bit 2j + 1: column word
-      }
-      const unsigned long long t0 = globaltimer_ns();
-      for (unsigned int spins = 1; __any_sync(0xffffffffu, pend != 0u); ++spins) {
-        // one round: every outstanding word is requested before the first is examined (a round costs one L2 round
-        // trip, not one per word)
-        uint4 wm[kKeep];
-        uint2 wu[kKeep];
-#pragma unroll
-        for (int j = 0; j < kKeep; ++j) {
-          const int g = lane + 32 * j;
-          wm[j] = make_uint4(0u, 0u, 0u, 0u);
-          wu[j] = make_uint2(0u, 0u);
-          if (pend & (1u << (2 * j)))  // {m, tag, s, tag}: two LL words, each validated on its own
-            asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
-                         : "=r"(wm[j].x), "=r"(wm[j].y), "=r"(wm[j].z), "=r"(wm[j].w) : "l"(all_ms + 2 * g) : "memory");
-          if (pend & (2u << (2 * j))) wu[j] = ld_ll(all_u + static_cast<size_t>(g) * ncol + c_first);
-        }
-#pragma unroll
-        for (int j = 0; j < kKeep; ++j) {
-          if ((pend & (1u << (2 * j))) && wm[j].y == tag && wm[j].w == tag) {
-            msr[j] = make_float2(__uint_as_float(wm[j].x), __uint_as_float(wm[j].z));
-            pend &= ~(1u << (2 * j));
-          }
-          if ((pend & (2u << (2 * j))) && wu[j].y == tag) {
-            ucol[j] = __uint_as_float(wu[j].x);
-            pend &= ~(2u << (2 * j));
-          }
-        }
-        if ((spins & 1023u) == 0u && globaltimer_ns() - t0 > kSpinLimitNs) {
-          if (P.err_flag != nullptr) atomicExch(P.err_flag, 1u);
-          pend = 0u;
-        }
-      }
-      if (stamp && lane == 0) P.dbg_ts[4] = clock64();
-      float lm = -FLT_MAX;
-#pragma unroll
-      for (int j = 0; j < kKeep; ++j) lm = fmaxf(lm, msr[j].x);
-      for (int g = lane + 32 * kKeep; g < nblk; g += 32) {  // (grids beyond 256 CTAs: short horizons, several CTAs per SM)
-        lm = fmaxf(lm, wait_ll(all_ms + 2 * g, tag, P.err_flag));
-      }
-      const float Ml = warp_max(lm);
-      float ls = 0.0f;
-#pragma unroll
-      for (int j = 0; j < kKeep; ++j) {
-        msr[j].x = __expf(msr[j].x - Ml);  // a_g (0 for the padding entries: exp(-FLT_MAX - Ml) = 0)
-        ls = fmaf(msr[j].x, msr[j].y, ls);
-      }
-      for (int g = lane + 32 * kKeep; g < nblk; g += 32)
-        ls = fmaf(__expf(wait_ll(all_ms + 2 * g, tag, P.err_flag) - Ml), wait_ll(all_ms + 2 * g + 1, tag, P.err_flag), ls);
-      const float Sl = warp_sum(ls);
-      float Mg = Ml, Sg = Sl;  // after the exchange: over all shards
-      if (stamp && lane == 0) P.dbg_ts[12] = clock64();
-      for (int c = c_first; c < ncol; c += nblk) {
-        float acc = 0.0f;
-#pragma unroll
-        for (int j = 0; j < kKeep; ++j) {
-          const int g = lane + 32 * j;
-          float uv = ucol[j];
-          if (c != c_first) uv = (g < nblk) ? wait_ll(all_u + static_cast<size_t>(g) * ncol + c, tag, P.err_flag) : 0.0f;
-          acc = fmaf(msr[j].x, uv, acc);
-        }
-        for (int g = lane + 32 * kKeep; g < nblk; g += 32)
-          acc = fmaf(__expf(wait_ll(all_ms + 2 * g, tag, P.err_flag) - Ml),
-                     wait_ll(all_u + static_cast<size_t>(g) * ncol + c, tag, P.err_flag), acc);
-        float Uc = warp_sum(acc);
-        if (fused) {
-          ColumnMerge cm{0.0f, 0.0f, 0.0f};
-          if (lane == 0) cm = exchange_column(P, c, ncol, Uc, Ml, Sl);
-          Uc = __shfl_sync(0xffffffffu, cm.U, 0);
-          Mg = __shfl_sync(0xffffffffu, cm.M, 0);
-          Sg = __shfl_sync(0xffffffffu, cm.S, 0);
-        }
-        if (lane == 0) {
-          if (complete) st_ll(ull_e + c, __fdiv_rn(Uc, Sg), tag);  // u*[c] = U[c] / S (mppi.py:196-199)
-          else P.shard_partial[2 + c] = Uc;  // unfused sharding: the host-side exchange + finalize_kernel take over
-        }
-      }
-      if (fused && c_first >= ncol) {  // a CTA without a column still needs the merged (M, S): column 0's cells carry them
-        ColumnMerge cm{0.0f, 0.0f, 0.0f};
-        if (lane == 0) cm = merge_column_cells(P, 0, ncol);
-        Mg = __shfl_sync(0xffffffffu, cm.M, 0);
-        Sg = __shfl_sync(0xffffffffu, cm.S, 0);
-      }
-      if (lane == 0) {
-        red_s[32] = Mg;
-        red_s[33] = complete ? Sg : 1.0f;  // 1/S is deferred to finalize_kernel when unfused-sharded
-        if (!complete && blockIdx.x == 0) {
-          P.shard_partial[0] = Ml;
-          P.shard_partial[1] = Sl;
-        }
-      }
-    }
-    __syncthreads();
-    {
-      // softmax weight of this thread's sample straight from registers (mppi.py:193)
-      const float Mw = red_s[32], Sw = red_s[33];
-      if (valid) weights_e[k] = e * __expf(m_cta - Mw) * __fdiv_rn(1.0f, Sw);
-    }
-    // the slab stores (17 MB over the grid) leave last: issued before the merge's traffic they were measured to stretch
-    // its L2 round trips from ~0.8k to ~3k cycles each
-    if (!kWide)
-      store_slabs<kRecord, kPhilox>(P, rec_e, noise_out_e, rec_s, nz_w, warp, lane, warp_first, warp_rows, nz_bytes);
-    if (is_final && complete && warp == 0) {
-      // collect u* from the column owners, publish it, run the batch-1 optimal rollout (mppi.py:202-214)
-      float* u_out_e = P.u_out + static_cast<size_t>(env) * ncol;
-      for (int c0 = 0; c0 < ncol; c0 += 128) {  // four words per lane requested per round
-        uint2 wv[4];
-        unsigned need = 0u;
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (c0 + 32 * i + lane < ncol) need |= 1u << i;
-        const unsigned long long t0 = globaltimer_ns();
-        for (unsigned int spins = 1; need != 0u; ++spins) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (need & (1u << i)) wv[i] = ld_ll(ull_e + c0 + 32 * i + lane);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if ((need & (1u << i)) && wv[i].y == tag) {
-              const int c = c0 + 32 * i + lane;
-              const float u = __uint_as_float(wv[i].x);
-              warpu_s[c] = clampf(u, (c & 1) ? C.u_min1 : C.u_min0, (c & 1) ? C.u_max1 : C.u_max0);
-              u_out_e[c] = u;
-              if (P.keep_mean) u_prev_e[c] = u;  // next call's mean sequence, unshifted (mppi.py:217)
-              need &= ~(1u << i);
-            }
-          }
-          if ((spins & 1023u) == 0u && globaltimer_ns() - t0 > kSpinLimitNs) {
-            if (P.err_flag != nullptr) atomicExch(P.err_flag, 1u);
-            need = 0u;
-          }
-        }
-      }
-      __syncwarp();
-      if (stamp) BNV_STAMP(6);
-      if (lane == 0) {
-        const XiSource xs{(kStoch && !kPhilox) ? P.xi_opt_in + static_cast<size_t>(env) * T : nullptr, kOptimalSample,
-                          iter_lo, iter_hi_e, key};
-        optimal_rollout<kPatch, kPow2, kFastAngles, kStoch>(T, C, warpu_s, sx, sy, sth,
-                                                            P.opt_rec + static_cast<size_t>(env) * 3 * (T + 1), xs);
-        signal_done(P);
-      }
-      if (stamp) BNV_STAMP(7);
-    }
-    if (!kWide && (kRecord || kPhilox)) bulk_wait_read_all();
-    if (stamp) BNV_STAMP_ANY(10, 32);
-    return;
-  }
-
   // Two epilogue schedules.  coop (the whole grid is co-resident; cooperative launch): the slab stores (17 MB over
   // the grid) are held back until the last CTA has merged the partials -- issued earlier, their burst through
   // L2 was measured to stretch the merge's loads from ~0.8k to ~3k cycles each -- and every CTA normalises its own

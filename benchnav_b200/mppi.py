@@ -164,10 +164,12 @@ class MPPI(nn.Module):
                           if self._shard.world_size > 1 else None)
         self._state_dev = torch.zeros(3, device=dev, dtype=torch.float32)
         self._forward_host_fn = self._lib.bnv_mppi_forward_host
-        self._slow_host_path = self._shard.world_size != 1 or noise_source != "philox"
         self._fused_exchange = False
         if self._shard.world_size > 1 and exchange == "p2p":
             self._fused_exchange = attach_peer_mailboxes(self._lib, self._handle, self._shard)
+        # the host-buffer call goes straight to the engine for an unsharded solver, and for a sharded one whose ranks
+        # exchange inside the kernel (then this rank leads and the others call forward_follow)
+        self._slow_host_path = noise_source != "philox" or (self._shard.world_size != 1 and not self._fused_exchange)
 
     # ------------------------------------------------------------------ plumbing
     def _draw_torch_noise(self) -> torch.Tensor:
@@ -328,6 +330,19 @@ class MPPI(nn.Module):
                                    self._stream())
         if rc != 0:
             _cabi.check(rc)
+        return u_opt, opt_states
+
+    def forward_follow(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        """The other ranks' half of a host-driven sharded iteration: while ONE rank (the leader) calls
+        ``forward_host(state)``, every other rank calls this once per leader call.  The kernel waits on the device for
+        the leader's state (broadcast over NVLink by the leader's kernel), rolls out this rank's shard and takes part
+        in the exchange.  Asynchronous; returns this rank's device copies of the (identical) results."""
+        u_opt = torch.empty(self._horizon, 2, device=self._device, dtype=torch.float32)
+        opt_states = torch.empty(1, self._horizon + 1, 3, device=self._device, dtype=torch.float32)
+        self._sync_problem()
+        with torch.cuda.device(self._device):
+            _cabi.check(self._lib.bnv_mppi_forward_follow(self._handle, None, u_opt.data_ptr(), opt_states.data_ptr(),
+                                                          self._stream()))
         return u_opt, opt_states
 
     def get_top_samples(self, num_samples: int) -> Tuple[torch.Tensor, torch.Tensor]:

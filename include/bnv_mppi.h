@@ -132,10 +132,15 @@ int bnv_mppi_forward_state(bnv_mppi* h, const float state_host[3], const float* 
  * caller reads on the host).  Host->device: the state rides in the launch packet.  Device->host: the kernel
  * stores u_out/opt_states into pinned, device-mapped staging (zero-copy over PCIe) and raises a completion word
  * there as soon as both are written; the call polls that word (falling back to a stream synchronisation if the
- * device faults or stalls) and copies the results to the caller's buffers.  world_size must be 1.
- * See bnv_mppi_prelaunch for the variant in which the kernel is already resident when the state arrives. */
+ * device faults or stalls) and copies the results to the caller's buffers.
+ * See bnv_mppi_prelaunch for the variant in which the kernel is already resident when the state arrives.
+ * Sharded solver (world_size > 1, peers attached): the control loop lives on ONE rank, the leader, which makes this
+ * call; its kernel broadcasts the state to the other ranks' mailboxes over NVLink.  Every other rank calls
+ * bnv_mppi_forward_follow once per leader call: its kernel waits on the device for the state, rolls out its shard
+ * and takes part in the exchange; the leader's host buffers receive the (identical on every rank) results. */
 int bnv_mppi_forward_host(bnv_mppi* h, const float state_host[3], const float* noise_dev, float* u_out_host,
                           float* opt_states_host, void* stream);
+int bnv_mppi_forward_follow(bnv_mppi* h, const float* noise_dev, float* u_out_dev, float* opt_states_dev, void* stream);
 
 /* Sample-sharded softmax (replaces the global torch.softmax of mppi.py:193-199).
  * bnv_mppi_partial: device pointer to this shard's (m, s, U[T,2]) -- m = max_k(-c_k/lambda),

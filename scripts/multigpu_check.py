@@ -24,12 +24,14 @@ def main() -> None:
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     G, T = 512, 50
-    K = 16384 * world + 37  # ragged shard sizes
     risk, start, goal, thr = benchmark_problem(G, 0.5, seed=0)
     dyn = UnicycleProblem(GridSpec(G, 0.5), risk)
     obj = GoalObjectives(dyn, goal, thr)
     sig = torch.tensor([0.5, 0.5])
-    for exchange in ("p2p", "nccl"):
+    # ragged shard sizes; the second size puts every shard on the wide variant of the rollout kernel (several waves),
+    # whose last CTA does the exchange, the first on the co-resident one, whose column owners do it
+    for exchange, K in (("p2p", 16384 * world + 37), ("nccl", 16384 * world + 37), ("p2p", 49152 * world + 5),
+                        ("nccl", 49152 * world + 5)):
         sharded = MPPI(T, K, 3, 2, dyn, obj, sig, 0.5, device=dev, seed=7, process_group=dist.group.WORLD,
                        exchange=exchange)
         if exchange == "p2p":
@@ -63,6 +65,23 @@ def main() -> None:
             if rank == 0:
                 print(f"{exchange} it{it}: |du*|={du:.2e} |dopt|={do:.2e} |dw|max={dw:.2e} sum(w)={float(wsum):.7f} "
                       f"shard {a}+{n} of {K}", flush=True)
+        if exchange == "p2p":
+            # host-driven iteration: rank 0 leads with forward_host(state), the others follow; every rank's result
+            # equals the unsharded solver's
+            sharded._previous_action_seq.copy_(single._previous_action_seq)
+            if rank == 0:
+                u_h, o_h = sharded.forward_host(start)
+                u_h, o_h = u_h.to(dev), o_h.to(dev)
+            else:
+                u_h, o_h = sharded.forward_follow()
+            u_1, o_1 = single.forward(st)
+            torch.cuda.synchronize()
+            assert float((u_h - u_1).abs().max()) <= 5e-6 and float((o_h - o_1).abs().max()) <= 5e-5
+            if rank == 0:
+                print(f"{exchange} K={K}: host-driven iteration ok |du*|={float((u_h - u_1).abs().max()):.2e}", flush=True)
+        sharded.check()  # no in-kernel wait timed out
+        if rank == 0:
+            print(f"{exchange} K={K}: launch {sharded.launch_geometry}", flush=True)
         del sharded, single
     dist.barrier()
     if rank == 0:

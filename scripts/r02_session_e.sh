@@ -1,0 +1,9 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -5 | tee gpurun_out/pytest_gpu.txt
+BNV_DEBUG_DISABLE=4096 timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -5 | tee gpurun_out/pytest_gpu_forced_wide.txt
+python scripts/phase_stamps.py 2>&1 | tail -2 | tee gpurun_out/phase_stamps.txt
+for c in ${CONFIGS:-c1 c3 c4}; do
+  timeout 600 python bench.py --config $c --steps ${STEPS:-1000} --warmup 20 > gpurun_out/bench_$c.json 2> gpurun_out/bench_$c.err
+  tail -2 gpurun_out/bench_$c.err; python scripts/bench_summary.py < gpurun_out/bench_$c.json
+done
