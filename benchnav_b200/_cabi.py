@@ -96,6 +96,10 @@ _SIGNATURES = {
     "bnv_mppi_draw_noise": (C.c_int, [_VP, C.c_uint64, _VP]),
     "bnv_mppi_draw_xi": (C.c_int, [_VP, C.c_uint64, _VP, _VP, _VP]),
     "bnv_mppi_device_counter": (C.c_int, [_VP, C.c_int32, _VP]),
+    "bnv_mppi_iteration_counter": (_VP, [_VP]),
+    "bnv_closed_loop_step": (C.c_int, [C.POINTER(Grid), _VP, _VP, C.c_int64, C.c_int32, C.c_int32, _VP, _VP, _VP, _VP,
+                                       C.c_uint64, _VP, _FP, _FP, C.c_float, C.c_float, C.c_float, _VP, _VP, _VP, _VP,
+                                       _VP, _VP, _VP, _VP, _VP]),
     "bnv_mppi_prelaunch": (C.c_int, [_VP, C.c_int32, C.c_uint32]),
     "bnv_mppi_set_keep_mean": (C.c_int, [_VP, C.c_int32]),
     "bnv_mppi_set_terminal_goal": (C.c_int, [_VP, _FP]),

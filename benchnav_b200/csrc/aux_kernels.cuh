@@ -113,6 +113,74 @@ __global__ void __launch_bounds__(128) env_step_kernel(GridGeom geom, int G, con
   terminated[e] = (d < goal_threshold) ? 1 : 0;
 }
 
+// ------------------------------------------------------------------------------------------------ closed-loop step
+// Everything Tutorial 3.3's loop does between two planner calls (test/test_mppi.py:180-185), for E environments in ONE
+// launch: apply the first planned action to the environment (PlanetaryEnv.step, planetary_env.py:189-219; robots that
+// have arrived stop), test the planned trajectory for collisions (PlanetaryEnv.collision_check, :221-232), and keep
+// the loop's books (step counter, first step at which each robot reached its goal, draw counters) -- so that a
+// control step is two kernels (rollout + this one) instead of the ~15 small launches the same sequence costs through
+// separate calls.  blockIdx.x = environment; thread 0 advances the robot, threads 0..T test the planned states.
+// Draws: exactly those of env_step_kernel (counter c) and trav_lookup_kernel (counter 2^40 + c + 1) called one after
+// the other, so the fused loop reproduces the unfused one bit for bit; the last block to finish advances *ctr_dev by 2,
+// *step_no by 1 and, when given, the planner's iteration counter by 1 (the rollout kernel then needs no bump kernel).
+__global__ void __launch_bounds__(128) closed_loop_step_kernel(
+    GridGeom geom, int G, const float* __restrict__ mean, const float* __restrict__ stdv, int pitch, long long env_stride,
+    int E, int T, float* __restrict__ states, const float* __restrict__ actions /*[E][T][2]*/,
+    const float* __restrict__ planned /*[E][T+1][3]*/, const float* __restrict__ goals, uint32_t seed_lo,
+    uint32_t seed_hi, unsigned long long* __restrict__ ctr_dev, Bounds b, float goal_threshold, float stuck_threshold,
+    float* __restrict__ reward, unsigned char* __restrict__ terminated, unsigned char* __restrict__ collisions,
+    unsigned char* __restrict__ done, long long* __restrict__ steps_to_goal, long long* __restrict__ step_no,
+    unsigned long long* __restrict__ planner_iter, unsigned int* __restrict__ ticket) {
+  const int e = blockIdx.x, tid = threadIdx.x;
+  const unsigned long long ctr = *ctr_dev;
+  const uint2 key = make_uint2(seed_lo, seed_hi);
+  // planned trajectory against the environment's true slip model (counter 2^40 + c + 1, index e (T+1) + t)
+  for (int t = tid; t <= T; t += blockDim.x) {
+    const long long i = static_cast<long long>(e) * (T + 1) + t;
+    const float* p = planned + i * 3;
+    const size_t cell = static_cast<size_t>(cell_of(geom, G, pitch, p[0], p[1])) + static_cast<size_t>(e) * env_stride;
+    const unsigned long long cc = (1ull << 40) + ctr + 1ull;
+    const float z = aux_normal(static_cast<uint32_t>(i), kStreamLookup + static_cast<uint32_t>(i >> 32) * 2u,
+                               static_cast<uint32_t>(cc), static_cast<uint32_t>(cc >> 32), key);
+    collisions[i] = (slip_to_trav(make_float2(mean[cell], stdv[cell]), z) <= stuck_threshold) ? 1 : 0;
+  }
+  if (tid == 0) {
+    const bool was_done = done[e] != 0;
+    float x = states[3 * e], y = states[3 * e + 1], th = states[3 * e + 2];
+    const size_t cell = static_cast<size_t>(cell_of(geom, G, pitch, x, y)) + static_cast<size_t>(e) * env_stride;
+    const float z = aux_normal(static_cast<uint32_t>(e), kStreamEnvStep, static_cast<uint32_t>(ctr),
+                               static_cast<uint32_t>(ctr >> 32), key);
+    const float tau = slip_to_trav(make_float2(mean[cell], stdv[cell]), z);
+    const float a0 = was_done ? 0.0f : actions[static_cast<size_t>(e) * T * 2];
+    const float a1 = was_done ? 0.0f : actions[static_cast<size_t>(e) * T * 2 + 1];
+    const float v0 = clampf(a0, b.u_min0, b.u_max0), v1 = clampf(a1, b.u_min1, b.u_max1);
+    StepConsts c{};
+    c.x_min = geom.x_min; c.y_min = geom.y_min; c.x_max = geom.x_max; c.y_max = geom.y_max; c.dt = b.dt;
+    float xr, yr, thr;
+    unicycle_step<false>(c, tau, v0, v1, x, y, th, xr, yr, thr);
+    states[3 * e] = x;
+    states[3 * e + 1] = y;
+    states[3 * e + 2] = th;
+    reward[e] = tau;
+    const float dx = __fsub_rn(x, goals[2 * e]), dy = __fsub_rn(y, goals[2 * e + 1]);
+    const bool term = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy))) < goal_threshold;
+    terminated[e] = term ? 1 : 0;
+    if (term && !was_done) steps_to_goal[e] = *step_no + 1;
+    if (term) done[e] = 1;
+  }
+  // the counters advance once every block has read them: last block out (release/acquire through the ticket)
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
+      *ticket = 0u;
+      *ctr_dev = ctr + 2ull;
+      *step_no += 1;
+      if (planner_iter != nullptr) *planner_iter += 1ull;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ risk map
 // Closed form for a Normal(mean, std) slip distribution: risk = mean + coef * std with
 //   expected value: coef = 0;  VaR_q: coef = Phi^-1(q);  CVaR_q: coef = phi(Phi^-1(q)) / (1 - q)

@@ -116,6 +116,32 @@ int bnv_env_step(const bnv_grid* grid, const float* mean_dev, const float* std_d
   return BNV_OK;
 }
 
+int bnv_closed_loop_step(const bnv_grid* grid, const float* mean_dev, const float* std_dev, int64_t env_stride,
+                         int32_t num_envs, int32_t horizon, float* states_dev, const float* actions_dev,
+                         const float* planned_dev, const float* goals_dev, uint64_t seed, uint64_t* counter_dev,
+                         const float u_min[2], const float u_max[2], float delta_t, float goal_threshold,
+                         float stuck_threshold, float* reward_out_dev, uint8_t* terminated_out_dev,
+                         uint8_t* collisions_out_dev, uint8_t* done_dev, int64_t* steps_to_goal_dev, int64_t* step_no_dev,
+                         uint64_t* planner_iteration_dev, uint32_t* ticket_dev, void* stream) {
+  bnv::GridGeom geom;
+  int rc = make_geom(grid, &geom);
+  if (rc != BNV_OK) return rc;
+  if (!mean_dev || !std_dev || !states_dev || !actions_dev || !planned_dev || !goals_dev || !counter_dev || !u_min ||
+      !u_max || !reward_out_dev || !terminated_out_dev || !collisions_out_dev || !done_dev || !steps_to_goal_dev ||
+      !step_no_dev || !ticket_dev)
+    return bnv_fail(BNV_ERR_INVALID, "null argument");
+  if (num_envs < 1 || horizon < 1 || env_stride < 0 || !(delta_t > 0.0f)) return bnv_fail(BNV_ERR_INVALID, "bad size argument");
+  bnv::Bounds b{u_min[0], u_min[1], u_max[0], u_max[1], delta_t};
+  bnv::closed_loop_step_kernel<<<num_envs, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      geom, grid->grid_size, mean_dev, std_dev, grid->pitch, env_stride, num_envs, horizon, states_dev, actions_dev,
+      planned_dev, goals_dev, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32),
+      reinterpret_cast<unsigned long long*>(counter_dev), b, goal_threshold, stuck_threshold, reward_out_dev,
+      terminated_out_dev, collisions_out_dev, done_dev, reinterpret_cast<long long*>(steps_to_goal_dev),
+      reinterpret_cast<long long*>(step_no_dev), reinterpret_cast<unsigned long long*>(planner_iteration_dev), ticket_dev);
+  BNV_CUDA(cudaGetLastError());
+  return BNV_OK;
+}
+
 int bnv_risk_map(int32_t metric, float confidence, int32_t method, const float* mean_dev, const float* std_dev,
                  int64_t n_cells, const float* samples_dev, int32_t num_samples, uint64_t seed, float* risk_out_dev,
                  float* samples_out_dev, void* stream) {

@@ -118,6 +118,7 @@ struct bnv_mppi {
   float* io_host = nullptr;  // pinned mirror of io_dev
   float* io_host_dev = nullptr;  // its device-side address (zero-copy)
   unsigned long long* iter_dev = nullptr;  // device-resident iteration counter (graph-capturable launches)
+  bool iter_external = false;              // ... advanced by the caller (bnv_closed_loop_step), no bump kernel
   // pre-launched iterations of forward_host (bnv_mppi_prelaunch)
   bool pre_enabled = false, pre_pending = false;
   cudaStream_t pre_stream = nullptr;        // internal stream of the pre-launched kernels
@@ -658,10 +659,12 @@ static int launch_forward(bnv_mppi* h, const float* state_dev, const float* stat
     h->ev_used += 2;
   }
   if (!coop) h->launches++;
-  if (h->iter_dev) {  // the counter advances on the device, in stream order (and on every replay of a captured graph)
-    bnv::bump_iteration_kernel<<<1, 1, 0, s>>>(h->iter_dev);
-    BNV_CUDA(cudaGetLastError());
-    h->launches++;
+  if (h->iter_dev && h->P.iter_dev) {  // the counter advances on the device, in stream order (and on every graph replay)
+    if (!h->iter_external) {
+      bnv::bump_iteration_kernel<<<1, 1, 0, s>>>(h->iter_dev);
+      BNV_CUDA(cudaGetLastError());
+      h->launches++;
+    }
   } else if (philox) {
     h->iteration++;
   }
@@ -890,7 +893,7 @@ int bnv_mppi_forward_host(bnv_mppi* h, const float state_host[3], const float* n
   if (h->stoch && noise_dev) return fail(BNV_ERR_INVALID, "stochastic-slip solver: inject noise through bnv_mppi_forward_ex");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   BNV_CUDA(cudaSetDevice(h->cfg.device));
-  if (h->pre_enabled && !noise_dev && !h->iter_dev)
+  if (h->pre_enabled && !noise_dev && !h->P.iter_dev)
     return forward_host_prelaunched(h, state_host, u_out_host, opt_states_host, 0);
   BNV_DRAIN(h);
   const int T = h->P.T;
@@ -1086,6 +1089,7 @@ int bnv_mppi_device_counter(bnv_mppi* h, int32_t enable, void* stream) {
     BNV_CUDA(cudaMemsetAsync(h->ticket, 0, 2 * static_cast<size_t>(h->E) * sizeof(unsigned int), s));
     BNV_CUDA(cudaStreamSynchronize(s));
     h->P.iter_dev = h->iter_dev;
+    h->iter_external = enable == 2;
   } else if (h->iter_dev && h->P.iter_dev) {
     BNV_CUDA(cudaMemsetAsync(h->ticket, 0, 2 * static_cast<size_t>(h->E) * sizeof(unsigned int), s));
     unsigned long long it = 0;
@@ -1095,6 +1099,10 @@ int bnv_mppi_device_counter(bnv_mppi* h, int32_t enable, void* stream) {
     h->P.iter_dev = nullptr;
   }
   return BNV_OK;
+}
+
+uint64_t* bnv_mppi_iteration_counter(bnv_mppi* h) {
+  return (h && h->P.iter_dev) ? reinterpret_cast<uint64_t*>(h->iter_dev) : nullptr;
 }
 
 int bnv_mppi_set_keep_mean(bnv_mppi* h, int32_t keep) {

@@ -178,6 +178,42 @@ class BatchedPlanetaryEnv:
         self._advance_counter()
         return stuck.bool()
 
+    def closed_loop_step(self, actions: torch.Tensor, planned: torch.Tensor, done: torch.Tensor,
+                         steps_to_goal: torch.Tensor, step_no: torch.Tensor, collisions: torch.Tensor,
+                         planner=None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """Everything Tutorial 3.3's loop does between two planner calls, in ONE launch (``bnv_closed_loop_step``):
+        ``step`` with the first planned action (robots with ``done[e]`` set stop), ``collision_check`` of the planned
+        trajectory into ``collisions`` [E,T+1] (uint8), and the loop's books -- ``done`` (uint8 [E], in place),
+        ``steps_to_goal`` (int64 [E]), ``step_no`` (int64 scalar, +1) and this environment's draw counter (+2).
+
+        ``actions`` [E,T,2] and ``planned`` [E,1,T+1,3] (or [E,T+1,3]) are the planner's outputs, untouched.  With
+        ``planner`` (a ``BatchedMPPI`` in ``graph_capturable(True, external_advance=True)`` mode) its iteration counter
+        is advanced too, so a captured control step is two kernels.  Needs ``graph_capturable=True`` at construction
+        (device-resident draw counter).  Bit-identical to ``step`` + ``collision_check`` + the torch bookkeeping."""
+        if self._counter_dev is None:
+            raise RuntimeError("closed_loop_step needs BatchedPlanetaryEnv(..., graph_capturable=True)")
+        E = self._num_envs
+        T = int(actions.shape[1])
+        assert tuple(actions.shape) == (E, T, 2) and planned.numel() == E * (T + 1) * 3
+        for t, dt_ in ((actions, torch.float32), (planned, torch.float32), (done, torch.uint8), (collisions, torch.uint8),
+                       (steps_to_goal, torch.int64), (step_no, torch.int64)):
+            if not (t.is_cuda and t.dtype == dt_ and t.is_contiguous()):
+                raise ValueError("closed_loop_step takes contiguous CUDA tensors of the documented dtypes")
+        if getattr(self, "_loop_ticket", None) is None:
+            self._loop_ticket = torch.zeros(1, dtype=torch.int32, device=self._device)
+        it_ptr = planner.iteration_counter_ptr if planner is not None else 0
+        with torch.cuda.device(self._device):
+            _cabi.check(self._lib.bnv_closed_loop_step(
+                C.byref(self._grid), self._mean.data_ptr(), self._std.data_ptr(), self._mean.stride(0), E, T,
+                self._robot_state.data_ptr(), actions.data_ptr(), planned.data_ptr(), self._goal_pos.data_ptr(),
+                self._seed, self._counter_dev.data_ptr(), self._u_min, self._u_max, self._delta_t, self._goal_threshold,
+                float(self.stuck_threshold), self._reward.data_ptr(), self._terminated.data_ptr(), collisions.data_ptr(),
+                done.data_ptr(), steps_to_goal.data_ptr(), step_no.data_ptr(), it_ptr or None,
+                self._loop_ticket.data_ptr(), torch.cuda.current_stream(self._device).cuda_stream))
+        self._counter += 2
+        self._elapsed_time += self._delta_t
+        return self._robot_state, self._reward, self._terminated
+
     def _advance_counter(self) -> None:
         self._counter += 1
         if self._counter_dev is not None:

@@ -380,11 +380,19 @@ class MPPI(nn.Module):
         with torch.cuda.device(self._device):
             _cabi.check(self._lib.bnv_mppi_prelaunch(self._handle, 1 if enable else 0, int(timeout_us)))
 
-    def graph_capturable(self, enable: bool = True) -> None:
+    def graph_capturable(self, enable: bool = True, external_advance: bool = False) -> None:
         """Keep the iteration counter (Philox counter word, launch epoch) in device memory so that ``forward`` can be
-        captured in a CUDA graph (``torch.cuda.graph``) and replayed: one graph launch per control step."""
+        captured in a CUDA graph (``torch.cuda.graph``) and replayed: one graph launch per control step.
+        ``external_advance``: the counter is advanced by the caller's own kernel (``BatchedPlanetaryEnv.closed_loop_step``
+        does it) instead of a one-thread kernel behind every ``forward``."""
         with torch.cuda.device(self._device):
-            _cabi.check(self._lib.bnv_mppi_device_counter(self._handle, 1 if enable else 0, self._stream()))
+            mode = (2 if external_advance else 1) if enable else 0
+            _cabi.check(self._lib.bnv_mppi_device_counter(self._handle, mode, self._stream()))
+
+    @property
+    def iteration_counter_ptr(self) -> int:
+        """Device address of the iteration counter in graph-capturable mode (0 otherwise)."""
+        return int(self._lib.bnv_mppi_iteration_counter(self._handle) or 0)
 
     @property
     def launch_count(self) -> int:

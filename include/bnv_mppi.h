@@ -203,6 +203,9 @@ int bnv_mppi_draw_xi(bnv_mppi* h, uint64_t iteration, float* xi_out_dev, float* 
  * control step, with the same noise stream as uncaptured calls.  enable = 0 returns to by-value counters, keeping
  * the count.  Synchronises `stream`; world_size must be 1; bnv_mppi_forward_host is not capturable. */
 int bnv_mppi_device_counter(bnv_mppi* h, int32_t enable, void* stream);
+/* enable = 2: as 1, but the counter is advanced by the CALLER (bnv_closed_loop_step does it), not by a bump kernel
+ * behind every forward.  bnv_mppi_iteration_counter: the device address of the counter (NULL unless enabled). */
+uint64_t* bnv_mppi_iteration_counter(bnv_mppi* h);
 
 /* Pre-launched iterations for the host-buffer call.  With enable != 0, bnv_mppi_forward_host queues the NEXT
  * iteration's kernel (on an internal stream) before it waits for the current one; that kernel becomes resident as soon
@@ -310,6 +313,22 @@ int bnv_env_step(const bnv_grid* grid, const float* mean_dev, const float* std_d
                  const float* xi_dev, uint64_t seed, uint64_t counter, const uint64_t* counter_dev, const float u_min[2],
                  const float u_max[2], float delta_t, float goal_threshold, float* reward_out_dev,
                  uint8_t* terminated_out_dev, void* stream);
+
+/* Everything Tutorial 3.3's loop does between two planner calls (test/test_mppi.py:180-185), for E environments in ONE
+ * launch: PlanetaryEnv.step with the first planned action actions_dev[e][0] (robots whose done_dev[e] is set stop),
+ * PlanetaryEnv.collision_check of the planned trajectory planned_dev [E,T+1,3] -> collisions_out_dev [E,T+1] (uint8),
+ * and the loop's books: done_dev[e] |= terminated, steps_to_goal_dev[e] = step number of the first arrival,
+ * *step_no_dev += 1, *counter_dev += 2 (the draws are those of bnv_env_step at counter c followed by
+ * bnv_trav_lookup at counter 2^40 + c + 1: bit-identical to the separate calls), and, when planner_iteration_dev is
+ * given (bnv_mppi_iteration_counter of a solver in externally-advanced mode), *planner_iteration_dev += 1.
+ * ticket_dev: one zero-initialised uint32 owned by the caller.  With this a graph-captured control step is two kernels. */
+int bnv_closed_loop_step(const bnv_grid* grid, const float* mean_dev, const float* std_dev, int64_t env_stride,
+                         int32_t num_envs, int32_t horizon, float* states_dev, const float* actions_dev,
+                         const float* planned_dev, const float* goals_dev, uint64_t seed, uint64_t* counter_dev,
+                         const float u_min[2], const float u_max[2], float delta_t, float goal_threshold,
+                         float stuck_threshold, float* reward_out_dev, uint8_t* terminated_out_dev,
+                         uint8_t* collisions_out_dev, uint8_t* done_dev, int64_t* steps_to_goal_dev, int64_t* step_no_dev,
+                         uint64_t* planner_iteration_dev, uint32_t* ticket_dev, void* stream);
 
 /* TraversabilityModel._infer_risk_map (traversability_model.py:28-51) over n_cells cells.
  *   metric      0 expected value, 1 VaR, 2 CVaR (utils.py:18); confidence = ModelConfig.confidence_value

@@ -400,10 +400,19 @@ def test_closed_loop_example_reaches_the_goals():
     spec = importlib.util.spec_from_file_location("closed_loop_example", path)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
+    runs = {}
     for use_graph in (True, False):  # one CUDA-graph launch per control step, or host-issued launches
-        steps, dist, _ = mod.run(envs=8, samples=2048, horizon=30, max_steps=900, verbose=False, use_graph=use_graph)
-        assert int((steps > 0).sum()) >= 7, (use_graph, steps.tolist(), dist.tolist())  # one straggler tolerated
-        assert float(dist.min()) < 1.0
+        for fused in (True, False):  # environment step + collision check + the loop's books as ONE kernel, or separately
+            steps, dist, _ = mod.run(envs=8, samples=2048, horizon=30, max_steps=900, verbose=False, use_graph=use_graph,
+                                     fused=fused)
+            assert int((steps > 0).sum()) >= 7, (use_graph, fused, steps.tolist(), dist.tolist())  # one straggler tolerated
+            assert float(dist.min()) < 1.0
+            runs[(use_graph, fused)] = (steps, dist)
+    # the fused kernel makes the same draws as the separate calls: identical closed loops, captured or not
+    ref_steps, ref_dist = runs[(False, False)]
+    for key, (steps, dist) in runs.items():
+        assert torch.equal(steps, ref_steps), (key, steps.tolist(), ref_steps.tolist())
+        assert torch.equal(dist, ref_dist), key
 
 
 # ------------------------------------------------------------------------------------------------ CUDA graphs
