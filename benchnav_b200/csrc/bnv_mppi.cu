@@ -468,8 +468,8 @@ int bnv_mppi_create(bnv_mppi** out, const bnv_mppi_cfg* cfg) {
   cudaDeviceGetAttribute(&coop_attr, cudaDevAttrCooperativeLaunch, cfg->device);
   h->coop_ok = coop_attr != 0 && !(debug_disable() & 64u);
   if (std::getenv("BNV_DEBUG_TS")) {
-    if (cudaMalloc(reinterpret_cast<void**>(&h->dbg_ts), 16 * sizeof(long long)) == cudaSuccess)
-      cudaMemset(h->dbg_ts, 0, 16 * sizeof(long long));
+    if (cudaMalloc(reinterpret_cast<void**>(&h->dbg_ts), 24 * sizeof(long long)) == cudaSuccess)
+      cudaMemset(h->dbg_ts, 0, 24 * sizeof(long long));
   }
   P.dbg_ts = h->dbg_ts;
   *out = h;
@@ -1220,10 +1220,10 @@ int bnv_mppi_kernel_time(bnv_mppi* h, double* total_ms, uint64_t* launches) {
   return BNV_OK;
 }
 
-int bnv_debug_timestamps(bnv_mppi* h, long long out[16]) {
+int bnv_debug_timestamps(bnv_mppi* h, long long out[24]) {
   if (!h || !out) return fail(BNV_ERR_INVALID, "null argument");
   if (!h->dbg_ts) return fail(BNV_ERR_STATE, "set BNV_DEBUG_TS=1 before creating the handle");
-  BNV_CUDA(cudaMemcpy(out, h->dbg_ts, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+  BNV_CUDA(cudaMemcpy(out, h->dbg_ts, 24 * sizeof(long long), cudaMemcpyDeviceToHost));
   return BNV_OK;
 }
 

@@ -115,7 +115,8 @@ struct alignas(64) EngineParams {
   int rank;
   float* u_out;         // [T][2]
   float* opt_rec;       // [T+1][3]
-  long long* dbg_ts;    // optional [16] clock64 stamps of the last CTA (BNV_DEBUG_TS; null in production)
+  long long* dbg_ts;    // optional [24] stamps (BNV_DEBUG_TS; null in production): clock64 phases of the last CTA in
+                        // [0, 16), wall-clock (ns) stamps of the kernel start [16] and of column 0's exchange [8, 9, 11]
 };
 
 #define BNV_STAMP(i)                                                   \
@@ -131,7 +132,7 @@ struct alignas(64) EngineParams {
 struct RolloutSmem {
   int off_patch, off_noise, off_rec, off_uprev, off_coef, off_e, off_warpu, off_red, off_merge, total;
 };
-constexpr int kMergeACap = 1024;    // fast grid merge: per-CTA rescale factors kept in shared memory
+constexpr int kMergeACap = 1280;    // fast grid merge: one copy PER WARP of the per-CTA rescale factors in shared memory
 constexpr int kMergeGrpCap = 1024;  // ... and ngrp x 2T partial column sums
 __host__ __device__ inline int rec_slab_slots(int T, int rec_split) {
   return rec_split > 0 ? (rec_split > T + 1 - rec_split ? rec_split : T + 1 - rec_split) : T + 1;
@@ -743,7 +744,7 @@ __global__ void __launch_bounds__((kWide ? kWideWarps : kMaxWarps) * 32, kWide ?
   extern __shared__ __align__(128) unsigned char smem[];
   const long long t_start = clock64();
   if (P.dbg_ts != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0)
-    P.dbg_ts[13] = static_cast<long long>(globaltimer_ns());  // BNV_DEBUG_TS: wall clock (ns) at the start of CTA 0
+    P.dbg_ts[16] = static_cast<long long>(globaltimer_ns());  // BNV_DEBUG_TS: wall clock (ns) at the start of CTA 0
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int T = P.T;
   const int nwarps = blockDim.x >> 5;
@@ -1278,21 +1279,24 @@ __global__ void __launch_bounds__((kWide ? kWideWarps : kMaxWarps) * 32, kWide ?
   // LSE merge of `nblk` partials (ms_src [nblk][2], u_src [nblk][2T]) by this CTA: leaves M, S and the un-normalised
   // column sums U in uprev_s.  Called by every thread of the CTA.
   auto merge_partials = [&](const float* part_ms_e, const float* part_u_e, const int nblk) {
-    // Fast path (2T a multiple of 4, one float4 column unit per thread, every a_g in shared memory): everything the
-    // merge needs from other SMs -- (m_g, s_g) and this thread's share of the U_g rows -- is requested up front and
-    // consumed from registers, so the merge costs one L2 round trip.  Fixed assignment and fixed-order sums keep
-    // the result bit-reproducible.
-    constexpr int kMsCache = 8, kMergeBatch = kWide ? 8 : 32;  // (the wide variant lives within 128 registers)
+    // Fast path (2T a multiple of 4, one float4 column unit per thread): everything the merge needs from other SMs --
+    // all (m_g, s_g) and this thread's share of the U_g rows -- is requested up front and consumed from registers, so
+    // the merge costs one L2 round trip.  EVERY WARP computes M, S and the rescale factors a_g = exp(m_g - M) for itself
+    // (same lanes, same order: bit-identical in every warp) into its own copy in shared memory, so the only CTA
+    // barrier of the merge is the one between the scaled row sums and the column sums (round 1: four barriers,
+    // 3.5k cycles after the loads; now ~1.5k).  Fixed assignment and fixed-order sums keep the result bit-reproducible.
+    constexpr int kMsCache = 10, kMergeBatch = kWide ? 8 : 32;  // (the wide variant lives within 128 registers)
     const int nunit = ncol >> 2;
-    const bool fast_merge = (ncol & 3) == 0 && nunit <= static_cast<int>(blockDim.x) && nblk <= kMergeACap &&
-                            ncol <= kMergeGrpCap && nblk <= kMsCache * static_cast<int>(blockDim.x);
+    const bool fast_merge = (ncol & 3) == 0 && nunit <= static_cast<int>(blockDim.x) && nblk * nwarps <= kMergeACap &&
+                            ncol <= kMergeGrpCap && nblk <= kMsCache * 32;
     int ngrp = 1;
+    bool s_known = false;
     if (fast_merge) {
       ngrp = min(min(static_cast<int>(blockDim.x) / nunit, kMergeGrpCap / ncol), nblk);
       float2 ms[kMsCache];
 #pragma unroll
       for (int j = 0; j < kMsCache; ++j) {
-        const int g = tid + j * static_cast<int>(blockDim.x);
+        const int g = lane + 32 * j;
         ms[j] = make_float2(-FLT_MAX, 0.0f);
         if (g < nblk) ms[j] = __ldcg(reinterpret_cast<const float2*>(part_ms_e) + g);
       }
@@ -1310,29 +1314,25 @@ __global__ void __launch_bounds__((kWide ? kWideWarps : kMaxWarps) * 32, kWide ?
 #pragma unroll
       for (int j = 0; j < kMsCache; ++j) lm = fmaxf(lm, ms[j].x);
       if (stamp) BNV_STAMP(12);
-      lm = warp_max(lm);
-      if (lane == 0) red_s[16 + warp] = lm;
-      __syncthreads();
-      if (stamp) BNV_STAMP(13);
-      M = red_s[16];
-      for (int w = 1; w < nwarps; ++w) M = fmaxf(M, red_s[16 + w]);
+      M = warp_max(lm);
+      float* a_w = a_s + warp * nblk;  // this warp's copy of the rescale factors
       float lsum = 0.0f;
 #pragma unroll
       for (int j = 0; j < kMsCache; ++j) {
-        const int g = tid + j * static_cast<int>(blockDim.x);
+        const int g = lane + 32 * j;
         if (g < nblk) {
           const float a = __expf(ms[j].x - M);
-          a_s[g] = a;
+          a_w[g] = a;
           lsum = fmaf(a, ms[j].y, lsum);
         }
       }
-      lsum = warp_sum(lsum);
-      if (lane == 0) red_s[24 + warp] = lsum;
-      __syncthreads();
+      S = warp_sum(lsum);
+      s_known = true;
+      __syncwarp();
       if (stamp) BNV_STAMP(14);
       if (cnt > 0) {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float* ap = a_s + grp;
+        const float* ap = a_w + grp;
 #pragma unroll
         for (int j = 0; j < kMergeBatch; ++j) {
           if (j < cnt) {
@@ -1386,8 +1386,10 @@ __global__ void __launch_bounds__((kWide ? kWideWarps : kMaxWarps) * 32, kWide ?
     }
     if (stamp) BNV_STAMP(15);
     __syncthreads();
-    S = 0.0f;
-    for (int w = 0; w < nwarps; ++w) S += red_s[24 + w];
+    if (!s_known) {
+      S = 0.0f;
+      for (int w = 0; w < nwarps; ++w) S += red_s[24 + w];
+    }
     for (int c = tid; c < ncol; c += blockDim.x) {
       float acc = 0.0f;
       for (int gq = 0; gq < ngrp; ++gq) acc += grp_s[gq * ncol + c];

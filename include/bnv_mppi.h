@@ -264,7 +264,7 @@ int bnv_mppi_kernel_time(bnv_mppi* h, double* total_ms, uint64_t* launches);
 
 /* Debug hook: clock64() stamps taken by the last CTA of the most recent rollout kernel (phase boundaries;
  * see mppi_kernels.cuh BNV_STAMP).  Only recorded when the handle was created with BNV_DEBUG_TS set. */
-int bnv_debug_timestamps(bnv_mppi* h, long long out[16]);
+int bnv_debug_timestamps(bnv_mppi* h, long long out[24]);
 
 /* Test hook: the raw Philox4x32-10 block function behind the engine's noise stream, for known-answer tests
  * (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3", SC'11; Random123 kat_vectors).

@@ -46,10 +46,10 @@ def main() -> None:
             solver.forward(st)
             ev1.record()
             torch.cuda.synchronize()
-            ts = (C.c_longlong * 16)()
+            ts = (C.c_longlong * 24)()
             _cabi.check(solver._lib.bnv_debug_timestamps(solver._handle, ts))
             if it >= 10:
-                rows.append((0 if mode == "flushed" else 1, ts[13], ts[8], ts[9], ts[11], ev0.elapsed_time(ev1) * 1e6))
+                rows.append((0 if mode == "flushed" else 1, ts[16], ts[8], ts[9], ts[11], ev0.elapsed_time(ev1) * 1e6))
     mine = torch.tensor(rows, dtype=torch.float64, device=dev)
     allr = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(allr, mine)

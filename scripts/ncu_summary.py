@@ -16,6 +16,9 @@ import os
 import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+import sys  # noqa: E402
+
+sys.path.insert(0, ROOT)
 OUT = os.path.join(ROOT, "gpurun_out")
 PROF = os.path.join(ROOT, "profiles")
 
@@ -30,9 +33,49 @@ METRICS = [
 ]
 
 
+EXTRA_METRICS = [
+    "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
+    "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "sm__warps_active.avg.per_cycle_active",
+]
+
+
 def to_bytes(value: str, unit: str) -> float:
     mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
     return float(value) * mult
+
+
+def summarize_launches(path: str, out_path: str, tag: str, cmd: str) -> None:
+    if not os.path.exists(path):
+        return
+    rows = [r for r in csv.reader(open(path)) if len(r) > 5]
+    ci = {n: i for i, n in enumerate(rows[0])}
+    d = collections.defaultdict(list)
+    for r in rows[1:]:
+        try:
+            d[r[ci["Kernel Name"]]].append(float(r[ci["Metric Value"]]))
+        except (ValueError, IndexError):
+            pass
+    tot = sum(sum(v) for v in d.values())
+    with open(out_path, "w") as f:
+        f.write(f"# {tag}: ncu --metrics gpu__time_duration.sum --clock-control none ... {cmd}\n")
+        f.write("# per-launch device time, cold-cache and serialised by ncu: compare SHARES, not absolutes\n")
+        for k, v in sorted(d.items(), key=lambda x: -sum(x[1])):
+            f.write(f"{k[:96]:96s} launches={len(v):4d} avg_us={sum(v) / len(v) / 1000:8.2f} share={sum(v) / tot * 100:5.1f}%\n")
+        f.write("# at::FillFunctor = bench.py's 256 MiB L2 flush between timed steps (outside the timed event pairs)\n")
+        ours = {k: v for k, v in d.items() if "bnv::" in k or "rollout_kernel" in k or "normalize_weights" in k}
+        tot_ours = sum(sum(v) for v in ours.values()) or 1.0
+        for k, v in ours.items():
+            f.write(f"# share of the step (our kernels only): {k[:70]} {sum(v) / tot_ours * 100:5.1f}%\n")
+    print(open(out_path).read())
 
 
 def main() -> None:
@@ -40,10 +83,18 @@ def main() -> None:
     ap.add_argument("--tag", default="r01")
     ap.add_argument("--workload", default="G256_K16384_T50")
     ap.add_argument("--cmd", default="python bench.py --steps 150 --warmup 10")
+    ap.add_argument("--out-dir", default=None, help="write the summaries here instead of profiles/ (on the GPU box: "
+                                                    "gpurun_out/summaries, the only directory that travels back)")
     args = ap.parse_args()
+    global PROF
+    if args.out_dir:
+        PROF = os.path.abspath(args.out_dir)
     os.makedirs(PROF, exist_ok=True)
 
-    path = os.path.join(OUT, "launches.csv")
+    for csv_name, suffix, cmd in (("launches.csv", "launches_summary", args.cmd),
+                                  ("launches_c2.csv", "launches_c2_summary", "python bench.py --config c2 --steps 30 --warmup 5")):
+        summarize_launches(os.path.join(OUT, csv_name), os.path.join(PROF, f"{args.tag}_{suffix}.txt"), args.tag, cmd)
+    path = os.path.join(OUT, "launches.csv.disabled")
     if os.path.exists(path):
         rows = [r for r in csv.reader(open(path)) if len(r) > 5]
         ci = {n: i for i, n in enumerate(rows[0])}
@@ -67,56 +118,48 @@ def main() -> None:
                 f.write(f"# share of the step (our kernels only): {k[:60]} {sum(v) / tot_ours * 100:5.1f}%\n")
         print(open(os.path.join(PROF, f"{args.tag}_launches_summary.txt")).read())
 
-    # extra full captures of the widened path (scripts/profile_targets.py): one summary file each
-    extra = {"prof_batch": ("batch_ncu_summary", "rollout_kernel<.., kBatch>: 8 environments x K=4096 x T=30 (config 3 per-GPU share)"),
-             "prof_stoch": ("stoch_ncu_summary", "rollout_kernel<.., kStoch>: G=256, K=32768, T=50 (config 4)"),
-             "prof_risk": ("risk_mc_ncu_summary", "risk_mc_kernel: G=256, 1000 draws per cell, CVaR")}
-    for stem, (name, what) in extra.items():
+    # full captures (ncu --set full): one summary file each, and the per-launch DRAM traffic of the rollout kernel into
+    # profiles/rollout_traffic.json under the key bench.py looks up, stamped with the kernel source hash
+    import bench
+
+    caps = {
+        "prof_rollout": ("rollout_ncu_summary", "c1_G256_K16384_T50",
+                         "latency variant, bench.py --config c1 (G=256, K=16384, T=50): python bench.py --steps 40 --warmup 10"),
+        "prof_wide": ("wide_ncu_summary", "c2_G512_K131072_T50",
+                      "wide variant, bench.py --config c2 on one GPU (G=512, K=131072, T=50)"),
+        "prof_batch": ("batch_ncu_summary", None, "rollout_kernel<.., kBatch>: 8 environments x K=4096 x T=30 (config 3 per-GPU share)"),
+        "prof_stoch": ("stoch_ncu_summary", "c4_G256_K32768_T50", "rollout_kernel<.., kStoch>: G=256, K=32768, T=50 (config 4)"),
+        "prof_risk": ("risk_mc_ncu_summary", None, "risk_mc_kernel: G=256, 1000 draws per cell, CVaR"),
+    }
+    tpath = os.path.join(PROF, "rollout_traffic.json")
+    tj = json.load(open(tpath)) if os.path.exists(tpath) else {}
+    for stem, (name, workload, what) in caps.items():
         rep_x = os.path.join(OUT, stem + ".ncu-rep")
         if not os.path.exists(rep_x):
             continue
         raw = subprocess.run(["ncu", "-i", rep_x, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(raw.splitlines()))
         hdr, units, data = rows[0], rows[1], rows[2:]
-        with open(os.path.join(PROF, f"{args.tag}_{name}.txt"), "w") as f:
-            f.write(f"# {args.tag}: ncu --set full --clock-control none --import-source on, {what}\n")
-            f.write("# one column per captured launch; ncu flushes caches between replays (cold)\n")
-            if "Kernel Name" in hdr:
-                f.write("# kernel: " + data[0][hdr.index("Kernel Name")][:150] + "\n")
-            for m in METRICS:
-                if m in hdr:
-                    i = hdr.index(m)
-                    f.write(f"{m:70s} [{units[i]:>16s}] " + "  ".join(r[i] for r in data) + "\n")
-        print(open(os.path.join(PROF, f"{args.tag}_{name}.txt")).read())
-
-    rep = os.path.join(OUT, "prof_rollout.ncu-rep")
-    if os.path.exists(rep):
-        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-        rows = list(csv.reader(raw.splitlines()))
-        hdr, units, data = rows[0], rows[1], rows[2:]
-        lines, traffic = [], []
-        for m in METRICS:
-            if m in hdr:
-                i = hdr.index(m)
-                lines.append(f"{m:70s} [{units[i]:>16s}] " + "  ".join(r[i] for r in data))
+        traffic = []
         if "dram__bytes_read.sum" in hdr:
             ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
             traffic = [to_bytes(r[ir], units[ir]) + to_bytes(r[iw], units[iw]) for r in data]
-        with open(os.path.join(PROF, f"{args.tag}_rollout_ncu_summary.txt"), "w") as f:
-            f.write(f"# {args.tag}: ncu --set full --clock-control none --import-source on -k regex:rollout_kernel "
-                    f"-s 20 -c {len(data)} python bench.py --steps 40 --warmup 10   (workload {args.workload})\n")
+        with open(os.path.join(PROF, f"{args.tag}_{name}.txt"), "w") as f:
+            f.write(f"# {args.tag}: ncu --set full --clock-control none --import-source on -k regex:<kernel>, {what}\n")
             f.write("# one column per captured launch; ncu flushes caches between replays (cold)\n")
-            f.write("\n".join(lines) + "\n")
+            if "Kernel Name" in hdr:
+                f.write("# kernel: " + data[0][hdr.index("Kernel Name")][:150] + "\n")
+            for m in METRICS + EXTRA_METRICS:
+                if m in hdr:
+                    i = hdr.index(m)
+                    f.write(f"{m:78s} [{units[i]:>16s}] " + "  ".join(r[i] for r in data) + "\n")
             if traffic:
-                f.write(f"# DRAM traffic per launch (read+write): {[int(t) for t in traffic]} bytes; the ~17 MB of slab writes "
-                        f"stay in the 126 MB L2 (write-back) for the kernel's lifetime\n")
-        print(open(os.path.join(PROF, f"{args.tag}_rollout_ncu_summary.txt")).read())
-        if traffic:
-            tpath = os.path.join(PROF, "rollout_traffic.json")
-            tj = json.load(open(tpath)) if os.path.exists(tpath) else {}
-            tj[args.workload] = {"dram_bytes_per_launch": int(sum(traffic) / len(traffic)), "source": f"{args.tag} ncu --set full",
-                                 "launches": len(traffic)}
-            json.dump(tj, open(tpath, "w"), indent=1)
+                f.write(f"# DRAM traffic per launch (read+write): {[int(t) for t in traffic]} bytes\n")
+        print(open(os.path.join(PROF, f"{args.tag}_{name}.txt")).read())
+        if traffic and workload:
+            tj[workload] = {"dram_bytes_per_launch": int(sum(traffic) / len(traffic)), "source": f"profiles/{args.tag}_{name}.txt",
+                            "launches": len(traffic), "kernel_source_hash": bench.kernel_source_hash()}
+    json.dump(tj, open(tpath, "w"), indent=1)
 
 
 if __name__ == "__main__":

@@ -29,7 +29,7 @@ for it in range(6):
         flush.fill_(it)
     s.forward(st, noise=nz)
     torch.cuda.synchronize()
-    ts = (C.c_longlong * 16)()
+    ts = (C.c_longlong * 24)()
     _cabi.check(s._lib.bnv_debug_timestamps(s._handle, ts))
     t0 = ts[0]
     print(("cold " if it >= 3 else "warm ") + " ".join(f"{n}={ts[i] - t0}" for i, n in enumerate(names)))
