@@ -639,6 +639,26 @@ def run_native(args) -> None:
                            "single_gpu_launch": single_ref.launch_geometry}
         barrier()
 
+    # ---- N = 1 of the weak-scaling family: the SAME per-GPU workload the N > 1 lines run (K = 16384 on the 512x512
+    # terrain), so that scaling efficiency has one baseline (the headline c1 is the 256x256 configuration)
+    weak_base = None
+    if world == 1 and w["name"] == "c1":
+        from benchnav_b200 import MPPI
+        from benchnav_b200.problem import GoalObjectives, GridSpec, UnicycleProblem
+
+        wb = resolve_workload("c2w", 1)
+        risk_b, start_b, goal_b, thr_b = build_problem(wb["grid"])
+        dyn_b = UnicycleProblem(GridSpec(wb["grid"], RESOLUTION), risk_b)
+        sol_b = MPPI(wb["horizon"], wb["k_total"], 3, 2, dyn_b, GoalObjectives(dyn_b, goal_b, thr_b), torch.tensor(SIGMAS),
+                     LAMBDA, device=dev, seed=SEED)
+        st_b = start_b.to(dev)
+        for _ in range(3):
+            sol_b.forward(st_b)
+        n_b = min(steps, 1000)
+        ms_b = timed_pass(lambda: sol_b.forward(st_b), n_b) / n_b
+        weak_base = {"workload": wb["label"], "ms_per_step": ms_b, "iters_per_sec": 1e3 / ms_b, "steps": n_b}
+        sol_b.close()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -658,6 +678,8 @@ def run_native(args) -> None:
         detail["launch"] = solver.launch_geometry
     if w["kind"] == "batch":
         detail["env_iters_per_sec"] = control_rate * w["envs"]
+    if weak_base is not None:
+        detail["weak_scaling_n1"] = weak_base
     if single_same is not None:
         detail.update(single_same)
         detail["speedup_vs_1gpu"] = single_same["single_gpu_same_total_ms"] / ms_per_step

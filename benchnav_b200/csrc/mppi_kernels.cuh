@@ -484,6 +484,42 @@ __device__ __forceinline__ void copy_rows_flat(float* __restrict__ dst, int dst_
   }
 }
 
+// The full chunk of recorded states (32 rows x 48 words), specialised: 48 words per row and 32 lanes per pass repeat
+// every 3 passes = 2 rows, so each lane needs only three (shared, global) word offsets, computed once; per row pair
+// the copy is 3 LDS + 3 STG with immediate shared-memory offsets (the generic flat copy spends ~9 instructions per
+// pass on index arithmetic -- measured 21 % of the wide variant's instructions before this).
+struct RecFlushLane {
+  int so[3], go[3];  // word offsets within a row pair: shared (row stride kWideRecStride) / global (row stride 3 (T+1))
+};
+__device__ __forceinline__ RecFlushLane rec_flush_lane(int T, int lane) {
+  RecFlushLane f;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const int w = 32 * j + lane;  // 0 .. 95 = two rows of 48 words
+    const int second = w >= 3 * kChunkSteps ? 1 : 0;
+    const int col = w - second * 3 * kChunkSteps;
+    f.so[j] = second * kWideRecStride + col;
+    f.go[j] = second * 3 * (T + 1) + col;
+  }
+  return f;
+}
+__device__ __forceinline__ void flush_rec_chunk(float* __restrict__ dst, int T, const float* __restrict__ src,
+                                                const RecFlushLane& f) {
+  const int pair_stride = 2 * 3 * (T + 1);
+#pragma unroll
+  for (int q0 = 0; q0 < 16; q0 += 4) {  // four row pairs = twelve loads in flight
+    float v[4][3];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) v[q][j] = src[(q0 + q) * 2 * kWideRecStride + f.so[j]];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) dst[(q0 + q) * pair_stride + f.go[j]] = v[q][j];
+  }
+}
+
 template <bool kRecord, bool kPhilox>
 __device__ __forceinline__ void store_slabs(const EngineParams& P, float* rec_env, float* noise_env, float* rec_s,
                                             float* nz_w, int warp, int lane, int warp_first, int warp_rows,
@@ -977,7 +1013,8 @@ __global__ void __launch_bounds__((kWide ? kWideWarps : kMaxWarps) * 32, kWide ?
       __syncwarp();
       if (kRecord) {
         const float* src = rec_s + warp * 32 * kWideRecStride;
-        if (nt_rec == kChunkSteps) copy_rows_flat<3 * kChunkSteps>(rec_g, 3 * (T + 1), src, kWideRecStride, 0, lane);
+        if (nt_rec == kChunkSteps) flush_rec_chunk(rec_g, T, src, rec_flush_lane(T, lane));  // (offsets recomputed per
+                                                                                             // flush: not kept live in the loop)
         else copy_rows_flat<0>(rec_g, 3 * (T + 1), src, kWideRecStride, 3 * nt_rec, lane);
       }
       if (kPhilox && nt_nz > 0) {
@@ -1180,15 +1217,31 @@ __global__ void __launch_bounds__((kWide ? kWideWarps : kMaxWarps) * 32, kWide ?
 #pragma unroll
         for (int q = 0; q < 4; ++q) acc[q][i] = 0.0f;
       }
+      const float* colp[4];  // this lane's four columns; a column group past the last column reads column 0 and is
+      bool col_ok[4];        // discarded at the end
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        col_ok[i] = cc[i] < ncol2;
+        colp[i] = nz_rows + (col_ok[i] ? cc[i] : 0);
+      }
 #pragma unroll 1
       for (int r0 = 0; r0 < 32; r0 += 16) {
         if (((nzmask >> r0) & 0xFFFFu) == 0u) continue;
         float v[16][4];
+        if (warp_rows == 32) {  // full warp: no row guards, row offsets are warp-uniform
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
+          for (int j = 0; j < 16; ++j) {
+            const int roff = (r0 + j) * ncol2;
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            v[j][i] = (r0 + j < warp_rows && cc[i] < ncol2) ? __ldcg(nz_rows + (r0 + j) * ncol2 + cc[i]) : 0.0f;
+            for (int i = 0; i < 4; ++i) v[j][i] = __ldcg(colp[i] + roff);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              v[j][i] = (r0 + j < warp_rows && col_ok[i]) ? __ldcg(colp[i] + (r0 + j) * ncol2) : 0.0f;
+        }
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const float ej = ew[r0 + j];
