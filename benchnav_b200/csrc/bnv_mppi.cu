@@ -598,6 +598,7 @@ static int launch_forward(bnv_mppi* h, const float* state_dev, const float* stat
   }
   bnv::EngineParams P = h->P;
   P.state_role = state_role;
+  P.dbg_flags = debug_disable() >> 14;
   const bool philox = noise_dev == nullptr;
   P.noise_in = noise_dev;
   P.noise_out = h->noise;

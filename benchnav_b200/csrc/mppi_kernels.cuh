@@ -75,6 +75,8 @@ struct alignas(64) EngineParams {
   const float* state;   // [3] device-resident current state, or
   float state_val[3];   // ... the same three floats passed by value in the launch packet (state_inline != 0)
   int state_inline;
+  unsigned int dbg_flags;  // measurement aids (BNV_DEBUG_DISABLE >> 14): 2 = the optimal rollout draws its lookup
+                           // normals in its own chain instead of reading the warp's pre-drawn ones
   int state_role;       // sharded solver driven from ONE rank's host (bnv_mppi_forward_host on the leader,
                         // bnv_mppi_forward_follow on the others): 1 = leader: broadcast state_val to every peer's state
                         // cell over NVLink at kernel start; 2 = follower: take the state from this rank's own cell
@@ -354,7 +356,7 @@ __device__ void optimal_rollout(int T, const StepConsts& c, const float* uc_s, f
   float2 ms = make_float2(0.0f, 0.0f);
   float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
   auto xi_at = [&](int t) -> float {
-    if (xi.row != nullptr) return __ldg(xi.row + t);
+    if (xi.row != nullptr) return xi.row[t];  // injected (global) or pre-drawn by the warp (shared memory)
     if ((t & 1) == 0) q = xi_quad(xi.sample, static_cast<uint32_t>(t >> 1), xi.iter_lo, xi.iter_hi, xi.key);
     return (t & 1) ? q.z : q.x;
   };
@@ -381,6 +383,20 @@ __device__ void optimal_rollout(int T, const StepConsts& c, const float* uc_s, f
     out[3 * t + 0] = xr; out[3 * t + 1] = yr; out[3 * t + 2] = thr;
   }
   out[3 * T + 0] = x; out[3 * T + 1] = y; out[3 * T + 2] = th;
+}
+
+// Stochastic mode: the optimal rollout's T lookup normals do not depend on the rollout, so the warp draws them up
+// front, one step pair per lane, into shared memory -- the serial thread then reads a float per step instead of running
+// Philox4x32-10 + Box-Muller inside its dependency chain (measured: 490 -> ~150 cycles per step, 17k cycles per iteration
+// of config 4).  Same xi_quad() calls as the in-chain draw: bit-identical.  All 32 lanes of the warp must call it.
+__device__ __forceinline__ void predraw_optimal_xi(float* xi_s, int T, uint32_t iter_lo, uint32_t iter_hi, uint2 key,
+                                                   int lane) {
+  for (int p = lane; 2 * p < T; p += 32) {
+    const float4 q = xi_quad(kOptimalSample, static_cast<uint32_t>(p), iter_lo, iter_hi, key);
+    xi_s[2 * p] = q.x;
+    if (2 * p + 1 < T) xi_s[2 * p + 1] = q.z;
+  }
+  __syncwarp();
 }
 
 // weights[k] *= scale(k): four samples per load, kBatch loads in flight per thread (the values were written by
@@ -1305,7 +1321,10 @@ __global__ void __launch_bounds__((kWide ? kWideWarps : kMaxWarps) * 32, kWide ?
   // one SM, measured 12 us), and the group merges overlap the rollouts still running.
   const int nblk_all = gridDim.x;
   const int ncol = 2 * T;
-  const bool two_level = !coop && nblk_all > kTwoLevelMin;
+  const bool two_level = !coop && nblk_all > kTwoLevelMin;  // (co-resident grids: measured SLOWER in two levels --
+                                                            // 256 CTAs: 53.1 vs 47.6 us at config 4, 42.3 vs 36.7 us
+                                                            // deterministic -- the waiting CTAs make the extra ticket
+                                                            // round trips expensive)
   const int ngroups = (nblk_all + kMergeGroup - 1) / kMergeGroup;
   const int my_group = blockIdx.x / kMergeGroup;
   const int group_cnt = min(kMergeGroup, nblk_all - my_group * kMergeGroup);
@@ -1397,6 +1416,8 @@ __global__ void __launch_bounds__((kWide ? kWideWarps : kMaxWarps) * 32, kWide ?
           }
         }
         for (int j0 = kMergeBatch; j0 < cnt; j0 += 8) {  // more CTAs than the first batch covers: eight loads at a time
+                                                         // (whole batches of 32 again measured slower: 15k vs 7k cycles
+                                                         // for the 20 extra rows per thread of a 256-CTA grid)
           float4 q[8];
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj) {
@@ -1535,13 +1556,19 @@ __global__ void __launch_bounds__((kWide ? kWideWarps : kMaxWarps) * 32, kWide ?
         stats_e[0] = M;
         stats_e[1] = complete ? S : 1.0f;
       }
-      if (complete && tid == 0) {
-        if (kWide) C.pin_all();  // the serial rollout is a pure latency chain: its invariants belong in registers
-        const XiSource xs{(kStoch && !kPhilox) ? P.xi_opt_in + static_cast<size_t>(env) * T : nullptr, kOptimalSample,
-                          iter_lo, iter_hi_e, key};
-        optimal_rollout<kPatch, kPow2, kFastAngles, kStoch>(T, C, warpu_s, sx, sy, sth,
-                                                            P.opt_rec + static_cast<size_t>(env) * 3 * (T + 1), xs);
-        signal_done(P);
+      if (complete && warp == 0) {
+        const float* xi_row = (kStoch && !kPhilox) ? P.xi_opt_in + static_cast<size_t>(env) * T : nullptr;
+        if (kStoch && kPhilox && T <= kMergeGrpCap && !(P.dbg_flags & 2u)) {  // (grp_s is free once the merge is done)
+          predraw_optimal_xi(grp_s, T, iter_lo, iter_hi_e, key, lane);
+          xi_row = grp_s;
+        }
+        if (lane == 0) {
+          if (kWide) C.pin_all();  // the serial rollout is a pure latency chain: its invariants belong in registers
+          const XiSource xs{xi_row, kOptimalSample, iter_lo, iter_hi_e, key};
+          optimal_rollout<kPatch, kPow2, kFastAngles, kStoch>(T, C, warpu_s, sx, sy, sth,
+                                                              P.opt_rec + static_cast<size_t>(env) * 3 * (T + 1), xs);
+          signal_done(P);
+        }
       }
       if (stamp) BNV_STAMP(7);
     }
@@ -1560,12 +1587,18 @@ __global__ void __launch_bounds__((kWide ? kWideWarps : kMaxWarps) * 32, kWide ?
     if (valid) weights_e[k] = e * __expf(m_cta - M) * (complete ? __fdiv_rn(1.0f, S) : 1.0f);
     if (!kWide)
       store_slabs<kRecord, kPhilox>(P, rec_e, noise_out_e, rec_s, nz_w, warp, lane, warp_first, warp_rows, nz_bytes);
-    if (is_last && complete && tid == 0) {
-      const XiSource xs{(kStoch && !kPhilox) ? P.xi_opt_in + static_cast<size_t>(env) * T : nullptr, kOptimalSample,
-                        iter_lo, iter_hi_e, key};
-      optimal_rollout<kPatch, kPow2, kFastAngles, kStoch>(T, C, warpu_s, sx, sy, sth,
-                                                          P.opt_rec + static_cast<size_t>(env) * 3 * (T + 1), xs);
-      signal_done(P);
+    if (is_last && complete && warp == 0) {
+      const float* xi_row = (kStoch && !kPhilox) ? P.xi_opt_in + static_cast<size_t>(env) * T : nullptr;
+      if (kStoch && kPhilox && T <= kMergeGrpCap && !(P.dbg_flags & 2u)) {
+        predraw_optimal_xi(grp_s, T, iter_lo, iter_hi_e, key, lane);
+        xi_row = grp_s;
+      }
+      if (lane == 0) {
+        const XiSource xs{xi_row, kOptimalSample, iter_lo, iter_hi_e, key};
+        optimal_rollout<kPatch, kPow2, kFastAngles, kStoch>(T, C, warpu_s, sx, sy, sth,
+                                                            P.opt_rec + static_cast<size_t>(env) * 3 * (T + 1), xs);
+        signal_done(P);
+      }
     }
     if (is_last && P.dbg_ts != nullptr && env == 0) BNV_STAMP(7);
   }

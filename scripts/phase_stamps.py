@@ -12,9 +12,20 @@ from benchnav_b200.problem import GoalObjectives, GridSpec, UnicycleProblem
 from benchnav_b200.synthetic import benchmark_problem
 
 K, T, G = int(sys.argv[1]) if len(sys.argv) > 1 else 16384, 50, 256
+STOCH = len(sys.argv) > 2 and sys.argv[2] == "stoch"  # BASELINE config 4: stochastic-slip lookups
 risk, start, goal, thr = benchmark_problem(G, 0.5, seed=0)
-dyn = UnicycleProblem(GridSpec(G, 0.5), risk)
-s = MPPI(T, K, 3, 2, dyn, GoalObjectives(dyn, goal, thr), torch.tensor([0.5, 0.5]), 0.5, device=torch.device("cuda"))
+if STOCH:
+    from benchnav_b200.problem import SlipDistribution
+    from benchnav_b200.synthetic import make_terrain
+
+    terr = make_terrain(G, 0.5, 0)
+    dyn = UnicycleProblem(GridSpec(G, 0.5, distributions={"predictions": SlipDistribution(terr["slip_mean"], terr["slip_std"])}),
+                          terr["slip_mean"])
+else:
+    dyn = UnicycleProblem(GridSpec(G, 0.5), risk)
+s = MPPI(T, K, 3, 2, dyn, GoalObjectives(dyn, goal, thr), torch.tensor([0.5, 0.5]), 0.5, device=torch.device("cuda"),
+         stochastic_slip=STOCH)
+print("launch", s.launch_geometry)
 st = start.cuda()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 # distributed schedule (default): 4 = barrier passed, 12 = (M, S) known, 5 = weights' (M, S) in smem, 6 = u* gathered,
