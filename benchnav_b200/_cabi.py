@@ -112,6 +112,7 @@ _SIGNATURES = {
     "bnv_mppi_kernel_timing": (C.c_int, [_VP, C.c_int32]),
     "bnv_mppi_kernel_time": (C.c_int, [_VP, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "bnv_debug_timestamps": (C.c_int, [_VP, C.POINTER(C.c_longlong)]),
+    "bnv_debug_flush": (C.c_int, [_VP, C.c_uint64, C.c_uint32, C.c_uint32, _VP]),
     "bnv_debug_philox": (C.c_int, [_VP, _VP, C.c_int32, _VP]),
     "bnv_debug_sincos": (C.c_int, [_VP, _VP, _VP, C.c_int32, _VP]),
     "bnv_trav_lookup": (C.c_int, [C.POINTER(Grid), _VP, _VP, C.c_int64, C.c_int64, _VP, C.c_int64, C.c_int32, _VP,

@@ -101,6 +101,8 @@ struct bnv_mppi {
   int max_groups = 1;
   unsigned int* err_flag = nullptr;      // device word raised by a timed-out in-kernel wait
   float* stats = nullptr;
+  float* replay = nullptr;             // [E][2T + 4] mean sequence + state of the last iteration (lean solvers' re-roll)
+  const float* last_noise = nullptr;   // noise array of the last iteration: h->noise, or the caller's injected tensor
   unsigned int epoch = 0;
   int num_sms = 0;
   bool coop_ok = true;
@@ -165,6 +167,7 @@ void free_all(bnv_mppi* h) {
   cudaFree(h->part2_u);
   cudaFree(h->err_flag);
   cudaFree(h->stats);
+  cudaFree(h->replay);
   cudaFree(h->dbg_ts);
   for (size_t r = 0; r < h->peer_ptrs.size(); ++r)
     if (h->peers_attached && static_cast<int>(r) != h->cfg.rank && h->peer_ptrs[r]) cudaIpcCloseMemHandle(h->peer_ptrs[r]);
@@ -397,6 +400,7 @@ int bnv_mppi_create(bnv_mppi** out, const bnv_mppi_cfg* cfg) {
   alloc(reinterpret_cast<void**>(&h->part2_u), sizeof(float) * nE * nG * 2 * T);
   alloc(reinterpret_cast<void**>(&h->err_flag), sizeof(unsigned int));
   alloc(reinterpret_cast<void**>(&h->stats), 4 * nE * sizeof(float));
+  if (!record) alloc(reinterpret_cast<void**>(&h->replay), nE * (2 * T + 4) * sizeof(float));
   alloc(reinterpret_cast<void**>(&h->goals_dev), 2 * nE * sizeof(float));
   if (cfg->world_size > 1) {  // mailbox: [2 parities][world ranks][2T columns] cells of three LL words {U[c] | M | S, tag}
     // + [2 parities] state cells of three LL words {x | y | theta, tag} (host-driven sharded solver)
@@ -463,6 +467,7 @@ int bnv_mppi_create(bnv_mppi** out, const bnv_mppi_cfg* cfg) {
   P.max_groups = h->max_groups;
   P.err_flag = h->err_flag;
   P.stats = h->stats;
+  P.replay = h->replay;
   cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, cfg->device);
   int coop_attr = 0;
   cudaDeviceGetAttribute(&coop_attr, cudaDevAttrCooperativeLaunch, cfg->device);
@@ -602,6 +607,7 @@ static int launch_forward(bnv_mppi* h, const float* state_dev, const float* stat
   const bool philox = noise_dev == nullptr;
   P.noise_in = noise_dev;
   P.noise_out = h->noise;
+  h->last_noise = philox ? h->noise : noise_dev;
   P.xi_in = xi_dev;
   P.xi_opt_in = xi_opt_dev;
   P.iter_lo = static_cast<uint32_t>(h->iteration);
@@ -982,8 +988,9 @@ int bnv_mppi_finalize(bnv_mppi* h, const float* gathered_partials_dev, float* u_
 
 int bnv_mppi_top_samples(bnv_mppi* h, int32_t n, float* states_out_dev, float* weights_out_dev, void* stream) {
   if (!h || !states_out_dev || !weights_out_dev) return fail(BNV_ERR_INVALID, "null argument");
-  if (!h->P.record) return fail(BNV_ERR_STATE, "top_samples needs BNV_FLAG_RECORD_STATES");
   if (!h->have_weights) return fail(BNV_ERR_STATE, "top_samples needs a completed forward");
+  if (!h->P.record && (!h->replay || !h->last_noise))
+    return fail(BNV_ERR_STATE, "top_samples on a solver without recorded states needs a completed forward");
   if (n < 1 || n > h->Kl) return fail(BNV_ERR_INVALID, "num_samples %d outside [1, %d]", n, h->Kl);  // mppi.py:229
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   BNV_CUDA(cudaSetDevice(h->cfg.device));
@@ -1017,7 +1024,20 @@ int bnv_mppi_top_samples(bnv_mppi* h, int32_t n, float* states_out_dev, float* w
   bnv::topn_select_kernel<<<h->E, bnv::kTopnThreads, smem, s>>>(h->weights, h->Kl, n, n_pad, pairs_global,
                                                                  weights_out_dev, h->top_idx);
   BNV_CUDA(cudaGetLastError());
-  bnv::gather_rows_kernel<<<dim3(n, h->E), 128, 0, s>>>(h->rec, h->top_idx, 3 * (h->P.T + 1), h->Kl, states_out_dev);
+  if (h->P.record) {
+    bnv::gather_rows_kernel<<<dim3(n, h->E), 128, 0, s>>>(h->rec, h->top_idx, 3 * (h->P.T + 1), h->Kl, states_out_dev);
+  } else {
+    // lean solver (no recorded states): roll the n selected samples out again from the iteration's saved start
+    // (E == 1: batched and stochastic solvers always record)
+    bnv::EngineParams P = h->P;
+    const bool pow2 = P.geom.fast_grid != 0;
+    using RerollFn = void (*)(bnv::EngineParams, const float*, const float*, const int*, int, float*);
+    RerollFn fn = pow2 ? (h->fast_angles ? bnv::reroll_kernel<true, true> : bnv::reroll_kernel<true, false>)
+                       : (h->fast_angles ? bnv::reroll_kernel<false, true> : bnv::reroll_kernel<false, false>);
+    const size_t smem_r = static_cast<size_t>(P.T) * 16;
+    if (smem_r > 48 * 1024) BNV_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_r)));
+    fn<<<(n + 127) / 128, 128, smem_r, s>>>(P, h->last_noise, h->replay, h->top_idx, n, states_out_dev);
+  }
   BNV_CUDA(cudaGetLastError());
   h->launches += 2;
   return BNV_OK;
@@ -1225,6 +1245,16 @@ int bnv_debug_timestamps(bnv_mppi* h, long long out[24]) {
   if (!h || !out) return fail(BNV_ERR_INVALID, "null argument");
   if (!h->dbg_ts) return fail(BNV_ERR_STATE, "set BNV_DEBUG_TS=1 before creating the handle");
   BNV_CUDA(cudaMemcpy(out, h->dbg_ts, 24 * sizeof(long long), cudaMemcpyDeviceToHost));
+  return BNV_OK;
+}
+
+int bnv_debug_flush(void* buf_dev, uint64_t bytes, uint32_t smem_bytes, uint32_t value, void* stream) {
+  if (!buf_dev || bytes < 16) return fail(BNV_ERR_INVALID, "bad argument");
+  if (smem_bytes > kMaxDynSmem) return fail(BNV_ERR_INVALID, "too much shared memory");
+  BNV_CUDA(cudaFuncSetAttribute(bnv::flush_debug_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMaxDynSmem)));
+  bnv::flush_debug_kernel<<<148 * 4, 256, smem_bytes, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<uint4*>(buf_dev), bytes / 16, value);
+  BNV_CUDA(cudaGetLastError());
   return BNV_OK;
 }
 

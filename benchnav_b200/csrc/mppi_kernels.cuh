@@ -75,6 +75,8 @@ struct alignas(64) EngineParams {
   const float* state;   // [3] device-resident current state, or
   float state_val[3];   // ... the same three floats passed by value in the launch packet (state_inline != 0)
   int state_inline;
+  float* replay;        // [E][2T + 4] (lean solvers, record == 0): the mean sequence and the state this iteration
+                        // started from, kept so that get_top_samples can re-roll the selected samples afterwards
   unsigned int dbg_flags;  // measurement aids (BNV_DEBUG_DISABLE >> 14): 2 = the optimal rollout draws its lookup
                            // normals in its own chain instead of reading the warp's pre-drawn ones
   int state_role;       // sharded solver driven from ONE rank's host (bnv_mppi_forward_host on the leader,
@@ -474,12 +476,10 @@ __device__ __forceinline__ void copy_rec_slots(float* rec_g, const float* rec_w,
 
 // Wide variant: copy a block of 32 rows x n words from a shared-memory chunk slab (row stride `src_stride` words) to
 // global rows (row stride `dst_stride` words), all 32 lanes on consecutive words of the flat (row, word) index space,
-// so that every store instruction covers whole 128-byte runs except where it crosses a row boundary.  kN = n when it is
-// known at compile time (the full chunk: division by a constant, fully unrolled), 0 = runtime n (last, partial chunk).
-template <int kN>
+// so that every store instruction covers whole 128-byte runs except where it crosses a row boundary.  Generic in n:
+// used for the last, partial chunk (the full chunk has its own specialisation below).
 __device__ __forceinline__ void copy_rows_flat(float* __restrict__ dst, int dst_stride, const float* __restrict__ src,
-                                               int src_stride, int n_rt, int lane) {
-  const int n = kN > 0 ? kN : n_rt;
+                                               int src_stride, int n, int lane) {
   const uint32_t magic = 0xFFFFFFFFu / static_cast<uint32_t>(n) + 1u;  // ceil(2^32 / n): row = umulhi(idx, magic), idx < 2^16
   const int total = 32 * n;
 #pragma unroll 1
@@ -489,7 +489,7 @@ __device__ __forceinline__ void copy_rows_flat(float* __restrict__ dst, int dst_
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int idx = base + 32 * j + lane;
-      const int row = kN > 0 ? idx / kN : static_cast<int>(__umulhi(static_cast<uint32_t>(idx), magic));
+      const int row = static_cast<int>(__umulhi(static_cast<uint32_t>(idx), magic));
       const int col = idx - row * n;
       off[j] = idx < total ? row * dst_stride + col : -1;
       v[j] = idx < total ? src[row * src_stride + col] : 0.0f;
@@ -998,6 +998,15 @@ __global__ void __launch_bounds__((kWide ? kWideWarps : kMaxWarps) * 32, kWide ?
     uc[0] = u;
     uc[2] = __fmul_rn(u, (i & 1) ? P.icov1 : P.icov0);
   }
+  if (!kRecord && blockIdx.x == 0 && P.replay != nullptr) {  // what a later re-roll of selected samples starts from
+    float* rp = P.replay + static_cast<size_t>(env) * (2 * T + 4);
+    for (int i = tid; i < 2 * T; i += blockDim.x) rp[i] = u_prev_e[i];
+    if (tid == 0) {
+      rp[2 * T] = sx;
+      rp[2 * T + 1] = sy;
+      rp[2 * T + 2] = sth;
+    }
+  }
   const float4* ucf_s = reinterpret_cast<const float4*>(coef_s);
   __syncthreads();
   if (kPatch) mbar_wait(bar_patch, 0);
@@ -1031,7 +1040,7 @@ __global__ void __launch_bounds__((kWide ? kWideWarps : kMaxWarps) * 32, kWide ?
         const float* src = rec_s + warp * 32 * kWideRecStride;
         if (nt_rec == kChunkSteps) flush_rec_chunk(rec_g, T, src, rec_flush_lane(T, lane));  // (offsets recomputed per
                                                                                              // flush: not kept live in the loop)
-        else copy_rows_flat<0>(rec_g, 3 * (T + 1), src, kWideRecStride, 3 * nt_rec, lane);
+        else copy_rows_flat(rec_g, 3 * (T + 1), src, kWideRecStride, 3 * nt_rec, lane);
       }
       if (kPhilox && nt_nz > 0) {
         if (nz_vec_ok && nt_nz == kChunkSteps) {  // 16-byte words: 8 lanes per row, 4 rows per pass
@@ -1043,7 +1052,7 @@ __global__ void __launch_bounds__((kWide ? kWideWarps : kMaxWarps) * 32, kWide ?
             *reinterpret_cast<float4*>(nz_g + static_cast<size_t>(r) * 2 * T + 4 * u) = v;
           }
         } else {
-          copy_rows_flat<0>(nz_g, 2 * T, nz_w, kWideNzStride, 2 * nt_nz, lane);
+          copy_rows_flat(nz_g, 2 * T, nz_w, kWideNzStride, 2 * nt_nz, lane);
         }
       }
       __syncwarp();
@@ -1655,6 +1664,58 @@ __global__ void __launch_bounds__(kFinalizeThreads) finalize_kernel(const __grid
   finish_iteration<kPatch, kPow2, kFastAngles>(P, C, S, w_scale, u_s, sx, sy, sth);
 }
 
+// --------------------------------------------------------------------------------------------- re-roll (lean solvers)
+// get_top_samples of a solver that keeps no recorded states (record_states=False): the n selected samples are rolled
+// out AGAIN from what the iteration started from (state and mean sequence saved by the rollout kernel, the sample's
+// noise row from the noise array) with the very step function of the rollout kernel -- same operations in the same
+// order on the same inputs, so the rows are bit-identical to what a recording solver would have stored (the lookup
+// goes to the global map instead of the staged window: same cells).  One thread = one selected sample.
+template <bool kPow2, bool kFastAngles>
+__global__ void __launch_bounds__(128) reroll_kernel(const __grid_constant__ EngineParams P, const float* __restrict__ noise,
+                                                     const float* __restrict__ replay, const int* __restrict__ idx, int n,
+                                                     float* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  float* coef_s = reinterpret_cast<float*>(smem);
+  const int T = P.T;
+  for (int i = threadIdx.x; i < 2 * T; i += blockDim.x) {
+    const float u = replay[i];
+    float* uc = coef_s + 4 * (i >> 1) + (i & 1);
+    uc[0] = u;
+    uc[2] = __fmul_rn(u, (i & 1) ? P.icov1 : P.icov0);
+  }
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4* ucf_s = reinterpret_cast<const float4*>(coef_s);
+  StepConsts C;
+  C.x_min = P.geom.x_min; C.y_min = P.geom.y_min; C.x_max = P.geom.x_max; C.y_max = P.geom.y_max;
+  C.res = P.geom.res; C.inv_res = P.geom.inv_res; C.dt = P.bounds.dt;
+  C.gx = P.goals != nullptr ? __ldg(P.goals) : P.goal_x;
+  C.gy = P.goals != nullptr ? __ldg(P.goals + 1) : P.goal_y;
+  C.thr = P.thr;
+  C.u_min0 = P.bounds.u_min0; C.u_min1 = P.bounds.u_min1; C.u_max0 = P.bounds.u_max0; C.u_max1 = P.bounds.u_max1;
+  C.lo_x = 0; C.lo_y = 0; C.hi_x = P.G - 1; C.hi_y = P.G - 1;
+  C.pitch = P.pitch;
+  C.win_addr = 0u;
+  C.map = P.tau;
+  C.finish(4u);
+  const int k = idx[i];
+  const float* nrow = noise + static_cast<size_t>(k) * 2 * T;
+  float* rrow = out + static_cast<size_t>(i) * 3 * (T + 1);
+  SampleState s;
+  s.x = replay[2 * T]; s.y = replay[2 * T + 1]; s.th = replay[2 * T + 2];
+  s.stage_sum = 0.0f; s.act0 = 0.0f; s.act1 = 0.0f;
+  s.ms = make_float2(0.0f, 0.0f);
+  s.tau = lookup_tau<false, kPow2, false>(C, s.x, s.y);
+  sample_step<false, kPow2, true, false, false>(s, C, 0, __ldg(nrow), __ldg(nrow + 1), 0.0f, 0.0f, ucf_s, rrow);
+  for (int t = 1; t < T; ++t)
+    sample_step<false, kPow2, true, kFastAngles, false>(s, C, t, __ldg(nrow + 2 * t), __ldg(nrow + 2 * t + 1), 0.0f, 0.0f,
+                                                        ucf_s, rrow);
+  rrow[3 * T + 0] = s.x;
+  rrow[3 * T + 1] = s.y;
+  rrow[3 * T + 2] = s.th;
+}
+
 // --------------------------------------------------------------------------------------------- top-n
 // MPPI.get_top_samples (mppi.py:221-240).  One CTA: 4-pass byte-wise radix select of the n-th largest
 // weight (weights are >= 0, so their bit patterns order like unsigned integers), compaction of the n
@@ -1752,6 +1813,17 @@ __global__ void gather_rows_kernel(const float* __restrict__ rec, const int* __r
 }
 
 // --------------------------------------------------------------------------------------------- debug
+// L2 flush for measurements: writes `n16` 16-byte words.  Launched with the same dynamic shared-memory size as the
+// rollout kernel, so that it can be used to test whether the shared-memory carve-out switch between a flush kernel
+// and the rollout kernel is part of the event-timed launch floor (scripts/launch_floor.py).
+__global__ void __launch_bounds__(256) flush_debug_kernel(uint4* __restrict__ buf, size_t n16, unsigned int v) {
+  extern __shared__ __align__(16) unsigned char flush_smem[];
+  if (threadIdx.x == 0 && v == 0xFFFFFFFFu) flush_smem[0] = 1;  // keep the allocation alive
+  const uint4 w = make_uint4(v, v, v, v);
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n16; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    buf[i] = w;
+}
+
 // in [n][6] = (counter x, y, z, w, key lo, key hi) -> out [n][4]: the raw Philox4x32-10 block (known-answer tests)
 __global__ void philox_debug_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;

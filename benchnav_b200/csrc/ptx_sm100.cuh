@@ -90,11 +90,6 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-// Bring the line holding `p` into L2 (no register result, nothing to wait for).
-__device__ __forceinline__ void prefetch_l2(const void* p) {
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(p) : "memory");
-}
-
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }

@@ -346,7 +346,8 @@ class MPPI(nn.Module):
         return u_opt, opt_states
 
     def get_top_samples(self, num_samples: int) -> Tuple[torch.Tensor, torch.Tensor]:
-        """Top ``num_samples`` rollouts by weight, descending (mppi.py:221-240)."""
+        """Top ``num_samples`` rollouts by weight, descending (mppi.py:221-240).  A solver built with
+        ``record_states=False`` keeps no state array: the selected samples are rolled out again (bit-identical rows)."""
         assert num_samples <= self._num_samples
         n_local = min(int(num_samples), self._local_samples)
         states = torch.empty(n_local, self._horizon + 1, 3, device=self._device, dtype=torch.float32)

@@ -164,7 +164,10 @@ int bnv_mppi_mailbox_handle(bnv_mppi* h, unsigned char out[64]);
 int bnv_mppi_attach_peers(bnv_mppi* h, const unsigned char* handles /* [world_size][64] */);
 
 /* MPPI.get_top_samples (mppi.py:221-240): the n highest-weight samples of this shard in descending
- * weight order.  states_out_dev [n,T+1,3], weights_out_dev [n]. Needs BNV_FLAG_RECORD_STATES. */
+ * weight order.  states_out_dev [n,T+1,3], weights_out_dev [n].  With BNV_FLAG_RECORD_STATES the rows are gathered from
+ * the recorded states; without it (a lean solver) the n selected samples are rolled out again from the iteration's
+ * saved start state, mean sequence and noise rows -- bit-identical rows (if the last forward injected its noise, that
+ * array must still be alive). */
 int bnv_mppi_top_samples(bnv_mppi* h, int32_t n, float* states_out_dev, float* weights_out_dev, void* stream);
 /* (batch mode: the n best samples of every environment, states_out_dev [E,n,T+1,3], weights_out_dev [E,n]) */
 
@@ -265,6 +268,9 @@ int bnv_mppi_kernel_time(bnv_mppi* h, double* total_ms, uint64_t* launches);
 /* Debug hook: clock64() stamps taken by the last CTA of the most recent rollout kernel (phase boundaries;
  * see mppi_kernels.cuh BNV_STAMP).  Only recorded when the handle was created with BNV_DEBUG_TS set. */
 int bnv_debug_timestamps(bnv_mppi* h, long long out[24]);
+/* Measurement aid: an L2-flushing fill of buf_dev[0, bytes) launched with `smem_bytes` of dynamic shared memory (to
+ * test whether the shared-memory carve-out switch between kernels is part of the event-timed launch floor). */
+int bnv_debug_flush(void* buf_dev, uint64_t bytes, uint32_t smem_bytes, uint32_t value, void* stream);
 
 /* Test hook: the raw Philox4x32-10 block function behind the engine's noise stream, for known-answer tests
  * (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3", SC'11; Random123 kat_vectors).
