@@ -1021,9 +1021,16 @@ int bnv_mppi_top_samples(bnv_mppi* h, int32_t n, float* states_out_dev, float* w
   }
   BNV_CUDA(cudaFuncSetAttribute(bnv::topn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 bnv::kTopnSmemPairs * 8));
+  const bool fused_gather = h->P.record && n <= bnv::kTopnFusedGatherMax;
   bnv::topn_select_kernel<<<h->E, bnv::kTopnThreads, smem, s>>>(h->weights, h->Kl, n, n_pad, pairs_global,
-                                                                 weights_out_dev, h->top_idx);
+                                                                 weights_out_dev, h->top_idx,
+                                                                 fused_gather ? h->rec : nullptr, 3 * (h->P.T + 1),
+                                                                 states_out_dev);
   BNV_CUDA(cudaGetLastError());
+  if (fused_gather) {
+    h->launches += 1;
+    return BNV_OK;
+  }
   if (h->P.record) {
     bnv::gather_rows_kernel<<<dim3(n, h->E), 128, 0, s>>>(h->rec, h->top_idx, 3 * (h->P.T + 1), h->Kl, states_out_dev);
   } else {

@@ -1724,9 +1724,14 @@ __global__ void __launch_bounds__(128) reroll_kernel(const __grid_constant__ Eng
 constexpr int kTopnThreads = 1024;
 constexpr int kTopnSmemPairs = 16384;
 
+// `rec` != nullptr (small n): the CTA also gathers the selected rows (rec [K][row_len] -> states_out [n][row_len]),
+// which saves the separate gather launch; large n leave the gather to gather_rows_kernel (one CTA per row).
+constexpr int kTopnFusedGatherMax = 128;
 __global__ void __launch_bounds__(kTopnThreads) topn_select_kernel(const float* __restrict__ weights, int K, int n,
                                                                    int n_pad, unsigned long long* pairs_global,
-                                                                   float* __restrict__ out_w, int* __restrict__ out_idx) {
+                                                                   float* __restrict__ out_w, int* __restrict__ out_idx,
+                                                                   const float* __restrict__ rec, int row_len,
+                                                                   float* __restrict__ states_out) {
   extern __shared__ __align__(128) unsigned char smem[];
   // blockIdx.x = environment (batch mode): each CTA selects within its own [K] weights
   weights += static_cast<size_t>(blockIdx.x) * K;
@@ -1743,14 +1748,38 @@ __global__ void __launch_bounds__(kTopnThreads) topn_select_kernel(const float* 
     n_gt = 0u;
     n_eq = 0u;
   }
+  // The keys are read in tiles of kTile per thread with all of a tile's loads in flight (one L2 round trip per tile
+  // instead of one per element: the element-by-element loop cost 16 dependent round trips per pass, 5 passes); when
+  // the whole array fits one tile (K <= 16384) it is read ONCE and every pass runs from registers.
+  constexpr int kTile = 16;
+  const bool cached = K <= kTile * static_cast<int>(blockDim.x);
+  unsigned int ck[kTile];
+#pragma unroll
+  for (int j = 0; j < kTile; ++j) {
+    const int i = j * static_cast<int>(blockDim.x) + tid;
+    ck[j] = (cached && i < K) ? __float_as_uint(weights[i]) : 0u;
+  }
+  const int lane = tid & 31;
   unsigned int mask = 0u;
   for (int shift = 24; shift >= 0; shift -= 8) {
     for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0u;
     __syncthreads();
     const unsigned int prefix = sel_prefix;
-    for (int i = tid; i < K; i += blockDim.x) {
-      unsigned int key = __float_as_uint(weights[i]);
-      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 0xFFu], 1u);
+    // (plain shared-memory atomics: grouping a warp's lanes by bucket first -- match.any, or a leader loop over
+    // ballots -- was measured slower, 65-69 vs 44 us per call at K = 16384: the weights of a real iteration spread over
+    // dozens of exponent buckets, so there is little same-address serialisation to remove)
+    for (int base = 0; base < K; base += kTile * static_cast<int>(blockDim.x)) {
+      unsigned int key[kTile];
+#pragma unroll
+      for (int j = 0; j < kTile; ++j) {
+        const int i = base + j * static_cast<int>(blockDim.x) + tid;
+        key[j] = cached ? ck[j] : (i < K ? __float_as_uint(weights[i]) : 0u);
+      }
+#pragma unroll
+      for (int j = 0; j < kTile; ++j) {
+        const int i = base + j * static_cast<int>(blockDim.x) + tid;
+        if (i < K && (key[j] & mask) == prefix) atomicAdd(&hist[(key[j] >> shift) & 0xFFu], 1u);
+      }
     }
     __syncthreads();
     if (tid == 0) {
@@ -1768,15 +1797,32 @@ __global__ void __launch_bounds__(kTopnThreads) topn_select_kernel(const float* 
   }
   const unsigned int thr_key = sel_prefix, take_eq = sel_remaining;
   const unsigned int first_eq = static_cast<unsigned int>(n) - take_eq;
-  for (int i = tid; i < K; i += blockDim.x) {
-    unsigned int key = __float_as_uint(weights[i]);
-    unsigned long long packed = (static_cast<unsigned long long>(key) << 32) | static_cast<unsigned int>(~i);
-    if (key > thr_key) {
-      unsigned int slot = atomicAdd(&n_gt, 1u);
-      pairs[slot] = packed;
-    } else if (key == thr_key) {
-      unsigned int slot = atomicAdd(&n_eq, 1u);
-      if (slot < take_eq) pairs[first_eq + slot] = packed;
+  for (int base = 0; base < K; base += kTile * static_cast<int>(blockDim.x)) {  // compaction: one atomic per warp and class
+    unsigned int key[kTile];
+#pragma unroll
+    for (int j = 0; j < kTile; ++j) {
+      const int i = base + j * static_cast<int>(blockDim.x) + tid;
+      key[j] = cached ? ck[j] : (i < K ? __float_as_uint(weights[i]) : 0u);
+    }
+#pragma unroll
+    for (int j = 0; j < kTile; ++j) {
+      const int i = base + j * static_cast<int>(blockDim.x) + tid;
+      const unsigned long long packed = (static_cast<unsigned long long>(key[j]) << 32) | static_cast<unsigned int>(~i);
+      const bool gt = i < K && key[j] > thr_key, eq = i < K && key[j] == thr_key;
+      const unsigned int m_gt = __ballot_sync(0xffffffffu, gt), m_eq = __ballot_sync(0xffffffffu, eq);
+      const unsigned int lane_lt = (1u << lane) - 1u;
+      unsigned int base_gt = 0u, base_eq = 0u;
+      if (lane == 0) {
+        if (m_gt) base_gt = atomicAdd(&n_gt, static_cast<unsigned int>(__popc(m_gt)));
+        if (m_eq) base_eq = atomicAdd(&n_eq, static_cast<unsigned int>(__popc(m_eq)));
+      }
+      base_gt = __shfl_sync(0xffffffffu, base_gt, 0);
+      base_eq = __shfl_sync(0xffffffffu, base_eq, 0);
+      if (gt) pairs[base_gt + __popc(m_gt & lane_lt)] = packed;
+      if (eq) {
+        const unsigned int slot = base_eq + __popc(m_eq & lane_lt);
+        if (slot < take_eq) pairs[first_eq + slot] = packed;
+      }
     }
   }
   for (int i = n + tid; i < n_pad; i += blockDim.x) pairs[i] = 0ull;  // pads sort last
@@ -1800,6 +1846,17 @@ __global__ void __launch_bounds__(kTopnThreads) topn_select_kernel(const float* 
     unsigned long long p = pairs[i];
     out_w[i] = __uint_as_float(static_cast<unsigned int>(p >> 32));
     out_idx[i] = static_cast<int>(~static_cast<unsigned int>(p & 0xFFFFFFFFull));
+  }
+  if (rec != nullptr) {  // fused gather: one warp per row, lanes on consecutive words
+    rec += static_cast<size_t>(blockIdx.x) * K * row_len;
+    states_out += static_cast<size_t>(blockIdx.x) * n * row_len;
+    const int warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+    for (int i = warp; i < n; i += nw) {
+      const unsigned int k = ~static_cast<unsigned int>(pairs[i] & 0xFFFFFFFFull);
+      const float* src = rec + static_cast<size_t>(k) * row_len;
+      float* dst = states_out + static_cast<size_t>(i) * row_len;
+      for (int j = lane; j < row_len; j += 32) dst[j] = src[j];
+    }
   }
 }
 
