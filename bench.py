@@ -114,11 +114,17 @@ def hbm_peak():
 
 
 def kernel_source_hash() -> str:
-    """Identity of the rollout kernel's source: the ncu traffic figure is only quoted for the kernel it was taken on."""
+    """Identity of the rollout kernel's source (comments and white space ignored): the ncu traffic figure is only quoted
+    for the kernel it was taken on."""
+    import re
+
     h = hashlib.sha256()
     for name in ("mppi_kernels.cuh", "mppi_math.cuh", "ptx_sm100.cuh"):
-        with open(os.path.join(ROOT, "benchnav_b200", "csrc", name), "rb") as f:
-            h.update(f.read())
+        with open(os.path.join(ROOT, "benchnav_b200", "csrc", name), "r", encoding="utf-8") as f:
+            text = f.read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)   # block comments
+        text = re.sub(r"//[^\n]*", "", text)                 # line comments
+        h.update(re.sub(r"\s+", "", text).encode())
     return h.hexdigest()[:16]
 
 

@@ -2,19 +2,26 @@
 //
 //   trav_map_kernel     risk map -> tau = 1 - clamp(risk,0,1), padded pitch            (traversability_model.py:71-72)
 //   rollout_kernel      noise draw (Philox, interleaved with the rollout), clamp, T-step unicycle rollout, costs,
-//                       per-CTA softmax partial; last CTA: grid merge, weights, optimal rollout (mppi.py:149-217)
+//                       per-CTA softmax partial; last CTA: grid merge, (sharded: exchange over NVLink), weights,
+//                       optimal rollout (mppi.py:149-217).  Two variants (template flag kWide, see below).
+//   normalize_weights_kernel  softmax weights of a launch whose grid was not co-resident
 //   noise_kernel        the same Philox stream as a stand-alone kernel (tests / bnv_mppi_draw_noise); xi_kernel,
 //                       slip_map_kernel, bump_iteration_kernel: stochastic-mode and graph-capture helpers
-//   finalize_kernel     multi-GPU: merge gathered shard partials, weights, optimal rollout
-//   top-n kernels       radix select + sort + gather                                    (mppi.py:221-240)
+//   finalize_kernel     multi-GPU with a host-side exchange: merge gathered shard partials, weights, optimal rollout
+//   top-n kernels       radix select + sort + gather (mppi.py:221-240); reroll_kernel for solvers without recorded states
 //
-// Work decomposition of rollout_kernel: one thread = one sample, state and running cost in registers;
-// one warp = 32 consecutive samples with its own slabs in shared memory -- noise (bulk-loaded from HBM when
-// injected, or produced in the loop and bulk-stored) and recorded states (bulk-stored; the clamped controls are
-// rebuilt from the noise when the weighted sum needs them) -- so warps never synchronise inside the T-loop; one CTA = up to 4 warps (one per SM sub-partition) sharing the
-// traversability window staged by one 2-D TMA load.  At K = 16384 there is at most one warp per scheduler: the
-// kernel is bound by the per-step dependency chain, not by bandwidth, so the loop body is branch-free, keeps
-// every invariant in registers, and fills the chain's stall slots with the next step pair's Philox draw.
+// Work decomposition of rollout_kernel: one thread = one sample, state and running cost in registers; one warp = 32
+// consecutive samples; warps never synchronise inside the T-loop; one CTA shares the traversability window staged by
+// one 2-D TMA load.
+//   Latency variant (kWide = false; every grid that fits the device in one co-resident wave, e.g. K = 16384): 4 warps
+//   per CTA, one per SM sub-partition, each with whole-horizon slabs in shared memory -- noise (bulk-loaded from HBM when
+//   injected, or produced in the loop and bulk-stored) and recorded states (bulk-stored).  At most one warp per
+//   scheduler: the kernel is bound by the per-step dependency chain, so the loop body is branch-free, keeps every
+//   invariant in registers, and fills the chain's stall slots with the next step pair's Philox draw.
+//   Wide variant (kWide = true; single solvers that need several waves, e.g. K = 131072): 8 warps per CTA, two CTAs per
+//   SM, <= 128 registers; recorded states and noise are staged in 16-step chunks and flushed with coalesced stores, the
+//   weighted control sum re-reads the noise from L2, partials merge in two levels and the weights are normalised by
+//   normalize_weights_kernel.  Bound by instruction issue, not by HBM.
 //
 // Two optional modes (template flags, separate instantiations so the single-solver path pays nothing):
 //   kBatch  blockIdx.y = environment: E independent MPPI problems (own map, state, goal, mean sequence) in ONE
