@@ -85,6 +85,7 @@ _SIGNATURES = {
     "bnv_mppi_partial_len": (C.c_int32, [_VP]),
     "bnv_mppi_finalize": (C.c_int, [_VP, _VP, _VP, _VP, _VP]),
     "bnv_mppi_top_samples": (C.c_int, [_VP, C.c_int32, _VP, _VP, _VP]),
+    "bnv_mppi_merge_top": (C.c_int, [_VP, _VP, C.c_int32, C.c_int32, C.c_int32, _VP, _VP, _VP]),
     "bnv_mppi_weights": (_VP, [_VP]),
     "bnv_mppi_costs": (_VP, [_VP]),
     "bnv_mppi_states": (_VP, [_VP]),

@@ -114,6 +114,8 @@ struct bnv_mppi {
   float** peer_mbox_dev = nullptr;    // device array of the same pointers
   bool peers_attached = false;
   unsigned int xchg_seq = 0;
+  float* merge_w = nullptr;  // dense copy of the candidate weights of bnv_mppi_merge_top
+  size_t merge_w_cap = 0;
   int* top_idx = nullptr;
   unsigned long long* top_pairs = nullptr;
   size_t top_pairs_cap = 0, top_idx_cap = 0;
@@ -174,6 +176,7 @@ void free_all(bnv_mppi* h) {
   cudaFree(h->peer_mbox_dev);
   cudaFree(h->mbox);
   cudaFree(h->top_idx);
+  cudaFree(h->merge_w);
   cudaFree(h->top_pairs);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   if (h->io_host) cudaFreeHost(h->io_host);
@@ -1045,6 +1048,60 @@ int bnv_mppi_top_samples(bnv_mppi* h, int32_t n, float* states_out_dev, float* w
     if (smem_r > 48 * 1024) BNV_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_r)));
     fn<<<(n + 127) / 128, 128, smem_r, s>>>(P, h->last_noise, h->replay, h->top_idx, n, states_out_dev);
   }
+  BNV_CUDA(cudaGetLastError());
+  h->launches += 2;
+  return BNV_OK;
+}
+
+int bnv_mppi_merge_top(bnv_mppi* h, const float* cand_dev, int32_t num_candidates, int32_t row_stride, int32_t n,
+                       float* states_out_dev, float* weights_out_dev, void* stream) {
+  if (!h || !cand_dev || !states_out_dev || !weights_out_dev) return fail(BNV_ERR_INVALID, "null argument");
+  const int row_len = 3 * (h->P.T + 1);
+  if (row_stride < row_len + 1) return fail(BNV_ERR_INVALID, "row_stride %d too small for a weight and %d state words", row_stride, row_len);
+  if (n < 1 || n > num_candidates) return fail(BNV_ERR_INVALID, "n %d outside [1, %d]", n, num_candidates);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  BNV_CUDA(cudaSetDevice(h->cfg.device));
+  BNV_DRAIN(h);
+  BNV_USER_WORK(h, stream);
+  // candidate weights gathered into a dense scratch (the selection kernel reads a contiguous array), then the same
+  // radix select + sort as get_top_samples, then a row gather out of the candidate table
+  const size_t need = static_cast<size_t>(num_candidates);
+  if (h->merge_w_cap < need) {
+    BNV_CUDA(cudaStreamSynchronize(s));
+    if (h->merge_w) BNV_CUDA(cudaFree(h->merge_w));
+    h->merge_w = nullptr;
+    BNV_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->merge_w), sizeof(float) * need));
+    h->merge_w_cap = need;
+  }
+  if (h->top_idx_cap < static_cast<size_t>(n)) {
+    BNV_CUDA(cudaStreamSynchronize(s));
+    if (h->top_idx) BNV_CUDA(cudaFree(h->top_idx));
+    h->top_idx = nullptr;
+    BNV_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->top_idx), sizeof(int) * n));
+    h->top_idx_cap = n;
+  }
+  BNV_CUDA(cudaMemcpy2DAsync(h->merge_w, sizeof(float), cand_dev, sizeof(float) * row_stride, sizeof(float), num_candidates,
+                             cudaMemcpyDeviceToDevice, s));
+  int n_pad = 1;
+  while (n_pad < n) n_pad <<= 1;
+  unsigned long long* pairs_global = nullptr;
+  size_t smem = static_cast<size_t>(n_pad) * 8;
+  if (n_pad > bnv::kTopnSmemPairs) {
+    if (h->top_pairs_cap < static_cast<size_t>(n_pad)) {
+      BNV_CUDA(cudaStreamSynchronize(s));
+      if (h->top_pairs) BNV_CUDA(cudaFree(h->top_pairs));
+      h->top_pairs = nullptr;
+      BNV_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->top_pairs), sizeof(unsigned long long) * n_pad));
+      h->top_pairs_cap = n_pad;
+    }
+    pairs_global = h->top_pairs;
+    smem = 0;
+  }
+  BNV_CUDA(cudaFuncSetAttribute(bnv::topn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bnv::kTopnSmemPairs * 8));
+  bnv::topn_select_kernel<<<1, bnv::kTopnThreads, smem, s>>>(h->merge_w, num_candidates, n, n_pad, pairs_global,
+                                                             weights_out_dev, h->top_idx, nullptr, 0, nullptr);
+  BNV_CUDA(cudaGetLastError());
+  bnv::gather_strided_rows_kernel<<<n, 128, 0, s>>>(cand_dev + 1, h->top_idx, row_len, row_stride, states_out_dev);
   BNV_CUDA(cudaGetLastError());
   h->launches += 2;
   return BNV_OK;

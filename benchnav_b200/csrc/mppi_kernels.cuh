@@ -1876,6 +1876,15 @@ __global__ void gather_rows_kernel(const float* __restrict__ rec, const int* __r
   for (int i = threadIdx.x; i < row_len; i += blockDim.x) dst[i] = src[i];
 }
 
+// out[i][:] = table[idx[i]][:row_len], table rows `row_stride` floats apart (bnv_mppi_merge_top: candidate rows are
+// {weight, states...}).
+__global__ void gather_strided_rows_kernel(const float* __restrict__ table, const int* __restrict__ idx, int row_len,
+                                           int row_stride, float* __restrict__ out) {
+  const float* src = table + static_cast<size_t>(idx[blockIdx.x]) * row_stride;
+  float* dst = out + static_cast<size_t>(blockIdx.x) * row_len;
+  for (int i = threadIdx.x; i < row_len; i += blockDim.x) dst[i] = src[i];
+}
+
 // --------------------------------------------------------------------------------------------- debug
 // L2 flush for measurements: writes `n16` 16-byte words.  Launched with the same dynamic shared-memory size as the
 // rollout kernel, so that it can be used to test whether the shared-memory carve-out switch between a flush kernel

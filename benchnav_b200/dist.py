@@ -79,10 +79,33 @@ def attach_peer_mailboxes(lib, handle, shard: ShardInfo) -> bool:
     return True
 
 
-def merge_top_candidates(states: torch.Tensor, weights: torch.Tensor, n: int, shard: ShardInfo
-                         ) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Global top-n from per-shard top lists (each already sorted descending); off the critical path."""
+def merge_top_candidates(states: torch.Tensor, weights: torch.Tensor, n: int, shard: ShardInfo, lib=None, handle=None,
+                         stream: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Global top-n from per-shard top lists (each already sorted descending); off the critical path.
+
+    On CUDA tensors with the engine at hand (``lib``, ``handle``) and equally long lists on every rank: ONE all-gather
+    of the packed candidate rows {weight, states} and the engine's own selection + gather (``bnv_mppi_merge_top``).
+    Otherwise (gloo / CPU tests, ragged lists): plain torch ops."""
     w = shard.world_size
+    if lib is not None and handle is not None and weights.is_cuda:
+        from . import _cabi
+
+        n_local = torch.tensor([weights.shape[0]], device=weights.device, dtype=torch.int64)
+        lo, hi = n_local.clone(), n_local.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=shard.group)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=shard.group)
+        if int(lo.item()) == int(hi.item()) and w * int(lo.item()) >= n:
+            m, row_len = int(lo.item()), int(states[0].numel())
+            packed = torch.empty(m, 1 + row_len, device=weights.device, dtype=torch.float32)
+            packed[:, 0] = weights
+            packed[:, 1:] = states.reshape(m, row_len)
+            table = torch.empty(w * m, 1 + row_len, device=weights.device, dtype=torch.float32)
+            dist.all_gather_into_tensor(table, packed, group=shard.group)
+            out_s = torch.empty((n,) + tuple(states.shape[1:]), device=weights.device, dtype=torch.float32)
+            out_w = torch.empty(n, device=weights.device, dtype=torch.float32)
+            _cabi.check(lib.bnv_mppi_merge_top(handle, table.data_ptr(), w * m, 1 + row_len, n, out_s.data_ptr(),
+                                               out_w.data_ptr(), stream))
+            return out_s, out_w
     n_local = torch.tensor([weights.shape[0]], device=weights.device, dtype=torch.int64)
     sizes = [torch.zeros_like(n_local) for _ in range(w)]
     dist.all_gather(sizes, n_local, group=shard.group)

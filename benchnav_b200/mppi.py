@@ -356,7 +356,9 @@ class MPPI(nn.Module):
             _cabi.check(self._lib.bnv_mppi_top_samples(self._handle, n_local, states.data_ptr(), weights.data_ptr(),
                                                        self._stream()))
         if self._shard.world_size > 1:
-            return merge_top_candidates(states, weights, int(num_samples), self._shard)
+            with torch.cuda.device(self._device):
+                return merge_top_candidates(states, weights, int(num_samples), self._shard, self._lib, self._handle,
+                                            self._stream())
         return states, weights
 
     # ------------------------------------------------------------------ extras

@@ -171,6 +171,13 @@ int bnv_mppi_attach_peers(bnv_mppi* h, const unsigned char* handles /* [world_si
 int bnv_mppi_top_samples(bnv_mppi* h, int32_t n, float* states_out_dev, float* weights_out_dev, void* stream);
 /* (batch mode: the n best samples of every environment, states_out_dev [E,n,T+1,3], weights_out_dev [E,n]) */
 
+/* Sharded solver: global top-n out of the ranks' local top lists.  cand_dev [num_candidates][row_stride] holds one
+ * candidate per row, {weight, states [T+1,3] ...} (row_stride >= 1 + 3 (T+1); the caller gathers the ranks' lists into
+ * it with whatever transport it uses -- one all-gather).  Selects the n largest weights with the same radix select +
+ * sort as bnv_mppi_top_samples and gathers their rows: states_out_dev [n,T+1,3], weights_out_dev [n], descending. */
+int bnv_mppi_merge_top(bnv_mppi* h, const float* cand_dev, int32_t num_candidates, int32_t row_stride, int32_t n,
+                       float* states_out_dev, float* weights_out_dev, void* stream);
+
 /* Module state the reference exposes as attributes (device pointers owned by the handle, shard-local):
  *   weights  [Kl]        `_weights`            (mppi.py:193)
  *   costs    [Kl]        per-sample cost        (mppi.py:186-190; not stored by the reference)

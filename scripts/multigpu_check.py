@@ -62,6 +62,13 @@ def main() -> None:
             ts, tw = sharded.get_top_samples(100)
             t1, w1 = single.get_top_samples(100)
             np.testing.assert_allclose(tw.cpu().numpy(), w1.cpu().numpy(), rtol=2e-2, atol=1e-7)
+            # the merged rows are the unsharded solver's rows (compared where the weights are clearly separated)
+            w_np = w1.cpu().numpy()
+            sep = np.ones(100, dtype=bool)
+            sep[1:] &= w_np[1:] < 0.98 * w_np[:-1]
+            sep[:-1] &= w_np[1:] < 0.98 * w_np[:-1]
+            if sep.any():
+                assert float((ts.cpu()[torch.from_numpy(sep)] - t1.cpu()[torch.from_numpy(sep)]).abs().max()) <= 1e-4
             if rank == 0:
                 print(f"{exchange} it{it}: |du*|={du:.2e} |dopt|={do:.2e} |dw|max={dw:.2e} sum(w)={float(wsum):.7f} "
                       f"shard {a}+{n} of {K}", flush=True)
