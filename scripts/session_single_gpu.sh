@@ -1,5 +1,5 @@
 #!/bin/bash
-# Round-2 final single-GPU session: parity suite (default kernel selection, then every eligible solver forced onto the
+# Single-GPU session: parity suite (default kernel selection, then every eligible solver forced onto the
 # wide variant), bench lines of every configuration, driver-style short run, reference arm, phase stamps, lean mode,
 # closed loop.
 mkdir -p gpurun_out
