@@ -20,7 +20,7 @@ BNV_OK = 0
 BNV_FLAG_RECORD_STATES = 0x1
 BNV_FLAG_STOCHASTIC_SLIP = 0x2
 BNV_RISK_CLOSED_FORM, BNV_RISK_MONTE_CARLO = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class BnvError(RuntimeError):
@@ -78,6 +78,8 @@ _SIGNATURES = {
     "bnv_mppi_forward_ex": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "bnv_mppi_forward_state": (C.c_int, [_VP, C.POINTER(C.c_float), _VP, _VP, _VP, _VP]),
     "bnv_mppi_forward_host": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP]),
+    "bnv_mppi_forward_host_action": (C.c_int, [_VP, _VP, _VP, _VP]),
+    "bnv_mppi_wait_states": (C.c_int, [_VP, _VP]),
     "bnv_mppi_forward_follow": (C.c_int, [_VP, _VP, _VP, _VP, _VP]),
     "bnv_mppi_mailbox_handle": (C.c_int, [_VP, C.POINTER(C.c_ubyte)]),
     "bnv_mppi_attach_peers": (C.c_int, [_VP, C.POINTER(C.c_ubyte)]),

@@ -119,6 +119,8 @@ struct bnv_mppi {
   int* top_idx = nullptr;
   unsigned long long* top_pairs = nullptr;
   size_t top_pairs_cap = 0, top_idx_cap = 0;
+  unsigned int states_epoch = 0;       // launch whose optimal state sequence bnv_mppi_wait_states collects
+  cudaStream_t states_stream = nullptr;
   float* io_host = nullptr;  // pinned mirror of io_dev
   float* io_host_dev = nullptr;  // its device-side address (zero-copy)
   unsigned long long* iter_dev = nullptr;  // device-resident iteration counter (graph-capturable launches)
@@ -780,9 +782,10 @@ int bnv_mppi_forward_state(bnv_mppi* h, const float state_host[3], const float* 
 
 // Spin on the completion word of launch `epoch` (and, for a pre-launched one, on its abort word).  Returns 1 when the
 // results are in the staging buffer, 0 when the launch aborted, negative on error.
-static int wait_host_results(bnv_mppi* h, cudaStream_t s, unsigned int epoch, bool may_abort, unsigned int seq = 0) {
+static int wait_host_results(bnv_mppi* h, cudaStream_t s, unsigned int epoch, bool may_abort, unsigned int seq = 0,
+                             int stage = 0) {  // stage 1: only u* is awaited (the word raised by signal_action)
   const int T = h->P.T;
-  const size_t flag_off = 3 + 2 * static_cast<size_t>(T) + 3 * static_cast<size_t>(T + 1);
+  const size_t flag_off = 3 + 2 * static_cast<size_t>(T) + 3 * static_cast<size_t>(T + 1) + (stage ? 1 : 0);
   volatile unsigned int* flag = reinterpret_cast<volatile unsigned int*>(h->io_host + flag_off);
   volatile unsigned int* aborted = h->pre_host ? h->pre_host + 8 + (seq & 1u) : nullptr;  // the awaited launch's own word
   bool seen = false;
@@ -871,7 +874,7 @@ static int forward_host_prelaunched(bnv_mppi* h, const float state_host[3], floa
   h->pre_epoch = h->epoch;
   h->pre_pending = true;
   const double t_d = now_us();
-  const int got = wait_host_results(h, ps, cur_epoch, posted, cur_seq);
+  const int got = wait_host_results(h, ps, cur_epoch, posted, cur_seq, opt_states_host ? 0 : 1);
   const double t_e = now_us();
   g_pre_stats.t_sync += t_b - t_a;
   g_pre_stats.t_post += t_c - t_b;
@@ -888,13 +891,40 @@ static int forward_host_prelaunched(bnv_mppi* h, const float state_host[3], floa
     return forward_host_prelaunched(h, state_host, u_out_host, opt_states_host, depth + 1);
   }
   std::memcpy(u_out_host, h->io_host + 3, 2 * static_cast<size_t>(T) * sizeof(float));
+  h->states_epoch = cur_epoch;
+  h->states_stream = ps;
+  if (opt_states_host) std::memcpy(opt_states_host, h->io_host + 3 + 2 * T, 3 * static_cast<size_t>(T + 1) * sizeof(float));
+  return BNV_OK;
+}
+
+static int forward_host_impl(bnv_mppi* h, const float state_host[3], const float* noise_dev, float* u_out_host,
+                             float* opt_states_host, void* stream);
+
+int bnv_mppi_forward_host(bnv_mppi* h, const float state_host[3], const float* noise_dev, float* u_out_host,
+                          float* opt_states_host, void* stream) {
+  if (!opt_states_host) return fail(BNV_ERR_INVALID, "null argument");
+  return forward_host_impl(h, state_host, noise_dev, u_out_host, opt_states_host, stream);
+}
+
+int bnv_mppi_forward_host_action(bnv_mppi* h, const float state_host[3], float* u_out_host, void* stream) {
+  return forward_host_impl(h, state_host, nullptr, u_out_host, nullptr, stream);
+}
+
+int bnv_mppi_wait_states(bnv_mppi* h, float* opt_states_host) {
+  if (!h || !opt_states_host) return fail(BNV_ERR_INVALID, "null argument");
+  if (h->states_epoch == 0u) return fail(BNV_ERR_STATE, "wait_states needs a preceding forward_host / forward_host_action");
+  BNV_CUDA(cudaSetDevice(h->cfg.device));
+  const int got = wait_host_results(h, h->states_stream, h->states_epoch, false, 0u, 0);
+  if (got < 0) return got;
+  const int T = h->P.T;
   std::memcpy(opt_states_host, h->io_host + 3 + 2 * T, 3 * static_cast<size_t>(T + 1) * sizeof(float));
   return BNV_OK;
 }
 
-int bnv_mppi_forward_host(bnv_mppi* h, const float state_host[3], const float* noise_dev, float* u_out_host,
-                          float* opt_states_host, void* stream) {
-  if (!h || !state_host || !u_out_host || !opt_states_host) return fail(BNV_ERR_INVALID, "null argument");
+// opt_states_host == nullptr: return as soon as u* is in host memory (bnv_mppi_forward_host_action)
+static int forward_host_impl(bnv_mppi* h, const float state_host[3], const float* noise_dev, float* u_out_host,
+                             float* opt_states_host, void* stream) {
+  if (!h || !state_host || !u_out_host) return fail(BNV_ERR_INVALID, "null argument");
   if (!h->problem_set) return fail(BNV_ERR_STATE, "bnv_mppi_set_problem must be called before forward");
   if (h->E != 1) return fail(BNV_ERR_INVALID, "forward_host needs a single environment");
   if (h->cfg.world_size != 1 && !h->peers_attached)
@@ -921,10 +951,12 @@ int bnv_mppi_forward_host(bnv_mppi* h, const float state_host[3], const float* n
   if (rc != BNV_OK) return rc;
   h->user_work = true;
   h->user_stream = s;
-  const int got = wait_host_results(h, s, h->epoch, false);
+  const int got = wait_host_results(h, s, h->epoch, false, 0u, opt_states_host ? 0 : 1);
   if (got < 0) return got;
   std::memcpy(u_out_host, h->io_host + 3, 2 * static_cast<size_t>(T) * sizeof(float));
-  std::memcpy(opt_states_host, h->io_host + 3 + 2 * T, 3 * static_cast<size_t>(T + 1) * sizeof(float));
+  h->states_epoch = h->epoch;
+  h->states_stream = s;
+  if (opt_states_host) std::memcpy(opt_states_host, h->io_host + 3 + 2 * T, 3 * static_cast<size_t>(T + 1) * sizeof(float));
   return BNV_OK;
 }
 

@@ -109,7 +109,8 @@ struct alignas(64) EngineParams {
   const unsigned long long* iter_dev;  // graph-capturable launches: the iteration counter lives in device memory (the
                                        // launch packet of a captured graph is frozen); then iteration = *iter_dev,
                                        // epoch = low word + 1, and bump_iteration_kernel advances it after the launch
-  unsigned int* done_flag;  // optional, mapped HOST memory: set to `epoch` once u_out / opt_rec are complete, so that a
+  unsigned int* done_flag;  // optional, mapped HOST memory: [0] set to `epoch` once u_out / opt_rec are complete, [1] as
+                            // soon as u_out alone is (signal_action), so that a
                             // host thread polling it sees the results without waiting for the kernel's tail
   // pre-launched iterations (bnv_mppi_prelaunch): the kernel is already resident when the state arrives.  It polls a
   // host-mapped slot {x, y, theta, sequence number} and every CTA follows one grid-wide decision (go / abort):
@@ -746,6 +747,16 @@ __device__ __forceinline__ void signal_done(const EngineParams& P) {
   if (P.done_flag != nullptr) {
     __threadfence_system();
     asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(P.done_flag), "r"(P.epoch) : "memory");
+  }
+}
+
+// First stage of the host-visible completion: u* is written (by other threads of this CTA, ordered before this thread by
+// the CTA / named barrier).  Raised by a thread that is NOT on the path to the serial optimal rollout, so a host that
+// only needs the controls (the next environment step) can go on ~3.7 us before the optimal state sequence is done.
+__device__ __forceinline__ void signal_action(const EngineParams& P) {
+  if (P.done_flag != nullptr) {
+    __threadfence_system();
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(P.done_flag + 1), "r"(P.epoch) : "memory");
   }
 }
 
@@ -1561,6 +1572,7 @@ __global__ void __launch_bounds__((kWide ? kWideWarps : kMaxWarps) * 32, kWide ?
     } else {
       __syncthreads();
     }
+    if (complete && tid == nwork - 1) signal_action(P);  // (thread 0 goes straight on to the optimal rollout)
     if (stamp) BNV_STAMP(5);
     if (tid == 0) *ticket_e = 0u;  // re-arm for the next launch (all arrivals of this one have happened)
     if (stamp) BNV_STAMP(6);

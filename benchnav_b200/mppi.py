@@ -164,6 +164,8 @@ class MPPI(nn.Module):
                           if self._shard.world_size > 1 else None)
         self._state_dev = torch.zeros(3, device=dev, dtype=torch.float32)
         self._forward_host_fn = self._lib.bnv_mppi_forward_host
+        self._forward_action_fn = self._lib.bnv_mppi_forward_host_action
+        self._pending_states = None
         self._fused_exchange = False
         if self._shard.world_size > 1 and exchange == "p2p":
             self._fused_exchange = attach_peer_mailboxes(self._lib, self._handle, self._shard)
@@ -331,6 +333,57 @@ class MPPI(nn.Module):
         if rc != 0:
             _cabi.check(rc)
         return u_opt, opt_states
+
+    def forward_action(self, state: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """First half of a two-stage ``forward_host``: returns the optimal action sequence [T,2] (HOST tensor) as soon as
+        the kernel has written it, before the serial optimal rollout (mppi.py:205-213) -- what a control loop needs to step
+        the environment (test/test_mppi.py:183-186).  ``wait_states()`` returns the optimal state sequence of the same
+        iteration; call it before the next ``forward_host`` / ``forward_action`` (the staging buffer is reused), or skip
+        it.  Bit-identical to ``forward_host``'s results."""
+        d = self.__dict__
+        if d["_slow_host_path"]:
+            u_opt, opt_states = self.forward_host(state)
+            d["_pending_states"] = opt_states
+            if out is not None:
+                out.copy_(u_opt)
+                return out
+            return u_opt
+        if out is None:
+            out = torch.empty(self._horizon, 2, dtype=torch.float32)
+        elif out is not d.get("_host_action_ok"):
+            if not (out.dtype == torch.float32 and out.device.type == "cpu" and out.is_contiguous()
+                    and out.shape == (self._horizon, 2)):
+                raise ValueError("out must be a contiguous fp32 CPU tensor of shape [T,2]")
+            d["_host_action_ok"] = out
+        if state is not d.get("_host_state_ok"):
+            if not (torch.is_tensor(state) and state.dtype == torch.float32 and state.device.type == "cpu"
+                    and state.is_contiguous()):
+                state = torch.as_tensor(state, dtype=torch.float32).detach().cpu().contiguous()
+            assert state.shape == (self._dim_state,)
+            d["_host_state_ok"] = state
+        self._sync_problem()
+        if d["_action_noises"] is not d["_engine_noise"]:
+            d["_action_noises"] = d["_engine_noise"]
+        rc = d["_forward_action_fn"](d["_handle"], state.data_ptr(), out.data_ptr(), self._stream())
+        if rc != 0:
+            _cabi.check(rc)
+        d["_pending_states"] = None
+        return out
+
+    def wait_states(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Second half of ``forward_action``: the optimal state sequence [1,T+1,3] (HOST tensor) of that iteration."""
+        d = self.__dict__
+        if out is None:
+            out = torch.empty(1, self._horizon + 1, 3, dtype=torch.float32)
+        elif not (out.dtype == torch.float32 and out.device.type == "cpu" and out.is_contiguous()
+                  and out.shape == (1, self._horizon + 1, 3)):
+            raise ValueError("out must be a contiguous fp32 CPU tensor of shape [1,T+1,3]")
+        pending = d.get("_pending_states")
+        if pending is not None:  # (slow host path: forward_action already has them)
+            out.copy_(pending)
+            return out
+        _cabi.check(self._lib.bnv_mppi_wait_states(self._handle, out.data_ptr()))
+        return out
 
     def forward_follow(self) -> Tuple[torch.Tensor, torch.Tensor]:
         """The other ranks' half of a host-driven sharded iteration: while ONE rank (the leader) calls

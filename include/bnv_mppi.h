@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define BNV_ABI_VERSION 2
+#define BNV_ABI_VERSION 3
 
 typedef enum bnv_status {
   BNV_OK = 0,
@@ -141,6 +141,15 @@ int bnv_mppi_forward_state(bnv_mppi* h, const float state_host[3], const float* 
 int bnv_mppi_forward_host(bnv_mppi* h, const float state_host[3], const float* noise_dev, float* u_out_host,
                           float* opt_states_host, void* stream);
 int bnv_mppi_forward_follow(bnv_mppi* h, const float* noise_dev, float* u_out_dev, float* opt_states_dev, void* stream);
+
+/* Two-stage form of bnv_mppi_forward_host for a control loop that needs the controls first (the reference's loop
+ * steps the environment with u*[0] and only draws the optimal trajectory, test/test_mppi.py:171-198).  The kernel
+ * raises a first completion word when u* is in the staging buffer -- before the serial optimal rollout
+ * (mppi.py:205-213), ~3.7 us at T = 50 -- and _action returns on it; bnv_mppi_wait_states then returns the optimal state
+ * sequence [T+1][3] of that same launch (usually complete by the time it is asked for).  The staging buffer is reused
+ * by the next launch: collect the states BEFORE the next forward_host / forward_host_action call, or not at all. */
+int bnv_mppi_forward_host_action(bnv_mppi* h, const float state_host[3], float* u_out_host, void* stream);
+int bnv_mppi_wait_states(bnv_mppi* h, float* opt_states_host);
 
 /* Sample-sharded softmax (replaces the global torch.softmax of mppi.py:193-199).
  * bnv_mppi_partial: device pointer to this shard's (m, s, U[T,2]) -- m = max_k(-c_k/lambda),

@@ -487,3 +487,36 @@ def test_prelaunched_forward_host_matches_plain_path():
     assert torch.equal(u, u_ref)
     torch.cuda.synchronize()
     assert torch.equal(pre._weights, plain._weights) and torch.equal(pre._state_seq_batch, plain._state_seq_batch)
+
+
+@pytest.mark.parametrize("prelaunched", [False, True])
+def test_two_stage_host_call_matches_forward_host(prelaunched):
+    """forward_action returns on the kernel's FIRST completion word (u* written, optimal rollout still running),
+    wait_states on the second: both halves must equal forward_host bit for bit, with and without pre-launching, and a
+    skipped wait_states must not disturb the following iteration."""
+    from benchnav_b200.synthetic import benchmark_problem
+
+    risk, start, goal, thr = benchmark_problem(64, 0.5, seed=0)
+    K, T = 2048, 24
+    ref = make_solver(risk, 0.5, goal.tolist(), thr, K, T, [0.5, 0.5], 0.5, seed=9)
+    two = make_solver(risk, 0.5, goal.tolist(), thr, K, T, [0.5, 0.5], 0.5, seed=9)
+    if prelaunched:
+        two.prelaunch(True, timeout_us=200000)
+    state = start.clone()
+    u_buf = torch.empty(T, 2)
+    for step in range(10):
+        u_ref, opt_ref = ref.forward_host(state)
+        u = two.forward_action(state, out=u_buf)
+        assert torch.equal(u, u_ref), f"step {step}: controls differ"
+        if step % 3 != 2:  # every third step the states are not collected
+            opt = two.wait_states()
+            assert torch.equal(opt, opt_ref), f"step {step}: optimal states differ"
+        state = opt_ref[0, 1].clone()
+        state[2] = ((state[2] + np.pi) % (2 * np.pi)) - np.pi
+    u_full, opt_full = two.forward_host(state)  # the one-stage call on the same handle still works
+    u_ref, opt_ref = ref.forward_host(state)
+    assert torch.equal(u_full, u_ref) and torch.equal(opt_full, opt_ref)
+    if prelaunched:
+        two.prelaunch(False)
+    torch.cuda.synchronize()
+    assert torch.equal(two._weights, ref._weights)
