@@ -1346,10 +1346,12 @@ int bnv_debug_timestamps(bnv_mppi* h, long long out[24]) {
 
 int bnv_debug_flush(void* buf_dev, uint64_t bytes, uint32_t smem_bytes, uint32_t value, void* stream) {
   if (!buf_dev || bytes < 16) return fail(BNV_ERR_INVALID, "bad argument");
+  const int read_only = (smem_bytes >> 31) & 1u;  // top bit of smem_bytes: read the buffer instead of writing it
+  smem_bytes &= 0x7FFFFFFFu;
   if (smem_bytes > kMaxDynSmem) return fail(BNV_ERR_INVALID, "too much shared memory");
   BNV_CUDA(cudaFuncSetAttribute(bnv::flush_debug_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMaxDynSmem)));
   bnv::flush_debug_kernel<<<148 * 4, 256, smem_bytes, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<uint4*>(buf_dev), bytes / 16, value);
+      static_cast<uint4*>(buf_dev), bytes / 16, value, read_only);
   BNV_CUDA(cudaGetLastError());
   return BNV_OK;
 }

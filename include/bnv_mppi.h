@@ -285,7 +285,8 @@ int bnv_mppi_kernel_time(bnv_mppi* h, double* total_ms, uint64_t* launches);
  * see mppi_kernels.cuh BNV_STAMP).  Only recorded when the handle was created with BNV_DEBUG_TS set. */
 int bnv_debug_timestamps(bnv_mppi* h, long long out[24]);
 /* Measurement aid: an L2-flushing fill of buf_dev[0, bytes) launched with `smem_bytes` of dynamic shared memory (to
- * test whether the shared-memory carve-out switch between kernels is part of the event-timed launch floor). */
+ * test whether the shared-memory carve-out switch between kernels is part of the event-timed launch floor).  Top bit
+ * of smem_bytes set: the buffer is READ instead (L2 left full of clean lines rather than dirty ones). */
 int bnv_debug_flush(void* buf_dev, uint64_t bytes, uint32_t smem_bytes, uint32_t value, void* stream);
 
 /* Test hook: the raw Philox4x32-10 block function behind the engine's noise stream, for known-answer tests

@@ -37,9 +37,24 @@ def run(flush, n=1500):
     return sum(ts) / n * 1e3, ts[n // 2] * 1e3
 
 
+# Does the flush leave L2 full of DIRTY lines whose write-back the iteration's 17 MB of stores then wait for?  The same
+# step behind a flush that only READS 256 MiB (L2 left full of clean lines), and for a solver that records no states.
+def read_flush(v):
+    _cabi.check(lib.bnv_debug_flush(buf.data_ptr(), buf.numel(), 0x80000000, v, stream))
+
+
+lean = MPPI(50, 16384, 3, 2, dyn, GoalObjectives(dyn, goal, thr), torch.tensor([0.5, 0.5]), 0.5, device=torch.device("cuda"),
+            record_states=False)
 for name, fl in (("torch fill_ (default carve-out)", lambda v: buf.fill_(v)),
                  ("library fill, 0 B dynamic smem", lambda v: _cabi.check(lib.bnv_debug_flush(buf.data_ptr(), buf.numel(), 0, v, stream))),
                  ("library fill, 145 KB dynamic smem", lambda v: _cabi.check(lib.bnv_debug_flush(buf.data_ptr(), buf.numel(), 148000, v, stream))),
                  ("no flush (back to back, per-step events)", lambda v: None)):
+    mean, med = run(fl)
+    print(f"{name:45s} mean {mean:6.2f} us  median {med:6.2f} us per forward()")
+mean, med = run(read_flush)
+print(f"{'read-only flush (sum of 256 MiB: clean L2)':45s} mean {mean:6.2f} us  median {med:6.2f} us per forward()")
+full = s
+s = lean
+for name, fl in (("record_states=False, torch fill_", lambda v: buf.fill_(v)), ("record_states=False, read-only flush", read_flush)):
     mean, med = run(fl)
     print(f"{name:45s} mean {mean:6.2f} us  median {med:6.2f} us per forward()")

@@ -500,6 +500,10 @@ def test_two_stage_host_call_matches_forward_host(prelaunched):
     K, T = 2048, 24
     ref = make_solver(risk, 0.5, goal.tolist(), thr, K, T, [0.5, 0.5], 0.5, seed=9)
     two = make_solver(risk, 0.5, goal.tolist(), thr, K, T, [0.5, 0.5], 0.5, seed=9)
+    with pytest.raises(RuntimeError):
+        two.wait_states()  # nothing to wait for yet
+    with pytest.raises(ValueError):
+        two.forward_action(start, out=torch.empty(T, 3))
     if prelaunched:
         two.prelaunch(True, timeout_us=200000)
     state = start.clone()
