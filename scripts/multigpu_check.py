@@ -86,6 +86,18 @@ def main() -> None:
             assert float((u_h - u_1).abs().max()) <= 5e-6 and float((o_h - o_1).abs().max()) <= 5e-5
             if rank == 0:
                 print(f"{exchange} K={K}: host-driven iteration ok |du*|={float((u_h - u_1).abs().max()):.2e}", flush=True)
+            # the same in two stages: the leader returns on the first completion word (u* written), then collects the states
+            sharded._previous_action_seq.copy_(single._previous_action_seq)
+            if rank == 0:
+                u_h = sharded.forward_action(start).to(dev)
+                o_h = sharded.wait_states().to(dev)
+            else:
+                u_h, o_h = sharded.forward_follow()
+            u_1, o_1 = single.forward(st)
+            torch.cuda.synchronize()
+            assert float((u_h - u_1).abs().max()) <= 5e-6 and float((o_h - o_1).abs().max()) <= 5e-5
+            if rank == 0:
+                print(f"{exchange} K={K}: host-driven two-stage iteration ok |du*|={float((u_h - u_1).abs().max()):.2e}", flush=True)
         sharded.check()  # no in-kernel wait timed out
         if rank == 0:
             print(f"{exchange} K={K}: launch {sharded.launch_geometry}", flush=True)
