@@ -402,22 +402,17 @@ def make_native(w: dict, dev, group, exchange: str, world: int, rank: int):
         e_l = hi - lo
         st_dev = torch.stack(states).to(dev)
         st_pin = torch.stack(states).pin_memory()
-        st_in = torch.empty_like(st_dev)
         u_pin = torch.empty(e_l, t_h, 2).pin_memory()
         o_pin = torch.empty(e_l, 1, t_h + 1, 3).pin_memory()
-        cur = torch.cuda.current_stream(dev)
 
         def e2e_step():
-            st_in.copy_(st_pin, non_blocking=True)
-            u, o = solver.forward(st_in)
-            u_pin.copy_(u, non_blocking=True)
-            o_pin.copy_(o, non_blocking=True)
-            cur.synchronize()
+            solver.forward_host(st_pin, out=(u_pin, o_pin))
 
         return {"solver": solver, "step": lambda: solver.forward(st_dev), "e2e_step": e2e_step,
                 "h2d": e_l * 12, "d2h": e_l * 4 * (2 * t_h + 3 * (t_h + 1)),
-                "e2e_how": "pinned states [E,3] -> device copy, BatchedMPPI.forward, u* [E,T,2] and optimal states "
-                           "[E,1,T+1,3] copied to pinned host tensors, stream synchronised; wall clock per step",
+                "e2e_how": "BatchedMPPI.forward_host(states [E,3] in host memory, out=caller buffers): one staged H2D copy "
+                           "of the states, the iteration, ONE D2H copy of u* [E,T,2] + optimal states [E,1,T+1,3], one "
+                           "stream synchronisation, all inside the library; wall clock per step",
                 "alg_bytes": e_l * algorithmic_bytes(w["k_total"], t_h, g), "units": e_l, "local_samples": w["k_total"],
                 "parallelism": f"environment-shard x{world}: {e_l} environments per GPU, one launch, no exchange"}
     if w["kind"] == "stoch":

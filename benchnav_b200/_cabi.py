@@ -78,6 +78,7 @@ _SIGNATURES = {
     "bnv_mppi_forward_ex": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "bnv_mppi_forward_state": (C.c_int, [_VP, C.POINTER(C.c_float), _VP, _VP, _VP, _VP]),
     "bnv_mppi_forward_host": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP]),
+    "bnv_mppi_forward_host_batch": (C.c_int, [_VP, _VP, _VP, _VP, _VP]),
     "bnv_mppi_forward_host_action": (C.c_int, [_VP, _VP, _VP, _VP]),
     "bnv_mppi_wait_states": (C.c_int, [_VP, _VP]),
     "bnv_mppi_forward_follow": (C.c_int, [_VP, _VP, _VP, _VP, _VP]),

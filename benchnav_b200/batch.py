@@ -110,6 +110,30 @@ class BatchedMPPI(nn.Module):
         self._keepalive = (states, noise)
         return u_opt, opt_states
 
+    def forward_host(self, states: torch.Tensor, out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
+                     ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """``forward`` for HOST states [E,3], returning HOST tensors ``(u* [E,T,2], optimal states [E,1,T+1,3])``: one
+        staged copy each way and one synchronisation inside the library (``bnv_mppi_forward_host_batch``) instead of
+        tensor copies around ``forward``.  ``out``: optional caller-owned contiguous fp32 CPU tensors."""
+        E, t = self._num_envs, self._horizon
+        if not (torch.is_tensor(states) and states.dtype == torch.float32 and states.device.type == "cpu"
+                and states.is_contiguous()):
+            states = torch.as_tensor(states, dtype=torch.float32).detach().cpu().contiguous()
+        assert tuple(states.shape) == (E, 3)
+        if out is None:
+            u_opt = torch.empty(E, t, 2, dtype=torch.float32)
+            opt_states = torch.empty(E, 1, t + 1, 3, dtype=torch.float32)
+        else:
+            u_opt, opt_states = out
+            if not (u_opt.dtype == torch.float32 and opt_states.dtype == torch.float32 and u_opt.device.type == "cpu"
+                    and opt_states.device.type == "cpu" and u_opt.is_contiguous() and opt_states.is_contiguous()
+                    and tuple(u_opt.shape) == (E, t, 2) and tuple(opt_states.shape) == (E, 1, t + 1, 3)):
+                raise ValueError("out must be contiguous fp32 CPU tensors of shapes [E,T,2] and [E,1,T+1,3]")
+        with torch.cuda.device(self._device):
+            _cabi.check(self._lib.bnv_mppi_forward_host_batch(self._handle, states.data_ptr(), u_opt.data_ptr(),
+                                                              opt_states.data_ptr(), self._stream()))
+        return u_opt, opt_states
+
     def get_top_samples(self, num_samples: int) -> Tuple[torch.Tensor, torch.Tensor]:
         """Top ``num_samples`` rollouts of every environment by weight (mppi.py:221-240 x E): [E,n,T+1,3], [E,n]."""
         assert num_samples <= self._num_samples

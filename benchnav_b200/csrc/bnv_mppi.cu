@@ -380,8 +380,8 @@ int bnv_mppi_create(bnv_mppi** out, const bnv_mppi_cfg* cfg) {
     delete h;
     return fail(BNV_ERR_UNSUPPORTED, "batched / stochastic-slip solvers need dt * max|omega| < 3 rad per step");
   }
-  // [3] state + [2T] u_out + [3(T+1)] opt states + completion word (padded to 4 floats)
-  const size_t io_floats = 3 + 2 * static_cast<size_t>(T) + 3 * static_cast<size_t>(T + 1) + 4;
+  // [E][3] states + [E][2T] u_out + [E][3(T+1)] opt states + completion words (padded to 4 floats)
+  const size_t io_floats = static_cast<size_t>(E) * (3 + 2 * static_cast<size_t>(T) + 3 * static_cast<size_t>(T + 1)) + 4;
   cudaError_t e = cudaSuccess;
   auto alloc = [&](void** p, size_t bytes) {
     if (e == cudaSuccess) e = cudaMalloc(p, bytes);
@@ -957,6 +957,30 @@ static int forward_host_impl(bnv_mppi* h, const float state_host[3], const float
   h->states_epoch = h->epoch;
   h->states_stream = s;
   if (opt_states_host) std::memcpy(opt_states_host, h->io_host + 3 + 2 * T, 3 * static_cast<size_t>(T + 1) * sizeof(float));
+  return BNV_OK;
+}
+
+int bnv_mppi_forward_host_batch(bnv_mppi* h, const float* states_host, float* u_out_host, float* opt_states_host,
+                                void* stream) {
+  if (!h || !states_host || !u_out_host || !opt_states_host) return fail(BNV_ERR_INVALID, "null argument");
+  if (!h->problem_set) return fail(BNV_ERR_STATE, "bnv_mppi_set_problem must be called before forward");
+  if (h->cfg.world_size != 1) return fail(BNV_ERR_INVALID, "forward_host_batch needs an unsharded solver");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  BNV_CUDA(cudaSetDevice(h->cfg.device));
+  BNV_DRAIN(h);
+  BNV_USER_WORK(h, stream);
+  // One staged copy each way: [E][3] states up, [E][2T] + [E][3(T+1)] results down in a single transfer, one
+  // synchronisation.  (The kernels read the states by many CTAs per environment: they belong in HBM, not behind PCIe.)
+  const size_t nE = static_cast<size_t>(h->E), T = static_cast<size_t>(h->P.T);
+  const size_t n_st = 3 * nE, n_u = 2 * T * nE, n_o = 3 * (T + 1) * nE;
+  std::memcpy(h->io_host, states_host, n_st * sizeof(float));
+  BNV_CUDA(cudaMemcpyAsync(h->io_dev, h->io_host, n_st * sizeof(float), cudaMemcpyHostToDevice, s));
+  const int rc = launch_forward(h, h->io_dev, nullptr, nullptr, h->io_dev + n_st, h->io_dev + n_st + n_u, s);
+  if (rc != BNV_OK) return rc;
+  BNV_CUDA(cudaMemcpyAsync(h->io_host + n_st, h->io_dev + n_st, (n_u + n_o) * sizeof(float), cudaMemcpyDeviceToHost, s));
+  BNV_CUDA(cudaStreamSynchronize(s));
+  std::memcpy(u_out_host, h->io_host + n_st, n_u * sizeof(float));
+  std::memcpy(opt_states_host, h->io_host + n_st + n_u, n_o * sizeof(float));
   return BNV_OK;
 }
 

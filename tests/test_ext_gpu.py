@@ -189,6 +189,27 @@ def test_batched_config3_full_size_in_engine_noise():
             np.testing.assert_array_equal(ts[e].cpu().numpy(), want_s.numpy())
 
 
+def test_batched_forward_host_equals_forward():
+    """BatchedMPPI.forward_host (host states in, host results out, one staged copy each way inside the library) against
+    forward() of a twin solver: bit-equal over chained iterations, caller-owned output buffers honoured."""
+    from benchnav_b200 import BatchedMPPI
+
+    E, K, T, g, sig, lam = 6, 1000, 20, 64, [0.5, 0.5], 0.5
+    dyns, objs, risks, goals, states, thr = _batch_problems(E, g)
+    a = BatchedMPPI(T, K, dyns, objs, torch.tensor(sig), lam, seed=7)
+    b = BatchedMPPI(T, K, dyns, objs, torch.tensor(sig), lam, seed=7)
+    out = (torch.empty(E, T, 2), torch.empty(E, 1, T + 1, 3))
+    for it in range(3):
+        u1, o1 = a.forward(states)
+        u2, o2 = b.forward_host(states, out=out if it else None)
+        assert not u2.is_cuda and o2.shape == (E, 1, T + 1, 3)
+        assert torch.equal(u1.cpu(), u2) and torch.equal(o1.cpu(), o2), f"iteration {it}"
+        states = o2[:, 0, 1, :].clone()  # every environment moves on
+        states[:, 2] = ((states[:, 2] + np.pi) % (2 * np.pi)) - np.pi
+    with pytest.raises(ValueError):
+        b.forward_host(states, out=(torch.empty(E, T, 3), out[1]))
+
+
 # ------------------------------------------------------------------------------------------------ N1 / N3
 class _GM:
     def __init__(self, c, mean, std):
