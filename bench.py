@@ -411,8 +411,9 @@ def make_native(w: dict, dev, group, exchange: str, world: int, rank: int):
         return {"solver": solver, "step": lambda: solver.forward(st_dev), "e2e_step": e2e_step,
                 "h2d": e_l * 12, "d2h": e_l * 4 * (2 * t_h + 3 * (t_h + 1)),
                 "e2e_how": "BatchedMPPI.forward_host(states [E,3] in host memory, out=caller buffers): one staged H2D copy "
-                           "of the states, the iteration, ONE D2H copy of u* [E,T,2] + optimal states [E,1,T+1,3], one "
-                           "stream synchronisation, all inside the library; wall clock per step",
+                           "of the states, the iteration -- every environment's last CTA stores u* [T,2] and the optimal "
+                           "states [T+1,3] straight into pinned, device-mapped host memory -- and one stream "
+                           "synchronisation, all inside the library; wall clock per step",
                 "alg_bytes": e_l * algorithmic_bytes(w["k_total"], t_h, g), "units": e_l, "local_samples": w["k_total"],
                 "parallelism": f"environment-shard x{world}: {e_l} environments per GPU, one launch, no exchange"}
     if w["kind"] == "stoch":

@@ -969,15 +969,16 @@ int bnv_mppi_forward_host_batch(bnv_mppi* h, const float* states_host, float* u_
   BNV_CUDA(cudaSetDevice(h->cfg.device));
   BNV_DRAIN(h);
   BNV_USER_WORK(h, stream);
-  // One staged copy each way: [E][3] states up, [E][2T] + [E][3(T+1)] results down in a single transfer, one
-  // synchronisation.  (The kernels read the states by many CTAs per environment: they belong in HBM, not behind PCIe.)
+  // One staged copy of the [E][3] states up, one synchronisation.  (The kernels read the states by many CTAs per environment: they belong in HBM, not behind PCIe.)
   const size_t nE = static_cast<size_t>(h->E), T = static_cast<size_t>(h->P.T);
   const size_t n_st = 3 * nE, n_u = 2 * T * nE, n_o = 3 * (T + 1) * nE;
   std::memcpy(h->io_host, states_host, n_st * sizeof(float));
   BNV_CUDA(cudaMemcpyAsync(h->io_dev, h->io_host, n_st * sizeof(float), cudaMemcpyHostToDevice, s));
-  const int rc = launch_forward(h, h->io_dev, nullptr, nullptr, h->io_dev + n_st, h->io_dev + n_st + n_u, s);
+  if (!h->io_host_dev) BNV_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->io_host_dev), h->io_host, 0));
+  // results: stored by each environment's last CTA straight into the pinned, device-mapped staging buffer (zero-copy
+  // over PCIe, as in bnv_mppi_forward_host) -- no copy behind the kernel
+  const int rc = launch_forward(h, h->io_dev, nullptr, nullptr, h->io_host_dev + n_st, h->io_host_dev + n_st + n_u, s);
   if (rc != BNV_OK) return rc;
-  BNV_CUDA(cudaMemcpyAsync(h->io_host + n_st, h->io_dev + n_st, (n_u + n_o) * sizeof(float), cudaMemcpyDeviceToHost, s));
   BNV_CUDA(cudaStreamSynchronize(s));
   std::memcpy(u_out_host, h->io_host + n_st, n_u * sizeof(float));
   std::memcpy(opt_states_host, h->io_host + n_st + n_u, n_o * sizeof(float));

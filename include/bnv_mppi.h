@@ -149,8 +149,8 @@ int bnv_mppi_forward_follow(bnv_mppi* h, const float* noise_dev, float* u_out_de
  * sequence [T+1][3] of that same launch (usually complete by the time it is asked for).  The staging buffer is reused
  * by the next launch: collect the states BEFORE the next forward_host / forward_host_action call, or not at all. */
 /* Host-buffer form for a batched solver (num_envs = E >= 1): states_host [E][3] in, u_out_host [E][T][2] and
- * opt_states_host [E][T+1][3] out; one staged copy each way through the handle's pinned buffer and one stream
- * synchronisation (E x `forward(state)` + `.cpu()` of the reference's loop, mppi.py:130-219, in one call). */
+ * opt_states_host [E][T+1][3] out; the states go up in one staged copy, the results are stored by the kernel into the
+ * handle's pinned, device-mapped buffer, one stream synchronisation (E x `forward(state)` + `.cpu()` of the reference's loop, mppi.py:130-219, in one call). */
 int bnv_mppi_forward_host_batch(bnv_mppi* h, const float* states_host, float* u_out_host, float* opt_states_host,
                                 void* stream);
 int bnv_mppi_forward_host_action(bnv_mppi* h, const float state_host[3], float* u_out_host, void* stream);
