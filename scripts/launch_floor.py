@@ -51,6 +51,9 @@ for name, fl in (("torch fill_ (default carve-out)", lambda v: buf.fill_(v)),
                  ("no flush (back to back, per-step events)", lambda v: None)):
     mean, med = run(fl)
     print(f"{name:45s} mean {mean:6.2f} us  median {med:6.2f} us per forward()")
+tiny = torch.zeros(32, device="cuda")
+mean, med = run(lambda v: (buf.fill_(v), tiny.add_(1.0)))
+print(f"{'torch fill_ + a 32-element kernel behind it':45s} mean {mean:6.2f} us  median {med:6.2f} us per forward()")
 mean, med = run(read_flush)
 print(f"{'read-only flush (sum of 256 MiB: clean L2)':45s} mean {mean:6.2f} us  median {med:6.2f} us per forward()")
 full = s
