@@ -492,6 +492,8 @@ def run_native(args) -> None:
         """n calls, each preceded by an L2 flush, each bracketed by its own CUDA-event pair; returns milliseconds."""
         ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(n)]
         ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(n)]
+        for e in ev0 + ev1:  # torch creates the CUDA event at its first record(): do that here, not inside the first
+            e.record()       # timed step, where the host then falls behind the device and the launch gap is timed
         sync()
         for i in range(n):
             flush.fill_(i & 0xFF)
@@ -499,7 +501,10 @@ def run_native(args) -> None:
             fn()
             ev1[i].record()
         sync()
-        return sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))
+        per_step = [a.elapsed_time(b) for a, b in zip(ev0, ev1)]
+        if os.environ.get("BNV_BENCH_DUMP_STEPS"):  # debug aid: the per-step device times of this pass, microseconds
+            print("per-step us:", " ".join(f"{t * 1e3:.1f}" for t in per_step[:64]), file=sys.stderr)
+        return sum(per_step)
 
     # ---- parity of the sharded solver, on its very first step (driver-run evidence in every multi-GPU line)
     parity = None
